@@ -1,0 +1,130 @@
+/* ivln_map.h -- C ABI of the B200-native semantic-map update (libivlnmap.so).
+ *
+ * The reference (jacobkrantz/IVLN-CE) is pure Python and has no FFI on this
+ * path; these entry points are what a binding for
+ *   ivlnce_baselines/common/mapping_module/mapper.py:904-947  (MappingModule.forward)
+ * would call.  Plain C: PODs, raw device pointers, a CUDA stream handle, int
+ * status codes (0 = ok).  No torch types, no C++ exceptions, no allocation and
+ * no synchronisation behind the caller's back (except ivm_read_status, which is
+ * documented to synchronise the given stream).  A context is not re-entrant.
+ *
+ * Which reference code each call replaces:
+ *   ivm_step_iterative  UpdateWorldSemanticPointcloud.forward    mapper.py:825-848
+ *                       (+ GenerateSemanticPointCloud 398-425, KeepHighest 428-474,
+ *                        projector/core.py:117-230, PredictSemantics argmax 795-798)
+ *                       FilterPointCloudByRobotHeight.forward     mapper.py:884-901
+ *                       OccupancySemanticMapMemory.update         mapper.py:555-636
+ *   ivm_known_load      SemanticPointcloud.from_npz_file + GetGTWorldSemanticPointcloud
+ *                                                                 mapper.py:283-294, 862-881
+ *   ivm_step_known      same raster as above on the loaded scene clouds
+ *   ivm_export_world    MappingModule.get_world_semantic_pointcloud  mapper.py:946-947
+ */
+#ifndef IVLN_MAP_H
+#define IVLN_MAP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ivm_ctx ivm_ctx;
+typedef void *ivm_stream_t; /* a cudaStream_t */
+
+enum {
+    IVM_OK = 0,
+    IVM_E_INVALID = 1,      /* bad argument */
+    IVM_E_WORKSPACE = 2,    /* workspace too small / misaligned */
+    IVM_E_CUDA = 3,         /* a CUDA runtime call failed; see ivm_last_cuda_error */
+    IVM_E_STEP_OVERFLOW = 4 /* 2^24-1 steps reached; call ivm_rebase_stamps */
+};
+
+typedef struct ivm_config {
+    int32_t max_envs;     /* envs this context can hold (batch size upper bound) */
+    int32_t height, width; /* depth image size (CameraParameters.features_spatial_dimensions) */
+    int32_t map_rows, map_cols; /* MapDimensions.num_rows / num_cols */
+    float res;            /* (float) resolution_meters */
+    float half_res;       /* (float)(resolution_meters / 2): de-dup cell, mapper.py:464 */
+    float half_h;         /* (float)(height_meters / 2), mapper.py:112 */
+    float half_w;         /* (float)(width_meters / 2) */
+    int32_t store_rows, store_cols; /* world store extent per env, in half-cells */
+    int32_t mode;         /* 0 = iterative (depth ingested every step), 1 = known map */
+    int64_t known_capacity; /* known mode: max points per env */
+    int32_t tile_rows, tile_cols;   /* ego tile per raster CTA; 0 = choose */
+    int32_t reserved[4];
+} ivm_config;
+
+typedef struct ivm_status {
+    uint32_t error_flags; /* 1 = point outside world store, 2 = edge list overflow, 4 = known cloud overflow */
+    uint32_t pad;
+    uint64_t stats[8];    /* valid pixels, frame survivors, world records, rasterised records, e1, e2, merged, - */
+} ivm_status;
+
+/* Bytes of device workspace a context with this config needs.  The caller
+ * allocates it (e.g. a torch uint8 tensor), ZERO-FILLED, 256-byte aligned. */
+size_t ivm_workspace_bytes(const ivm_config *cfg);
+
+int ivm_create(const ivm_config *cfg, void *workspace_dev, size_t workspace_bytes, ivm_ctx **out);
+int ivm_destroy(ivm_ctx *ctx);
+
+/* Camera scale tables x_scale[width], y_scale[height] (projector/core.py:86-107),
+ * device pointers, copied into the workspace on `stream`. */
+int ivm_set_camera(ivm_ctx *ctx, const float *xs_dev, const float *ys_dev, ivm_stream_t stream);
+
+/* One map update for `num_envs` envs (iterative / episodic mode).  All pointers
+ * are device pointers:
+ *   depth   f32 [B,H,W]   normalised depth (Observations.depth_normalized)
+ *   labels  u8  [B,H,W]   GT labels, or NULL when `logits` is given
+ *   logits  f32 [B,num_classes,H,W]  class scores (NCHW) or NULL; argmax'ed in-kernel
+ *   labels_out u8 [B,H,W] receives the argmax labels (required with logits)
+ *   T12     f32 [B,12]    rows 0..2 of the camera->world matrix (core.py:6-37)
+ *   pose    f32 [B,3]     world_robot_pose
+ *   cs      f32 [B,2]     cos(-heading), sin(-heading) as f32 (mapper.py:38-48,264-266)
+ *   masks   u8  [B]       not_done_masks; 0 wipes that env first (mapper.py:320-326)
+ *   occ,sem u8  [B,R,C]   outputs (OccupancySemanticMapMemory.occupancy / .semantic)
+ * Envs with index >= num_envs are dropped (mapper.py:315-318). */
+int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const uint8_t *labels,
+                       const float *logits, int32_t num_classes, uint8_t *labels_out, const float *T12,
+                       const float *pose, const float *cs, const uint8_t *masks, uint8_t *occ, uint8_t *sem,
+                       ivm_stream_t stream);
+
+/* Known-map mode.  ivm_known_load replaces env `env`'s scene cloud
+ * (xyz f32 [n,3], sem u8 [n], device pointers; list order = npz order);
+ * origin_row/origin_col place the store window (absolute half-cell of store cell 0,0). */
+int ivm_known_load(ivm_ctx *ctx, int32_t env, int64_t n, const float *xyz, const uint8_t *sem, int32_t origin_row,
+                   int32_t origin_col, ivm_stream_t stream);
+int ivm_known_clear(ivm_ctx *ctx, int32_t env, ivm_stream_t stream);
+int ivm_step_known(ivm_ctx *ctx, int32_t num_envs, const float *pose, const float *cs, uint8_t *occ, uint8_t *sem,
+                   ivm_stream_t stream);
+
+/* Compacts the live world records into (env i64, xyz f32 x3, label u8, list key u64)
+ * arrays of capacity `cap`; *count_dev (u64, device) receives the number of records.
+ * Records come out grouped by env in (half-row, half-col) order; sorting by `key`
+ * (stable) yields the reference's list order. */
+int ivm_export_world(ivm_ctx *ctx, int32_t num_envs, int64_t cap, int64_t *env_out, float *xyz_out, uint8_t *label_out,
+                     uint64_t *key_out, uint64_t *count_dev, ivm_stream_t stream);
+
+/* Copies error flags and statistics of the last step to host memory; synchronises `stream`. */
+int ivm_read_status(ivm_ctx *ctx, ivm_status *host_out, ivm_stream_t stream);
+
+/* Per-kernel device timing: when enabled, CUDA events bracket each kernel of the next
+ * steps; ivm_stage_times returns the accumulated milliseconds per stage since the last
+ * reset (synchronises the events).  Stages: 0 prep, 1 ingest-scatter, 2 ingest-resolve,
+ * 3 edge fix-up, 4 raster. */
+int ivm_set_timing(ivm_ctx *ctx, int32_t enabled);
+int ivm_stage_times(ivm_ctx *ctx, float *ms_out5, int32_t *launches_out5, int32_t reset);
+
+/* Number of kernels launched by this context so far. */
+int64_t ivm_kernel_launches(const ivm_ctx *ctx);
+
+/* Rewrites all live stamps to 1 (call when IVM_E_STEP_OVERFLOW is returned). */
+int ivm_rebase_stamps(ivm_ctx *ctx, ivm_stream_t stream);
+
+const char *ivm_last_cuda_error(const ivm_ctx *ctx);
+const char *ivm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IVLN_MAP_H */

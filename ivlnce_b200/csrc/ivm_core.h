@@ -1,0 +1,598 @@
+// ivm_core.h -- data layout and per-thread logic of the B200 semantic-map update.
+//
+// Everything that decides a result bit lives here as host/device inline code:
+// the CUDA kernels (ivm_kernels.cu) call it from parallel drivers, and the
+// test-only serial emulator (tests/emu/emulator.cpp) calls the very same
+// functions from plain loops, so the algorithm can be checked against the
+// oracle on a machine without a GPU.
+//
+// What is computed (reference: ivlnce_baselines/common/mapping_module/mapper.py):
+//   * the reference keeps a world POINT LIST, de-duplicated to the highest point
+//     per half-resolution cell (mapper.py:428-474) and re-rasterised every step
+//     (mapper.py:555-617);
+//   * here the same state is a dense per-env grid of half-cells ("world store"),
+//     one 16-byte record per cell, and the per-step work is bounded to the cells
+//     a frame touches (ingest) and the cells under the ego window (raster);
+//   * the reference's de-dup key is `b*(Rmax*Cmax) + r*Cmax + c` with strides
+//     max instead of max+1 (mapper.py:468-469), so cells on the bounding-box
+//     edge of a batch collide and are merged.  Only edge cells can collide (see
+//     DESIGN.md), so the dense store reproduces this with a small "edge fix-up"
+//     program per de-dup stage (ivm_fixup_program below).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define IVM_HD __host__ __device__ __forceinline__
+#else
+#define IVM_HD inline
+#endif
+
+// ---------------------------------------------------------------------------
+// Exactly rounded fp32 primitives.  The device versions are intrinsics that the
+// compiler never contracts into FMAs; the host versions rely on
+// -ffp-contract=off.  (SURVEY.md Appendix A pins where the reference fuses.)
+#if defined(__CUDA_ARCH__)
+IVM_HD float ivm_mul(float a, float b) { return __fmul_rn(a, b); }
+IVM_HD float ivm_add(float a, float b) { return __fadd_rn(a, b); }
+IVM_HD float ivm_sub(float a, float b) { return __fsub_rn(a, b); }
+IVM_HD float ivm_div(float a, float b) { return __fdiv_rn(a, b); }
+IVM_HD float ivm_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+IVM_HD uint32_t ivm_f2u(float f) { return __float_as_uint(f); }
+#else
+IVM_HD float ivm_mul(float a, float b) { volatile float r = a * b; return r; }
+IVM_HD float ivm_add(float a, float b) { volatile float r = a + b; return r; }
+IVM_HD float ivm_sub(float a, float b) { volatile float r = a - b; return r; }
+IVM_HD float ivm_div(float a, float b) { volatile float r = a / b; return r; }
+IVM_HD float ivm_fma(float a, float b, float c) { return fmaf(a, b, c); }
+IVM_HD uint32_t ivm_f2u(float f) { union { float f; uint32_t u; } v; v.f = f; return v.u; }
+#endif
+
+// monotone float -> uint map (x < y  <=>  ord(x) < ord(y)); -0 and +0 map to the
+// same value because the reference compares heights with a float '>'.
+IVM_HD uint32_t ivm_orderable(float y) {
+    uint32_t u = ivm_f2u(ivm_add(y, 0.0f));
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+// ---------------------------------------------------------------------------
+// Device-resident layout.
+
+// One half-cell of an env's world store.  meta = (stamp << 8) | label; stamp is
+// the 24-bit step counter of the call that wrote the record, 0 = never written /
+// deleted.  A record is live iff stamp != 0 && stamp >= env.reset_stamp.
+struct IvmRecord {
+    float x, y, z;
+    uint32_t meta;
+};
+
+struct IvmEnv {                   // 64 bytes
+    int32_t origin_r, origin_c;   // absolute half-cell index of store cell (0,0)
+    uint32_t reset_stamp;         // records older than this are dead (O(1) reset)
+    int32_t count;                // live records
+    int32_t rmin, rmax, cmin, cmax; // exact bbox of live records (absolute), if count>0
+    int32_t dirty;                // bbox must be rebuilt from rowcount/colcount
+    int32_t known_n;              // known-map mode: points in this env's CSR store
+    int32_t pad[6];
+};
+
+// A de-dup winner sitting on a bounding-box edge cell, waiting for the fix-up.
+struct IvmEdge {
+    float x, y, z;
+    uint32_t label;
+    int32_t b, r, c;              // env, absolute half-row / half-col
+    uint32_t slot;                // hash slot of its collision class
+    unsigned long long xorder;    // position in the reference's point list (tie-break)
+    unsigned long long addr;      // record index in the store (stage 2)
+};
+
+#define IVM_STAT_VALID 0   // pixels surviving the depth+height filters (this step)
+#define IVM_STAT_LOCAL 1   // survivors of the frame de-dup
+#define IVM_STAT_WORLD 2   // live world records after the step
+#define IVM_STAT_IN 3      // world records rasterised into the ego window
+#define IVM_STAT_E1 4      // stage-1 edge candidates
+#define IVM_STAT_E2 5      // stage-2 edge candidates
+#define IVM_STAT_MERGED 6  // records deleted by edge collisions (cumulative)
+#define IVM_NSTATS 8
+
+#define IVM_ERR_STORE_OVERFLOW 1u  // a point fell outside an env's world store window
+#define IVM_ERR_EDGE_OVERFLOW 2u   // edge list / hash capacity exceeded
+#define IVM_ERR_KNOWN_OVERFLOW 4u  // known-map cloud larger than capacity / index range
+
+struct IvmGlobal {
+    int32_t loc[4];               // frame (stage-1) bbox over all envs: rmin,rmax,cmin,cmax
+    int32_t glob[4];              // world (stage-2) bbox over all envs
+    int32_t prev_valid, prev_rmin, prev_cmin, pad0;
+    long long prev_R, prev_C;     // stage-2 bbox extents of the previous step (list order)
+    uint32_t n_e1, n_e2;
+    uint32_t err;
+    uint32_t any_dirty;
+    uint32_t n_seg;
+    uint32_t pad1[3];
+    unsigned long long stats[IVM_NSTATS];
+};
+
+struct IvmParams {
+    // geometry
+    int32_t H, W, HW;
+    int32_t R, C;                 // ego map rows / cols
+    float res, half_res, half_h, half_w;
+    int32_t SR, SC;               // world store rows / cols (half-cells) per env
+    int32_t maxB;
+    int32_t tile_r, tile_c;       // ego tile of one raster CTA
+    // persistent device memory
+    IvmRecord *store;             // [maxB][SR][SC]
+    unsigned long long *cand;     // [maxB][SR][SC] frame de-dup scratch, all zero between steps
+    IvmEnv *env;                  // [maxB]
+    int32_t *rowcount, *colcount; // [maxB][SR], [maxB][SC] live records per store row / col
+    IvmGlobal *g;
+    IvmEdge *e1, *e2;             // edge lists, capacity ecap each
+    uint32_t ecap;
+    int32_t *segs;                // [4*maxB][4] edge-line segments to scan: b, is_col, line, pad
+    unsigned long long *hkeys;    // open-addressing hash of collision classes
+    uint32_t *hbest;              // best height per class
+    unsigned long long *hxord;    // first list position among the best
+    uint32_t hmask;
+    const float *xs, *ys;         // camera scale tables [W], [H]
+    // known-map mode (CSR store)
+    IvmRecord *kpts;              // [maxB][kcap] points sorted by half-cell
+    uint32_t *koff;               // [maxB][SR*SC+1]
+    long long kcap;
+    // per step
+    int32_t B;
+    uint32_t step;
+    const float *depth;           // [B][H][W] normalised
+    const uint8_t *labels;        // [B][H][W]
+    const float *T12;             // [B][12] rows 0..2 of camera->world
+    const float *pose;            // [B][3]
+    const float *cs;              // [B][2] cos(-heading), sin(-heading)
+    const uint8_t *masks;         // [B] 0 = reset this env before ingesting
+    uint8_t *occ, *sem;           // [B][R][C]
+};
+
+#define IVM_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+IVM_HD bool ivm_live(uint32_t meta, uint32_t reset_stamp) {
+    return meta != 0u && (meta >> 8) >= reset_stamp;
+}
+
+// ---------------------------------------------------------------------------
+// Atomics policy.  Device: hardware atomics.  Host emulator: plain serial ops.
+#if defined(__CUDA_ARCH__)
+struct IvmAtomics {
+    static __device__ __forceinline__ void add_i(int32_t *p, int32_t v) { atomicAdd(p, v); }
+    static __device__ __forceinline__ uint32_t add_u(uint32_t *p, uint32_t v) { return atomicAdd(p, v); }
+    static __device__ __forceinline__ void add_ull(unsigned long long *p, unsigned long long v) { atomicAdd(p, v); }
+    static __device__ __forceinline__ void min_i(int32_t *p, int32_t v) { atomicMin(p, v); }
+    static __device__ __forceinline__ void max_i(int32_t *p, int32_t v) { atomicMax(p, v); }
+    static __device__ __forceinline__ void max_u(uint32_t *p, uint32_t v) { atomicMax(p, v); }
+    static __device__ __forceinline__ void or_u(uint32_t *p, uint32_t v) { atomicOr(p, v); }
+    static __device__ __forceinline__ void max_ull(unsigned long long *p, unsigned long long v) { atomicMax(p, v); }
+    static __device__ __forceinline__ void min_ull(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
+    static __device__ __forceinline__ unsigned long long cas_ull(unsigned long long *p, unsigned long long c,
+                                                                  unsigned long long v) { return atomicCAS(p, c, v); }
+    static __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+#else
+struct IvmAtomics {
+    static void add_i(int32_t *p, int32_t v) { *p += v; }
+    static uint32_t add_u(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
+    static void add_ull(unsigned long long *p, unsigned long long v) { *p += v; }
+    static void min_i(int32_t *p, int32_t v) { if (v < *p) *p = v; }
+    static void max_i(int32_t *p, int32_t v) { if (v > *p) *p = v; }
+    static void max_u(uint32_t *p, uint32_t v) { if (v > *p) *p = v; }
+    static void or_u(uint32_t *p, uint32_t v) { *p |= v; }
+    static void max_ull(unsigned long long *p, unsigned long long v) { if (v > *p) *p = v; }
+    static void min_ull(unsigned long long *p, unsigned long long v) { if (v < *p) *p = v; }
+    static unsigned long long cas_ull(unsigned long long *p, unsigned long long c, unsigned long long v) {
+        unsigned long long o = *p; if (o == c) *p = v; return o;
+    }
+    static void sync() {}
+};
+#endif
+
+// ---------------------------------------------------------------------------
+// Unprojection of one depth pixel: reference mapper.py:381-384 (x10),
+// projector/core.py:117-149 (x = z*xs, y = z*ys), core.py:171 (T * [x y z 1],
+// evaluated as mul + 3 fma per row, the order the reference's BLAS uses),
+// filters mapper.py:416-424 (strict), de-dup cell mapper.py:464.
+struct IvmPoint {
+    float x, y, z;
+    int32_t r, c;  // absolute half-row (from z) and half-col (from x)
+};
+
+// returns 0 = filtered out, 1 = valid point, 2 = valid but its cell index is not representable
+// (non-finite / absurd coordinates; the caller flags IVM_ERR_STORE_OVERFLOW)
+IVM_HD int ivm_unproject(float d, float xs_u, float ys_v, const float *T, float h, float half_res, IvmPoint &p) {
+    if (!(d > 0.01f && d < 0.99f)) return 0;
+    const float z = ivm_mul(d, 10.0f);
+    const float xc = ivm_mul(z, xs_u);
+    const float yc = ivm_mul(z, ys_v);
+    float w[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        float acc = ivm_mul(T[4 * r + 0], xc);
+        acc = ivm_fma(T[4 * r + 1], yc, acc);
+        acc = ivm_fma(T[4 * r + 2], z, acc);
+        acc = ivm_fma(T[4 * r + 3], 1.0f, acc);
+        w[r] = acc;
+    }
+    if (!(w[1] > ivm_sub(h, 1.0f) && w[1] < ivm_add(h, 0.5f))) return 0;
+    const float rf = rintf(ivm_div(w[2], half_res));
+    const float cf = rintf(ivm_div(w[0], half_res));
+    if (!(fabsf(rf) < 1.0e9f && fabsf(cf) < 1.0e9f)) return 2;
+    p.x = w[0]; p.y = w[1]; p.z = w[2];
+    p.r = (int32_t)rf; p.c = (int32_t)cf;
+    return 1;
+}
+
+// frame de-dup candidate: highest point wins, lowest pixel index on ties
+// (first-index rule of scatter_max; pixels are listed in (v,u) order, mapper.py:32-35).
+IVM_HD unsigned long long ivm_cand_key(float y, uint32_t pix) {
+    return ((unsigned long long)ivm_orderable(y) << 32) | (unsigned long long)(0xFFFFFFFFu - pix);
+}
+
+IVM_HD bool ivm_store_index(const IvmParams &P, const IvmEnv &e, int b, int32_t r, int32_t c, size_t &idx) {
+    const int32_t rr = r - e.origin_r, cc = c - e.origin_c;
+    if (rr < 0 || rr >= P.SR || cc < 0 || cc >= P.SC) return false;
+    idx = ((size_t)b * P.SR + (size_t)rr) * P.SC + (size_t)cc;
+    return true;
+}
+
+// the reference's flattened de-dup key (mapper.py:468-469) for a bbox with
+// minima (rmin,cmin) and extents Rx = rows.max(), Cx = cols.max()
+IVM_HD unsigned long long ivm_list_key(int b, int32_t r, int32_t c, int32_t rmin, int32_t cmin, long long Rx, long long Cx) {
+    return (unsigned long long)((long long)b * (Rx * Cx) + (long long)(r - rmin) * Cx + (long long)(c - cmin));
+}
+
+// Insert the frame/edge survivor into the world store ("world.concatenate(local)" +
+// second keep_highest for a cell that does not collide): the older record wins ties
+// because world points precede local points in the list (mapper.py:226-230, 299-308).
+template <class A>
+IVM_HD void ivm_merge_into_world(const IvmParams &P, int b, size_t idx, int32_t r, int32_t c, float x, float y, float z,
+                                 uint32_t label) {
+    IvmEnv *e = &P.env[b];
+    IvmRecord old = P.store[idx];
+    const bool live = ivm_live(old.meta, e->reset_stamp);
+    if (live && !(y > old.y)) return;
+    IvmRecord rec;
+    rec.x = x; rec.y = y; rec.z = z; rec.meta = (P.step << 8) | (label & 0xFFu);
+    P.store[idx] = rec;
+    if (!live) {
+        A::add_i(&P.rowcount[(size_t)b * P.SR + (r - e->origin_r)], 1);
+        A::add_i(&P.colcount[(size_t)b * P.SC + (c - e->origin_c)], 1);
+        A::add_i(&e->count, 1);
+        A::min_i(&e->rmin, r); A::max_i(&e->rmax, r);
+        A::min_i(&e->cmin, c); A::max_i(&e->cmax, c);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K0: per-env preparation.  Envs whose mask is 0 (episode/tour finished,
+// mapper.py:320-326) or whose index is >= B (paused, mapper.py:315-318) are
+// wiped in O(1) by advancing reset_stamp; the store window is re-centred on the
+// pose of a reset env.  Called by every thread of the env's CTA.
+template <class A>
+IVM_HD void ivm_prep_env(const IvmParams &P, int b, int tid, int nthreads, bool empty) {
+    // `empty`: the env holds no record (first use, or back from a pause); its window may be
+    // re-centred freely.  Must be evaluated by the caller BEFORE any thread runs this function.
+    const bool dropped = b >= P.B;
+    const bool reset = dropped || empty || P.masks[b] == 0;
+    if (!reset) return;
+    for (int i = tid; i < P.SR; i += nthreads) P.rowcount[(size_t)b * P.SR + i] = 0;
+    for (int i = tid; i < P.SC; i += nthreads) P.colcount[(size_t)b * P.SC + i] = 0;
+    if (tid == 0) {
+        IvmEnv *e = &P.env[b];
+        e->reset_stamp = P.step;
+        e->count = 0;
+        e->rmin = INT32_MAX; e->rmax = INT32_MIN; e->cmin = INT32_MAX; e->cmax = INT32_MIN;
+        e->dirty = 0;
+        if (!dropped) {
+            const float pr = rintf(ivm_div(P.pose[3 * b + 2], P.half_res));
+            const float pc = rintf(ivm_div(P.pose[3 * b + 0], P.half_res));
+            e->origin_r = (fabsf(pr) < 1.0e9f ? (int32_t)pr : 0) - P.SR / 2;
+            e->origin_c = (fabsf(pc) < 1.0e9f ? (int32_t)pc : 0) - P.SC / 2;
+        }
+    }
+}
+
+IVM_HD void ivm_prep_global(const IvmParams &P) {
+    IvmGlobal *g = P.g;
+    g->loc[0] = INT32_MAX; g->loc[1] = INT32_MIN; g->loc[2] = INT32_MAX; g->loc[3] = INT32_MIN;
+    g->n_e1 = 0; g->n_e2 = 0; g->n_seg = 0; g->any_dirty = 0;
+    g->stats[IVM_STAT_VALID] = 0; g->stats[IVM_STAT_LOCAL] = 0; g->stats[IVM_STAT_IN] = 0;
+    g->stats[IVM_STAT_E1] = 0; g->stats[IVM_STAT_E2] = 0;
+}
+
+// ---------------------------------------------------------------------------
+// K1b per-pixel resolve.  `p` is the pixel's point (already unprojected and
+// valid).  The pixel that owns the candidate slot of its cell is the frame
+// de-dup winner of that cell.  Winners on the frame bbox edge go to the edge
+// list (they may collide with other cells); all others are
+// merged into the world store directly.  Returns 1 if the pixel was a
+// non-edge winner (for the LOCAL statistic).
+template <class A>
+IVM_HD int ivm_resolve_pixel(const IvmParams &P, int b, uint32_t pix, const IvmPoint &p, uint32_t label) {
+    const IvmEnv &e = P.env[b];
+    size_t idx;
+    if (!ivm_store_index(P, e, b, p.r, p.c, idx)) return 0;  // overflow was flagged in K1a
+    const unsigned long long cand = P.cand[idx];
+    if ((uint32_t)(cand & 0xFFFFFFFFull) != 0xFFFFFFFFu - pix || (uint32_t)(cand >> 32) != ivm_orderable(p.y)) return 0;
+    P.cand[idx] = 0ull;  // leave the scratch plane clean for the next step
+    const IvmGlobal *g = P.g;
+    const bool edge = p.r == g->loc[0] || p.r == g->loc[1] || p.c == g->loc[2] || p.c == g->loc[3];
+    if (edge) {
+        const uint32_t k = A::add_u(&P.g->n_e1, 1u);
+        if (k >= P.ecap) { A::or_u(&P.g->err, IVM_ERR_EDGE_OVERFLOW); return 0; }
+        IvmEdge ed;
+        ed.x = p.x; ed.y = p.y; ed.z = p.z; ed.label = label;
+        ed.b = b; ed.r = p.r; ed.c = p.c; ed.slot = 0;
+        ed.xorder = (unsigned long long)b * (unsigned long long)P.HW + pix;  // position in the frame point list
+        ed.addr = idx;
+        P.e1[k] = ed;
+        return 0;
+    }
+    ivm_merge_into_world<A>(P, b, idx, p.r, p.c, p.x, p.y, p.z, label);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------
+// Collision-class resolution shared by both de-dup stages: every edge entry is
+// hashed by the reference's flattened key; per class the highest point wins,
+// ties go to the entry that comes first in the reference's list (xorder).
+// Runs inside ONE thread block (tid / nthreads), phases separated by A::sync().
+IVM_HD uint32_t ivm_mix(unsigned long long k) {
+    k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33; k *= 0xc4ceb9fe1a85ec53ull; k ^= k >> 33;
+    return (uint32_t)k;
+}
+
+// on return E[i].slot = 0xFFFFFFFF for losers, anything else for winners
+template <class A>
+IVM_HD void ivm_resolve_classes(const IvmParams &P, IvmEdge *E, uint32_t n, int32_t rmin, int32_t cmin, long long Rx,
+                                long long Cx, int tid, int nthreads) {
+    for (uint32_t i = tid; i < n; i += nthreads) {
+        const unsigned long long k = ivm_list_key(E[i].b, E[i].r, E[i].c, rmin, cmin, Rx, Cx);
+        uint32_t s = ivm_mix(k) & P.hmask;
+        for (;;) {
+            const unsigned long long prev = A::cas_ull(&P.hkeys[s], IVM_EMPTY_KEY, k);
+            if (prev == IVM_EMPTY_KEY || prev == k) break;
+            s = (s + 1) & P.hmask;
+        }
+        E[i].slot = s;
+        A::max_u(&P.hbest[s], ivm_orderable(E[i].y));
+    }
+    A::sync();
+    for (uint32_t i = tid; i < n; i += nthreads)
+        if (ivm_orderable(E[i].y) == P.hbest[E[i].slot]) A::min_ull(&P.hxord[E[i].slot], E[i].xorder);
+    A::sync();
+    for (uint32_t i = tid; i < n; i += nthreads) {
+        const uint32_t s = E[i].slot;
+        const bool win = ivm_orderable(E[i].y) == P.hbest[s] && E[i].xorder == P.hxord[s];
+        E[i].addr = win ? E[i].addr : (E[i].addr | 0x8000000000000000ull);  // tag losers, keep slot for cleanup
+    }
+    A::sync();
+    for (uint32_t i = tid; i < n; i += nthreads) {
+        const uint32_t s = E[i].slot;
+        P.hkeys[s] = IVM_EMPTY_KEY; P.hbest[s] = 0u; P.hxord[s] = IVM_EMPTY_KEY;
+        const bool lose = (E[i].addr >> 63) != 0ull;
+        E[i].addr &= 0x7FFFFFFFFFFFFFFFull;
+        E[i].slot = lose ? 0xFFFFFFFFu : 0u;
+    }
+    A::sync();
+}
+
+// scan one store cell of an edge line; live records join the stage-2 edge list
+template <class A>
+IVM_HD void ivm_scan_edge_cell(const IvmParams &P, int b, int32_t r, int32_t c) {
+    const IvmEnv &e = P.env[b];
+    size_t idx;
+    if (!ivm_store_index(P, e, b, r, c, idx)) return;
+    const IvmRecord rec = P.store[idx];
+    if (!ivm_live(rec.meta, e.reset_stamp)) return;
+    const uint32_t k = A::add_u(&P.g->n_e2, 1u);
+    if (k >= P.ecap) { A::or_u(&P.g->err, IVM_ERR_EDGE_OVERFLOW); return; }
+    const IvmGlobal *g = P.g;
+    const bool fresh = (rec.meta >> 8) == P.step;
+    IvmEdge ed;
+    ed.x = rec.x; ed.y = rec.y; ed.z = rec.z; ed.label = rec.meta & 0xFFu;
+    ed.b = b; ed.r = r; ed.c = c; ed.slot = 0; ed.addr = idx;
+    // position in the concatenated list [world(t-1) ; frame survivors]: old records keep
+    // the order of the previous sort (previous stage-2 key), fresh ones follow in
+    // frame-key order (mapper.py:226-230, 471-474).
+    if (fresh)
+        ed.xorder = (1ull << 62) | ivm_list_key(b, r, c, g->loc[0], g->loc[2], (long long)g->loc[1] - g->loc[0],
+                                                (long long)g->loc[3] - g->loc[2]);
+    else
+        ed.xorder = ivm_list_key(b, r, c, g->prev_rmin, g->prev_cmin, g->prev_R, g->prev_C);
+    P.e2[k] = ed;
+}
+
+// F: the edge fix-up of both de-dup stages + bbox bookkeeping, one thread block.
+template <class A>
+IVM_HD void ivm_fixup_program(const IvmParams &P, int tid, int nthreads) {
+    IvmGlobal *g = P.g;
+    // ---- stage 1: collisions on the frame bbox edge (mapper.py:840-842)
+    const uint32_t n1 = g->n_e1 < P.ecap ? g->n_e1 : P.ecap;
+    if (n1 > 0) {
+        ivm_resolve_classes<A>(P, P.e1, n1, g->loc[0], g->loc[2], (long long)g->loc[1] - g->loc[0],
+                               (long long)g->loc[3] - g->loc[2], tid, nthreads);
+        for (uint32_t i = tid; i < n1; i += nthreads) {
+            const IvmEdge ed = P.e1[i];
+            if (ed.slot == 0xFFFFFFFFu) continue;
+            A::add_ull(&g->stats[IVM_STAT_LOCAL], 1ull);
+            ivm_merge_into_world<A>(P, ed.b, (size_t)ed.addr, ed.r, ed.c, ed.x, ed.y, ed.z, ed.label);
+        }
+        if (tid == 0) g->stats[IVM_STAT_E1] = n1;
+    }
+    A::sync();
+    // ---- stage-2 bbox over all live records of all envs (mapper.py:461-469 on world+local)
+    if (tid == 0) { g->glob[0] = INT32_MAX; g->glob[1] = INT32_MIN; g->glob[2] = INT32_MAX; g->glob[3] = INT32_MIN; }
+    A::sync();
+    for (int b = tid; b < P.B; b += nthreads) {
+        const IvmEnv &e = P.env[b];
+        if (e.count > 0) {
+            A::min_i(&g->glob[0], e.rmin); A::max_i(&g->glob[1], e.rmax);
+            A::min_i(&g->glob[2], e.cmin); A::max_i(&g->glob[3], e.cmax);
+        }
+    }
+    A::sync();
+    const int32_t grmin = g->glob[0], grmax = g->glob[1], gcmin = g->glob[2], gcmax = g->glob[3];
+    if (grmin > grmax) {  // nothing alive: the reference skips keep_highest on an empty cloud
+        if (tid == 0) { g->prev_valid = 0; g->stats[IVM_STAT_WORLD] = 0; }
+        return;
+    }
+    // ---- which edge lines hold records?  an env has cells on a global edge line only
+    //      if its own bbox touches that line.
+    for (int b = tid; b < P.B; b += nthreads) {
+        const IvmEnv &e = P.env[b];
+        if (e.count <= 0) continue;
+        const bool t0 = e.rmin == grmin, t1 = e.rmax == grmax && grmax != grmin;
+        const bool t2 = e.cmin == gcmin, t3 = e.cmax == gcmax && gcmax != gcmin;
+        const int lines[4] = {grmin, grmax, gcmin, gcmax};
+        const bool touch[4] = {t0, t1, t2, t3};
+        for (int s = 0; s < 4; ++s)
+            if (touch[s]) {
+                const uint32_t k = A::add_u(&g->n_seg, 1u);
+                P.segs[4 * k + 0] = b; P.segs[4 * k + 1] = s >> 1; P.segs[4 * k + 2] = lines[s]; P.segs[4 * k + 3] = 0;
+            }
+    }
+    A::sync();
+    const uint32_t nseg = g->n_seg;
+    for (uint32_t q = 0; q < nseg; ++q) {
+        const int b = P.segs[4 * q + 0], is_col = P.segs[4 * q + 1], line = P.segs[4 * q + 2];
+        const IvmEnv &e = P.env[b];
+        if (!is_col) {
+            for (int32_t c = e.cmin + tid; c <= e.cmax; c += nthreads) ivm_scan_edge_cell<A>(P, b, line, c);
+        } else {
+            for (int32_t r = e.rmin + tid; r <= e.rmax; r += nthreads)
+                if (r != grmin && r != grmax) ivm_scan_edge_cell<A>(P, b, r, line);  // corners belong to the row scans
+        }
+    }
+    A::sync();
+    // ---- stage 2: collisions on the world bbox edge (mapper.py:844-847)
+    const uint32_t n2 = g->n_e2 < P.ecap ? g->n_e2 : P.ecap;
+    if (n2 > 1) {
+        ivm_resolve_classes<A>(P, P.e2, n2, grmin, gcmin, (long long)grmax - grmin, (long long)gcmax - gcmin, tid, nthreads);
+        for (uint32_t i = tid; i < n2; i += nthreads) {
+            const IvmEdge ed = P.e2[i];
+            if (ed.slot != 0xFFFFFFFFu) continue;
+            IvmEnv *e = &P.env[ed.b];
+            P.store[(size_t)ed.addr].meta = 0u;  // merged away for good
+            A::add_i(&P.rowcount[(size_t)ed.b * P.SR + (ed.r - e->origin_r)], -1);
+            A::add_i(&P.colcount[(size_t)ed.b * P.SC + (ed.c - e->origin_c)], -1);
+            A::add_i(&e->count, -1);
+            e->dirty = 1;
+            g->any_dirty = 1u;
+            A::add_ull(&g->stats[IVM_STAT_MERGED], 1ull);
+        }
+    }
+    A::sync();
+    if (tid == 0) g->stats[IVM_STAT_E2] = n2;
+    // ---- rebuild the bbox of envs that lost records
+    if (g->any_dirty) {
+        for (int b = tid; b < P.B; b += nthreads) {
+            IvmEnv *e = &P.env[b];
+            if (e->dirty) { e->rmin = INT32_MAX; e->rmax = INT32_MIN; e->cmin = INT32_MAX; e->cmax = INT32_MIN; }
+        }
+        A::sync();
+        const long long per_env = (long long)P.SR + P.SC;
+        for (long long i = tid; i < per_env * P.B; i += nthreads) {
+            const int b = (int)(i / per_env);
+            IvmEnv *e = &P.env[b];
+            if (!e->dirty) continue;
+            const int j = (int)(i - (long long)b * per_env);
+            if (j < P.SR) {
+                if (P.rowcount[(size_t)b * P.SR + j] > 0) { A::min_i(&e->rmin, e->origin_r + j); A::max_i(&e->rmax, e->origin_r + j); }
+            } else {
+                const int jc = j - P.SR;
+                if (P.colcount[(size_t)b * P.SC + jc] > 0) { A::min_i(&e->cmin, e->origin_c + jc); A::max_i(&e->cmax, e->origin_c + jc); }
+            }
+        }
+        A::sync();
+        for (int b = tid; b < P.B; b += nthreads) P.env[b].dirty = 0;
+    }
+    A::sync();
+    // ---- remember this step's list order (the next step's tie-breaks need it)
+    if (tid == 0) {
+        g->prev_valid = 1; g->prev_rmin = grmin; g->prev_cmin = gcmin;
+        g->prev_R = (long long)grmax - grmin; g->prev_C = (long long)gcmax - gcmin;
+        unsigned long long total = 0;
+        for (int b = 0; b < P.B; ++b) total += (unsigned long long)(P.env[b].count > 0 ? P.env[b].count : 0);
+        g->stats[IVM_STAT_WORLD] = total;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2 geometry: which store columns of half-row `rr` can hold records that land
+// in ego tile rows [r0,r1) x cols [c0,c1)?  Conservative (never drops a record
+// that maps into the tile); exactness comes from evaluating the reference
+// arithmetic per record afterwards.
+struct IvmTileGeom {
+    float px, pz, c, s;
+    float xe_lo, xe_hi, ze_lo, ze_hi;  // ego-frame metric bounds of the tile, with slack
+    float hr;
+    int32_t row_lo, row_hi;            // absolute half-rows to visit
+};
+
+IVM_HD void ivm_tile_geom(const IvmParams &P, float px, float pz, float c, float s, int r0, int r1, int c0, int c1,
+                          IvmTileGeom &G) {
+    const float slack = 2.0e-3f;  // metres; covers fp32 rounding of the reference transform (<1e-5 m at 100 m)
+    G.px = px; G.pz = pz; G.c = c; G.s = s; G.hr = P.half_res;
+    G.xe_lo = ((float)c0 - 0.5f) * P.res - P.half_w - slack;
+    G.xe_hi = ((float)c1 - 0.5f) * P.res - P.half_w + slack;
+    G.ze_lo = ((float)r0 - 0.5f) * P.res - P.half_h - slack;
+    G.ze_hi = ((float)r1 - 0.5f) * P.res - P.half_h + slack;
+    // world z of the four corners: z1 = s*xe + c*ze
+    float zmin = 3.0e38f, zmax = -3.0e38f;
+    const float xe[2] = {G.xe_lo, G.xe_hi}, ze[2] = {G.ze_lo, G.ze_hi};
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j) {
+            const float z1 = s * xe[i] + c * ze[j] + pz;
+            zmin = fminf(zmin, z1); zmax = fmaxf(zmax, z1);
+        }
+    const float q0 = zmin / G.hr - 0.55f, q1 = zmax / G.hr + 0.55f;
+    G.row_lo = (fabsf(q0) < 1.0e9f) ? (int32_t)floorf(q0) : 0;
+    G.row_hi = (fabsf(q1) < 1.0e9f) ? (int32_t)ceilf(q1) : -1;
+}
+
+// one slab  L <= a*x1 + b*z1 <= U  with z1 in [za, zb]: tighten [xlo, xhi]
+IVM_HD void ivm_slab(float a, float b, float L, float U, float za, float zb, float &xlo, float &xhi) {
+    const float bz0 = b * za, bz1 = b * zb;
+    const float bzmin = fminf(bz0, bz1), bzmax = fmaxf(bz0, bz1);
+    if (fabsf(a) < 1.0e-6f) {
+        if (bzmax < L || bzmin > U) { xlo = 1.0f; xhi = -1.0f; }  // empty
+        return;
+    }
+    float lo = (L - bzmax) / a, hi = (U - bzmin) / a;
+    if (a < 0.0f) { lo = (U - bzmin) / a; hi = (L - bzmax) / a; }
+    xlo = fmaxf(xlo, lo); xhi = fminf(xhi, hi);
+}
+
+IVM_HD void ivm_row_span(const IvmTileGeom &G, int32_t rr, int32_t &clo, int32_t &chi) {
+    // records of half-row rr have z/hr within rr +- 0.5 (rint of an fp32 quotient)
+    const float za = ((float)rr - 0.55f) * G.hr - G.pz, zb = ((float)rr + 0.55f) * G.hr - G.pz;
+    float xlo = -1.0e30f, xhi = 1.0e30f;
+    ivm_slab(G.c, G.s, G.xe_lo, G.xe_hi, za, zb, xlo, xhi);    // xe =  c*x1 + s*z1
+    ivm_slab(-G.s, G.c, G.ze_lo, G.ze_hi, za, zb, xlo, xhi);   // ze = -s*x1 + c*z1
+    if (!(xlo <= xhi)) { clo = 0; chi = -1; return; }
+    const float q0 = (xlo + G.px) / G.hr - 0.55f, q1 = (xhi + G.px) / G.hr + 0.55f;
+    clo = (q0 > -1.0e9f) ? (int32_t)floorf(q0) : -1000000000;
+    chi = (q1 < 1.0e9f) ? (int32_t)ceilf(q1) : 1000000000;
+}
+
+// One world record against the ego map: band filter (mapper.py:884-901), translate
+// + rotate (mapper.py:255-267: x+(-px); unfused c*x+s*z), cell index
+// (mapper.py:101-114).  Returns true and (row, col) if the record is inside the map.
+IVM_HD bool ivm_ego_cell(const IvmParams &P, float x, float y, float z, float px, float h, float pz, float c, float s,
+                         int32_t &row, int32_t &col) {
+    if (!(y > ivm_sub(h, 1.25f) && y < ivm_add(h, 0.75f))) return false;
+    const float x1 = ivm_add(x, -px);
+    const float z1 = ivm_add(z, -pz);
+    const float xe = ivm_add(ivm_mul(c, x1), ivm_mul(s, z1));
+    const float ze = ivm_add(ivm_mul(-s, x1), ivm_mul(c, z1));
+    const float rf = rintf(ivm_div(ivm_add(ze, P.half_h), P.res));
+    const float cf = rintf(ivm_div(ivm_add(xe, P.half_w), P.res));
+    if (!(rf >= 0.0f && rf < (float)P.R && cf >= 0.0f && cf < (float)P.C)) return false;
+    row = (int32_t)rf; col = (int32_t)cf;
+    return true;
+}

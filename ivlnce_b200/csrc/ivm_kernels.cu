@@ -1,0 +1,815 @@
+// ivm_kernels.cu -- sm_100a kernels + C ABI of the semantic-map update.
+//
+// Step pipeline (iterative mode), all on the caller's stream:
+//   K0 k_prep            per-env O(1) reset / store re-centring            (mapper.py:310-326)
+//   K1 k_ingest_scatter  [argmax ->] unproject -> transform -> filter -> half-cell ->
+//                        64-bit atomicMax into the frame-candidate plane   (mapper.py:381-474, core.py:117-230)
+//   K2 k_ingest_resolve  the owning pixel of each candidate merges into the world store
+//   K3 k_fixup           edge-collision fix-up of both de-dup stages        (mapper.py:461-474 quirk)
+//   K4 k_raster          band filter -> ego transform -> cell -> smem max/or -> u8 maps (mapper.py:555-617, 884-901)
+// No point cloud is ever written to HBM; the only per-pixel state is the 8-byte
+// candidate word of the touched half-cells.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ivln_map.h"
+#include "ivm_core.h"
+
+#define IVM_THREADS 256
+#define IVM_NSTAGES 5
+#define IVM_EVPOOL 64
+
+// ------------------------------------------------------------------ helpers
+__device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
+__device__ __forceinline__ int warp_max(int v) { return __reduce_max_sync(0xffffffffu, v); }
+__device__ __forceinline__ unsigned warp_sum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
+
+__device__ __forceinline__ float4 ld_stream4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+
+// ------------------------------------------------------------------ K0
+__global__ void __launch_bounds__(IVM_THREADS) k_prep(IvmParams P, int first_call) {
+    const int b = blockIdx.x;
+    if (b == 0 && threadIdx.x == 0) ivm_prep_global(P);
+    if (first_call) {  // one-time init of the class hash (workspace arrives zero-filled)
+        const size_t n = (size_t)P.hmask + 1;
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+            P.hkeys[i] = IVM_EMPTY_KEY; P.hxord[i] = IVM_EMPTY_KEY; P.hbest[i] = 0u;
+        }
+    }
+    if (b < P.maxB) {
+        // an env that holds nothing can be re-centred freely (first use, or back from a pause)
+        __shared__ int s_empty;
+        if (threadIdx.x == 0) s_empty = (b < P.B) && (P.env[b].count <= 0);
+        __syncthreads();
+        ivm_prep_env<IvmAtomics>(P, b, threadIdx.x, blockDim.x, s_empty != 0);
+    }
+}
+
+// ------------------------------------------------------------------ K1: scatter
+// One thread = VEC consecutive pixels of one image row (128-bit loads for VEC=4).
+template <bool PRED, int VEC>
+__global__ void __launch_bounds__(IVM_THREADS)
+k_ingest_scatter(IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out) {
+    const int b = blockIdx.y;
+    const int pix0 = (blockIdx.x * IVM_THREADS + threadIdx.x) * VEC;
+    __shared__ float sT[12];
+    __shared__ int sbb[4];
+    __shared__ unsigned s_valid;
+    if (threadIdx.x < 12) sT[threadIdx.x] = P.T12[12 * b + threadIdx.x];
+    if (threadIdx.x == 0) { sbb[0] = INT32_MAX; sbb[1] = INT32_MIN; sbb[2] = INT32_MAX; sbb[3] = INT32_MIN; s_valid = 0; }
+    __syncthreads();
+    int rmin = INT32_MAX, rmax = INT32_MIN, cmin = INT32_MAX, cmax = INT32_MIN;
+    unsigned nvalid = 0;
+    if (pix0 < P.HW) {
+        const size_t base = (size_t)b * P.HW + pix0;
+        float d[VEC];
+        if (VEC == 4) {
+            const float4 v = ld_stream4(P.depth + base);
+            d[0] = v.x; d[1 % VEC] = v.y; d[2 % VEC] = v.z; d[3 % VEC] = v.w;
+        } else {
+            d[0] = P.depth[base];
+        }
+        if (PRED) {
+            // PredictSemantics tail (mapper.py:795-798): argmax over class planes, first max wins,
+            // NaN counts as maximal (torch.argmax).  Planes are streamed with evict-first loads.
+            const float *lp = logits + (size_t)b * ncls * P.HW + pix0;
+            float best[VEC];
+            int arg[VEC];
+            if (VEC == 4) {
+                const float4 v = ld_stream4(lp);
+                best[0] = v.x; best[1 % VEC] = v.y; best[2 % VEC] = v.z; best[3 % VEC] = v.w;
+            } else {
+                best[0] = __ldcs(lp);
+            }
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) arg[j] = 0;
+            int k = 1;
+            constexpr int U = 8;
+            for (; k + U <= ncls; k += U) {
+                float vals[U][VEC];
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    if (VEC == 4) {
+                        const float4 v = ld_stream4(lp + (size_t)(k + q) * P.HW);
+                        vals[q][0] = v.x; vals[q][1 % VEC] = v.y; vals[q][2 % VEC] = v.z; vals[q][3 % VEC] = v.w;
+                    } else {
+                        vals[q][0] = __ldcs(lp + (size_t)(k + q) * P.HW);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < U; ++q)
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const float v = vals[q][j];
+                        if ((v > best[j]) || (v != v && best[j] == best[j])) { best[j] = v; arg[j] = k + q; }
+                    }
+            }
+            for (; k < ncls; ++k) {
+                float vals[VEC];
+                if (VEC == 4) {
+                    const float4 v = ld_stream4(lp + (size_t)k * P.HW);
+                    vals[0] = v.x; vals[1 % VEC] = v.y; vals[2 % VEC] = v.z; vals[3 % VEC] = v.w;
+                } else {
+                    vals[0] = __ldcs(lp + (size_t)k * P.HW);
+                }
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) {
+                    const float v = vals[j];
+                    if ((v > best[j]) || (v != v && best[j] == best[j])) { best[j] = v; arg[j] = k; }
+                }
+            }
+            if (VEC == 4) {
+                uchar4 o;
+                o.x = (uint8_t)arg[0]; o.y = (uint8_t)arg[1 % VEC]; o.z = (uint8_t)arg[2 % VEC]; o.w = (uint8_t)arg[3 % VEC];
+                *reinterpret_cast<uchar4 *>(labels_out + base) = o;
+            } else {
+                labels_out[base] = (uint8_t)arg[0];
+            }
+        }
+        const IvmEnv &e = P.env[b];
+        const float h = P.pose[3 * b + 1];
+        const int v = pix0 / P.W, u0 = pix0 - v * P.W;
+        const float ysv = P.ys[v];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            IvmPoint p;
+            const int ok = ivm_unproject(d[j], P.xs[u0 + j], ysv, sT, h, P.half_res, p);
+            if (ok == 0) continue;
+            size_t idx;
+            if (ok == 2 || !ivm_store_index(P, e, b, p.r, p.c, idx)) { atomicOr(&P.g->err, IVM_ERR_STORE_OVERFLOW); continue; }
+            atomicMax(&P.cand[idx], ivm_cand_key(p.y, (uint32_t)(pix0 + j)));
+            rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
+            ++nvalid;
+        }
+    }
+    // frame bbox over ALL envs (the reference subtracts batch-global minima, mapper.py:465)
+    const unsigned wv = warp_sum(nvalid);
+    if (wv) {  // warp-uniform
+        rmin = warp_min(rmin); rmax = warp_max(rmax); cmin = warp_min(cmin); cmax = warp_max(cmax);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&sbb[0], rmin); atomicMax(&sbb[1], rmax); atomicMin(&sbb[2], cmin); atomicMax(&sbb[3], cmax);
+            atomicAdd(&s_valid, wv);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_valid) {
+        atomicMin(&P.g->loc[0], sbb[0]); atomicMax(&P.g->loc[1], sbb[1]);
+        atomicMin(&P.g->loc[2], sbb[2]); atomicMax(&P.g->loc[3], sbb[3]);
+        atomicAdd(&P.g->stats[IVM_STAT_VALID], (unsigned long long)s_valid);
+    }
+}
+
+// ------------------------------------------------------------------ K2: resolve
+template <int VEC>
+__global__ void __launch_bounds__(IVM_THREADS) k_ingest_resolve(IvmParams P) {
+    const int b = blockIdx.y;
+    const int pix0 = (blockIdx.x * IVM_THREADS + threadIdx.x) * VEC;
+    __shared__ float sT[12];
+    __shared__ unsigned s_local;
+    if (threadIdx.x < 12) sT[threadIdx.x] = P.T12[12 * b + threadIdx.x];
+    if (threadIdx.x == 0) s_local = 0;
+    __syncthreads();
+    unsigned nlocal = 0;
+    if (pix0 < P.HW) {
+        const size_t base = (size_t)b * P.HW + pix0;
+        float d[VEC];
+        uint8_t lab[VEC];
+        if (VEC == 4) {
+            const float4 v = *reinterpret_cast<const float4 *>(P.depth + base);
+            d[0] = v.x; d[1 % VEC] = v.y; d[2 % VEC] = v.z; d[3 % VEC] = v.w;
+            const uchar4 l = *reinterpret_cast<const uchar4 *>(P.labels + base);
+            lab[0] = l.x; lab[1 % VEC] = l.y; lab[2 % VEC] = l.z; lab[3 % VEC] = l.w;
+        } else {
+            d[0] = P.depth[base];
+            lab[0] = P.labels[base];
+        }
+        const float h = P.pose[3 * b + 1];
+        const int v = pix0 / P.W, u0 = pix0 - v * P.W;
+        const float ysv = P.ys[v];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+            IvmPoint p;
+            if (ivm_unproject(d[j], P.xs[u0 + j], ysv, sT, h, P.half_res, p) != 1) continue;
+            nlocal += (unsigned)ivm_resolve_pixel<IvmAtomics>(P, b, (uint32_t)(pix0 + j), p, lab[j]);
+        }
+    }
+    const unsigned wl = warp_sum(nlocal);
+    if (wl && (threadIdx.x & 31) == 0) atomicAdd(&s_local, wl);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_local) atomicAdd(&P.g->stats[IVM_STAT_LOCAL], (unsigned long long)s_local);
+}
+
+// ------------------------------------------------------------------ K3: fix-up
+__global__ void __launch_bounds__(1024) k_fixup(IvmParams P) {
+    ivm_fixup_program<IvmAtomics>(P, threadIdx.x, blockDim.x);
+}
+
+// ------------------------------------------------------------------ K4: raster
+// One CTA = one ego tile of one env.  Warps walk the half-rows of the world store
+// under the (rotated) tile; lanes read 16-byte records along the row span.
+template <bool KNOWN>
+__global__ void __launch_bounds__(IVM_THREADS) k_raster(IvmParams P) {
+    extern __shared__ uint32_t skey[];
+    const int tr = P.tile_r, tc = P.tile_c;
+    uint8_t *socc = reinterpret_cast<uint8_t *>(skey + tr * tc);
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * tr, c0 = blockIdx.x * tc;
+    const int r1 = min(r0 + tr, P.R), c1 = min(c0 + tc, P.C);
+    for (int i = threadIdx.x; i < tr * tc; i += blockDim.x) { skey[i] = 0u; socc[i] = 0; }
+    __syncthreads();
+    const IvmEnv e = P.env[b];
+    const float px = P.pose[3 * b + 0], h = P.pose[3 * b + 1], pz = P.pose[3 * b + 2];
+    const float c = P.cs[2 * b + 0], s = P.cs[2 * b + 1];
+    unsigned n_in = 0;
+    if (e.count > 0) {
+        IvmTileGeom G;
+        ivm_tile_geom(P, px, pz, c, s, r0, r1, c0, c1, G);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+        const int row_lo = max(G.row_lo, KNOWN ? e.origin_r : e.rmin);
+        const int row_hi = min(G.row_hi, KNOWN ? e.origin_r + P.SR - 1 : e.rmax);
+        for (int rr = row_lo + warp; rr <= row_hi; rr += nwarps) {
+            int clo, chi;
+            ivm_row_span(G, rr, clo, chi);
+            clo = max(clo, KNOWN ? e.origin_c : e.cmin);
+            chi = min(chi, KNOWN ? e.origin_c + P.SC - 1 : e.cmax);
+            if (clo > chi) continue;
+            const size_t rowbase = ((size_t)b * P.SR + (size_t)(rr - e.origin_r)) * P.SC;
+            if (!KNOWN) {
+                for (int cc = clo + lane; cc <= chi; cc += 32) {
+                    const int ccr = cc - e.origin_c;
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(P.store + rowbase + ccr));
+                    if (!ivm_live(raw.w, e.reset_stamp)) continue;
+                    int row, col;
+                    if (!ivm_ego_cell(P, __uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), px, h, pz,
+                                      c, s, row, col))
+                        continue;
+                    if (row < r0 || row >= r1 || col < c0 || col >= c1) continue;
+                    ++n_in;
+                    const int t = (row - r0) * tc + (col - c0);
+                    socc[t] = 1;  // OccupancyStatus.OCCUPIED
+                    const uint32_t label = raw.w & 0xFFu;
+                    // last point in list order wins (mapper.py:569-571); list order within an env is
+                    // (half-row, half-col) lexicographic, labels 0 are excluded (mapper.py:611)
+                    if (label) atomicMax(&skey[t], ((uint32_t)((rr - e.origin_r) * P.SC + ccr) << 8) | label);
+                }
+            } else {
+                const uint32_t *off = P.koff + (size_t)b * ((size_t)P.SR * P.SC + 1) + (size_t)(rr - e.origin_r) * P.SC;
+                const uint32_t p0 = off[clo - e.origin_c], p1 = off[chi - e.origin_c + 1];
+                const IvmRecord *pts = P.kpts + (size_t)b * P.kcap;
+                for (uint32_t q = p0 + lane; q < p1; q += 32) {
+                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(pts + q));
+                    int row, col;
+                    if (!ivm_ego_cell(P, __uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), px, h, pz,
+                                      c, s, row, col))
+                        continue;
+                    if (row < r0 || row >= r1 || col < c0 || col >= c1) continue;
+                    ++n_in;
+                    const int t = (row - r0) * tc + (col - c0);
+                    socc[t] = 1;
+                    // raw.w = (npz index << 8) | label: later points overwrite earlier ones
+                    if (raw.w & 0xFFu) atomicMax(&skey[t], raw.w);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int wr = r1 - r0, wc = c1 - c0;
+    for (int i = threadIdx.x; i < wr * wc; i += blockDim.x) {
+        const int rr = i / wc, cc = i - rr * wc;
+        const size_t o = ((size_t)b * P.R + (size_t)(r0 + rr)) * P.C + (size_t)(c0 + cc);
+        P.occ[o] = socc[rr * tc + cc];
+        P.sem[o] = (uint8_t)(skey[rr * tc + cc] & 0xFFu);
+    }
+    const unsigned wn = warp_sum(n_in);
+    if (wn && (threadIdx.x & 31) == 0) atomicAdd(&P.g->stats[IVM_STAT_IN], (unsigned long long)wn);
+}
+
+// ------------------------------------------------------------------ known-map store build
+__global__ void k_known_reset_env(IvmParams P, int b, long long n, int origin_r, int origin_c) {
+    IvmEnv *e = &P.env[b];
+    e->origin_r = origin_r; e->origin_c = origin_c;
+    e->count = (int32_t)n; e->known_n = (int32_t)n;
+    e->rmin = origin_r; e->rmax = origin_r + P.SR - 1; e->cmin = origin_c; e->cmax = origin_c + P.SC - 1;
+    e->reset_stamp = 0; e->dirty = 0;
+}
+
+__device__ __forceinline__ bool known_cell(const IvmParams &P, const float *xyz, long long i, int origin_r, int origin_c,
+                                           uint32_t &cell) {
+    const float rf = rintf(ivm_div(xyz[3 * i + 2], P.half_res));
+    const float cf = rintf(ivm_div(xyz[3 * i + 0], P.half_res));
+    if (!(fabsf(rf) < 1.0e9f && fabsf(cf) < 1.0e9f)) return false;
+    const int rr = (int)rf - origin_r, cc = (int)cf - origin_c;
+    if (rr < 0 || rr >= P.SR || cc < 0 || cc >= P.SC) return false;
+    cell = (uint32_t)rr * (uint32_t)P.SC + (uint32_t)cc;
+    return true;
+}
+
+__global__ void k_known_hist(IvmParams P, int b, long long n, const float *xyz, int origin_r, int origin_c, uint32_t *hist) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t cell;
+        if (known_cell(P, xyz, i, origin_r, origin_c, cell)) atomicAdd(&hist[cell + 1], 1u);
+        else atomicOr(&P.g->err, IVM_ERR_KNOWN_OVERFLOW);
+    }
+}
+
+// inclusive scan of `n` u32 in chunks of 4096 per block (3 phases)
+__global__ void __launch_bounds__(1024) k_scan_local(uint32_t *data, size_t n, uint32_t *totals) {
+    __shared__ uint32_t sw[32];
+    const size_t base = (size_t)blockIdx.x * 4096 + (size_t)threadIdx.x * 4;
+    uint32_t v[4];
+    for (int j = 0; j < 4; ++j) v[j] = (base + j < n) ? data[base + j] : 0u;
+    v[1] += v[0]; v[2] += v[1]; v[3] += v[2];
+    uint32_t x = v[3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) sw[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = sw[lane];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+        sw[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t prefix = (x - v[3]) + (warp ? sw[warp - 1] : 0u);
+    for (int j = 0; j < 4; ++j) if (base + j < n) data[base + j] = v[j] + prefix;
+    if (threadIdx.x == 1023) totals[blockIdx.x] = x + (warp ? sw[warp - 1] : 0u);
+}
+__global__ void __launch_bounds__(1024) k_scan_totals(uint32_t *totals, int nblocks) {
+    __shared__ uint32_t sw[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int start = 0; start < nblocks; start += 1024) {
+        const int i = start + threadIdx.x;
+        uint32_t x = (i < nblocks) ? totals[i] : 0u;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) sw[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = sw[lane];
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+            sw[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t incl = x + (warp ? sw[warp - 1] : 0u) + carry;
+        if (i < nblocks) totals[i] = incl;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = incl;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(1024) k_scan_add(uint32_t *data, size_t n, const uint32_t *totals) {
+    if (blockIdx.x == 0) return;
+    const uint32_t add = totals[blockIdx.x - 1];
+    const size_t base = (size_t)blockIdx.x * 4096 + (size_t)threadIdx.x * 4;
+    for (int j = 0; j < 4; ++j) if (base + j < n) data[base + j] += add;
+}
+
+__global__ void k_known_scatter(IvmParams P, int b, long long n, const float *xyz, const uint8_t *sem, int origin_r,
+                                int origin_c, const uint32_t *off, uint32_t *fill) {
+    IvmRecord *pts = P.kpts + (size_t)b * P.kcap;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t cell;
+        if (!known_cell(P, xyz, i, origin_r, origin_c, cell)) continue;
+        const uint32_t pos = off[cell] + atomicAdd(&fill[cell], 1u);
+        IvmRecord r;
+        r.x = xyz[3 * i]; r.y = xyz[3 * i + 1]; r.z = xyz[3 * i + 2];
+        r.meta = ((uint32_t)i << 8) | (uint32_t)sem[i];
+        pts[pos] = r;
+    }
+}
+
+// ------------------------------------------------------------------ export / maintenance
+// one warp per (env, store row): count, then ordered write
+__global__ void k_export_count(IvmParams P, uint32_t *rowlive) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (gw >= P.B * P.SR) return;
+    const int b = gw / P.SR, rr = gw - b * P.SR;
+    const IvmEnv e = P.env[b];
+    unsigned n = 0;
+    if (e.count > 0 && P.rowcount[(size_t)b * P.SR + rr] > 0) {
+        const IvmRecord *row = P.store + ((size_t)b * P.SR + rr) * P.SC;
+        for (int cc = lane; cc < P.SC; cc += 32) n += ivm_live(row[cc].meta, e.reset_stamp) ? 1u : 0u;
+    }
+    n = warp_sum(n);
+    if (lane == 0) rowlive[gw] = n;
+}
+__global__ void k_export_write(IvmParams P, const uint32_t *rowoff_incl, long long cap, long long *env_out, float *xyz_out,
+                               uint8_t *label_out, unsigned long long *key_out, unsigned long long *count_dev) {
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int total_rows = P.B * P.SR;
+    if (gw == 0 && lane == 0) *count_dev = total_rows ? rowoff_incl[total_rows - 1] : 0ull;
+    if (gw >= total_rows) return;
+    const int b = gw / P.SR, rr = gw - b * P.SR;
+    const IvmEnv e = P.env[b];
+    if (e.count <= 0 || P.rowcount[(size_t)b * P.SR + rr] <= 0) return;
+    long long pos = gw ? rowoff_incl[gw - 1] : 0;
+    const IvmRecord *row = P.store + ((size_t)b * P.SR + rr) * P.SC;
+    const IvmGlobal *g = P.g;
+    for (int c0 = 0; c0 < P.SC; c0 += 32) {
+        const int cc = c0 + lane;
+        IvmRecord rec;
+        rec.meta = 0;
+        if (cc < P.SC) rec = row[cc];
+        const bool live = cc < P.SC && ivm_live(rec.meta, e.reset_stamp);
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (live) {
+            const long long o = pos + __popc(m & ((1u << lane) - 1u));
+            if (o < cap) {
+                env_out[o] = b;
+                xyz_out[3 * o] = rec.x; xyz_out[3 * o + 1] = rec.y; xyz_out[3 * o + 2] = rec.z;
+                label_out[o] = (uint8_t)(rec.meta & 0xFFu);
+                key_out[o] = ivm_list_key(b, e.origin_r + rr, e.origin_c + cc, g->prev_rmin, g->prev_cmin, g->prev_R, g->prev_C);
+            }
+        }
+        pos += __popc(m);
+    }
+}
+
+__global__ void k_rebase(IvmParams P) {
+    const size_t n = (size_t)P.maxB * P.SR * P.SC;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const int b = (int)(i / ((size_t)P.SR * P.SC));
+        const uint32_t meta = P.store[i].meta;
+        if (meta == 0u) continue;
+        P.store[i].meta = ivm_live(meta, P.env[b].reset_stamp) ? ((1u << 8) | (meta & 0xFFu)) : 0u;
+    }
+}
+__global__ void k_rebase_env(IvmParams P) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < P.maxB) P.env[b].reset_stamp = 1u;
+}
+
+// ------------------------------------------------------------------ host side
+struct ivm_ctx {
+    ivm_config cfg;
+    IvmParams P;       // persistent part filled at create
+    uint32_t step;     // 24-bit stamp of the last call
+    int hi_water;      // envs [0, hi_water) may hold records
+    int first_call;
+    int64_t launches;
+    // known-mode scratch
+    uint32_t *kfill, *ktotals;
+    size_t kcells;
+    // export scratch
+    uint32_t *rowlive, *rowtotals;
+    // timing
+    int timing;
+    cudaEvent_t ev[IVM_EVPOOL][IVM_NSTAGES][2];
+    int ev_used;
+    int ev_created;
+    float stage_ms[IVM_NSTAGES];
+    int stage_launches[IVM_NSTAGES];
+    char err[256];
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Carver {
+    char *base; size_t off;
+    template <class T> T *take(size_t count) {
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += align_up(count * sizeof(T));
+        return p;
+    }
+};
+
+static uint32_t edge_capacity(const ivm_config *c) {
+    long long cap = (long long)c->max_envs * 8192;
+    if (cap > (1ll << 20)) cap = 1ll << 20;
+    return (uint32_t)cap;
+}
+static uint32_t hash_size(uint32_t ecap) { uint32_t h = 1024; while (h < 2 * ecap) h <<= 1; return h; }
+
+static void carve(const ivm_config *c, void *ws, IvmParams *P, ivm_ctx *ctx, size_t *total) {
+    Carver cv{(char *)ws, 0};
+    const size_t B = c->max_envs, SR = c->store_rows, SC = c->store_cols;
+    const uint32_t ecap = edge_capacity(c), hs = hash_size(ecap);
+    IvmParams q;
+    memset(&q, 0, sizeof(q));
+    q.g = cv.take<IvmGlobal>(1);
+    q.env = cv.take<IvmEnv>(B);
+    float *xs = cv.take<float>(c->width > 0 ? c->width : 1);
+    float *ys = cv.take<float>(c->height > 0 ? c->height : 1);
+    q.xs = xs; q.ys = ys;
+    q.rowcount = cv.take<int32_t>(B * SR);
+    q.colcount = cv.take<int32_t>(B * SC);
+    q.segs = cv.take<int32_t>(16 * B);
+    q.e1 = cv.take<IvmEdge>(ecap);
+    q.e2 = cv.take<IvmEdge>(ecap);
+    q.ecap = ecap;
+    q.hkeys = cv.take<unsigned long long>(hs);
+    q.hxord = cv.take<unsigned long long>(hs);
+    q.hbest = cv.take<uint32_t>(hs);
+    q.hmask = hs - 1;
+    uint32_t *rowlive = cv.take<uint32_t>(B * SR);
+    uint32_t *rowtotals = cv.take<uint32_t>((B * SR + 4095) / 4096 + 1);
+    uint32_t *kfill = nullptr, *ktotals = nullptr;
+    if (c->mode == 0) {
+        q.store = cv.take<IvmRecord>(B * SR * SC);
+        q.cand = cv.take<unsigned long long>(B * SR * SC);
+    } else {
+        q.kcap = c->known_capacity;
+        q.kpts = cv.take<IvmRecord>(B * (size_t)c->known_capacity);
+        q.koff = cv.take<uint32_t>(B * (SR * SC + 1));
+        kfill = cv.take<uint32_t>(SR * SC);
+        ktotals = cv.take<uint32_t>((SR * SC + 1 + 4095) / 4096 + 1);
+    }
+    if (P) *P = q;
+    if (ctx) { ctx->kfill = kfill; ctx->ktotals = ktotals; ctx->kcells = SR * SC; ctx->rowlive = rowlive; ctx->rowtotals = rowtotals; }
+    if (total) *total = cv.off;
+}
+
+static int valid_config(const ivm_config *c) {
+    if (!c) return 0;
+    if (c->max_envs < 1 || c->map_rows < 1 || c->map_cols < 1) return 0;
+    if (c->store_rows < 8 || c->store_cols < 8) return 0;
+    if ((long long)c->store_rows * c->store_cols > (1ll << 24)) return 0;  // raster key = cell index << 8 | label
+    if (!(c->res > 0.f) || !(c->half_res > 0.f)) return 0;
+    if (c->mode == 0 && (c->height < 1 || c->width < 1)) return 0;
+    if (c->mode == 1 && (c->known_capacity < 1 || c->known_capacity >= (1ll << 24))) return 0;
+    if (c->mode != 0 && c->mode != 1) return 0;
+    return 1;
+}
+
+extern "C" {
+
+const char *ivm_version(void) { return "ivlnmap 0.1 (sm_100a)"; }
+
+size_t ivm_workspace_bytes(const ivm_config *cfg) {
+    if (!valid_config(cfg)) return 0;
+    size_t total = 0;
+    carve(cfg, nullptr, nullptr, nullptr, &total);
+    return total;
+}
+
+int ivm_create(const ivm_config *cfg, void *workspace_dev, size_t workspace_bytes, ivm_ctx **out) {
+    if (!out || !valid_config(cfg) || !workspace_dev) return IVM_E_INVALID;
+    if (((uintptr_t)workspace_dev & 255) != 0) return IVM_E_WORKSPACE;
+    size_t need = 0;
+    carve(cfg, nullptr, nullptr, nullptr, &need);
+    if (workspace_bytes < need) return IVM_E_WORKSPACE;
+    ivm_ctx *ctx = new ivm_ctx();
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->cfg = *cfg;
+    carve(cfg, workspace_dev, &ctx->P, ctx, nullptr);
+    IvmParams &P = ctx->P;
+    P.H = cfg->height; P.W = cfg->width; P.HW = cfg->height * cfg->width;
+    P.R = cfg->map_rows; P.C = cfg->map_cols;
+    P.res = cfg->res; P.half_res = cfg->half_res; P.half_h = cfg->half_h; P.half_w = cfg->half_w;
+    P.SR = cfg->store_rows; P.SC = cfg->store_cols; P.maxB = cfg->max_envs;
+    int tr = cfg->tile_rows, tc = cfg->tile_cols;
+    if (tr <= 0 || tc <= 0) { tr = 32; tc = 32; }
+    if (tr > P.R) tr = P.R;
+    if (tc > P.C) tc = P.C;
+    P.tile_r = tr; P.tile_c = tc;
+    ctx->first_call = 1;
+    *out = ctx;
+    return IVM_OK;
+}
+
+int ivm_destroy(ivm_ctx *ctx) {
+    if (!ctx) return IVM_E_INVALID;
+    if (ctx->ev_created)
+        for (int i = 0; i < IVM_EVPOOL; ++i)
+            for (int s = 0; s < IVM_NSTAGES; ++s) { cudaEventDestroy(ctx->ev[i][s][0]); cudaEventDestroy(ctx->ev[i][s][1]); }
+    delete ctx;
+    return IVM_OK;
+}
+
+static int cuda_fail(ivm_ctx *ctx, cudaError_t e, const char *where) {
+    snprintf(ctx->err, sizeof(ctx->err), "%s: %s", where, cudaGetErrorString(e));
+    return IVM_E_CUDA;
+}
+#define IVM_CHECK_LAUNCH(where)                                   \
+    do {                                                          \
+        cudaError_t _e = cudaGetLastError();                      \
+        if (_e != cudaSuccess) return cuda_fail(ctx, _e, where);  \
+    } while (0)
+
+const char *ivm_last_cuda_error(const ivm_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+int64_t ivm_kernel_launches(const ivm_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int ivm_set_camera(ivm_ctx *ctx, const float *xs_dev, const float *ys_dev, ivm_stream_t stream) {
+    if (!ctx || !xs_dev || !ys_dev) return IVM_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync((void *)ctx->P.xs, xs_dev, sizeof(float) * ctx->P.W, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "set_camera xs");
+    e = cudaMemcpyAsync((void *)ctx->P.ys, ys_dev, sizeof(float) * ctx->P.H, cudaMemcpyDeviceToDevice, st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "set_camera ys");
+    return IVM_OK;
+}
+
+// ---- timing helpers
+static void timing_flush(ivm_ctx *ctx) {
+    for (int i = 0; i < ctx->ev_used; ++i)
+        for (int s = 0; s < IVM_NSTAGES; ++s) {
+            cudaEventSynchronize(ctx->ev[i][s][1]);
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->ev[i][s][0], ctx->ev[i][s][1]) == cudaSuccess) {
+                ctx->stage_ms[s] += ms;
+                ctx->stage_launches[s] += 1;
+            }
+        }
+    ctx->ev_used = 0;
+    cudaGetLastError();
+}
+static int timing_slot(ivm_ctx *ctx) {
+    if (!ctx->timing) return -1;
+    if (!ctx->ev_created) {
+        for (int i = 0; i < IVM_EVPOOL; ++i)
+            for (int s = 0; s < IVM_NSTAGES; ++s) { cudaEventCreate(&ctx->ev[i][s][0]); cudaEventCreate(&ctx->ev[i][s][1]); }
+        ctx->ev_created = 1;
+    }
+    if (ctx->ev_used == IVM_EVPOOL) timing_flush(ctx);
+    return ctx->ev_used++;
+}
+#define T_BEGIN(stage) do { if (slot >= 0) cudaEventRecord(ctx->ev[slot][stage][0], st); } while (0)
+#define T_END(stage) do { if (slot >= 0) cudaEventRecord(ctx->ev[slot][stage][1], st); } while (0)
+
+int ivm_set_timing(ivm_ctx *ctx, int32_t enabled) {
+    if (!ctx) return IVM_E_INVALID;
+    if (!enabled && ctx->timing) timing_flush(ctx);
+    ctx->timing = enabled ? 1 : 0;
+    return IVM_OK;
+}
+int ivm_stage_times(ivm_ctx *ctx, float *ms_out5, int32_t *launches_out5, int32_t reset) {
+    if (!ctx) return IVM_E_INVALID;
+    timing_flush(ctx);
+    for (int s = 0; s < IVM_NSTAGES; ++s) {
+        if (ms_out5) ms_out5[s] = ctx->stage_ms[s];
+        if (launches_out5) launches_out5[s] = ctx->stage_launches[s];
+        if (reset) { ctx->stage_ms[s] = 0.f; ctx->stage_launches[s] = 0; }
+    }
+    return IVM_OK;
+}
+
+static int next_step(ivm_ctx *ctx) {
+    if (ctx->step >= 0xFFFFFFu) return IVM_E_STEP_OVERFLOW;
+    ctx->step += 1;
+    return IVM_OK;
+}
+
+static void launch_raster(ivm_ctx *ctx, const IvmParams &P, cudaStream_t st, bool known) {
+    dim3 grid((P.C + P.tile_c - 1) / P.tile_c, (P.R + P.tile_r - 1) / P.tile_r, P.B);
+    const size_t smem = (size_t)P.tile_r * P.tile_c * 5 + 16;
+    if (known) k_raster<true><<<grid, IVM_THREADS, smem, st>>>(P);
+    else k_raster<false><<<grid, IVM_THREADS, smem, st>>>(P);
+    ctx->launches += 1;
+}
+
+int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const uint8_t *labels, const float *logits,
+                       int32_t num_classes, uint8_t *labels_out, const float *T12, const float *pose, const float *cs,
+                       const uint8_t *masks, uint8_t *occ, uint8_t *sem, ivm_stream_t stream) {
+    if (!ctx || ctx->cfg.mode != 0) return IVM_E_INVALID;
+    if (num_envs < 1 || num_envs > ctx->cfg.max_envs) return IVM_E_INVALID;
+    if (!depth || !T12 || !pose || !cs || !masks || !occ || !sem) return IVM_E_INVALID;
+    if (!labels && !(logits && labels_out && num_classes >= 1 && num_classes <= 256)) return IVM_E_INVALID;
+    int rc = next_step(ctx);
+    if (rc != IVM_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    IvmParams P = ctx->P;
+    P.B = num_envs; P.step = ctx->step;
+    P.depth = depth; P.labels = labels ? labels : labels_out; P.T12 = T12; P.pose = pose; P.cs = cs; P.masks = masks;
+    P.occ = occ; P.sem = sem;
+    const int slot = timing_slot(ctx);
+
+    const int nprep = num_envs > ctx->hi_water ? num_envs : ctx->hi_water;
+    T_BEGIN(0);
+    k_prep<<<nprep, IVM_THREADS, 0, st>>>(P, ctx->first_call);
+    T_END(0);
+    IVM_CHECK_LAUNCH("k_prep");
+    ctx->first_call = 0;
+    ctx->hi_water = num_envs;
+
+    const bool vec4 = (P.W % 4 == 0) && (((uintptr_t)depth & 15) == 0) && (((uintptr_t)P.labels & 3) == 0) &&
+                      (!logits || ((uintptr_t)logits & 15) == 0);
+    const int vec = vec4 ? 4 : 1;
+    dim3 grid((P.HW + IVM_THREADS * vec - 1) / (IVM_THREADS * vec), num_envs);
+    T_BEGIN(1);
+    if (logits) {
+        if (vec4) k_ingest_scatter<true, 4><<<grid, IVM_THREADS, 0, st>>>(P, logits, num_classes, labels_out);
+        else k_ingest_scatter<true, 1><<<grid, IVM_THREADS, 0, st>>>(P, logits, num_classes, labels_out);
+    } else {
+        if (vec4) k_ingest_scatter<false, 4><<<grid, IVM_THREADS, 0, st>>>(P, nullptr, 0, nullptr);
+        else k_ingest_scatter<false, 1><<<grid, IVM_THREADS, 0, st>>>(P, nullptr, 0, nullptr);
+    }
+    T_END(1);
+    IVM_CHECK_LAUNCH("k_ingest_scatter");
+    T_BEGIN(2);
+    if (vec4) k_ingest_resolve<4><<<grid, IVM_THREADS, 0, st>>>(P);
+    else k_ingest_resolve<1><<<grid, IVM_THREADS, 0, st>>>(P);
+    T_END(2);
+    IVM_CHECK_LAUNCH("k_ingest_resolve");
+    T_BEGIN(3);
+    k_fixup<<<1, 1024, 0, st>>>(P);
+    T_END(3);
+    IVM_CHECK_LAUNCH("k_fixup");
+    T_BEGIN(4);
+    launch_raster(ctx, P, st, false);
+    T_END(4);
+    IVM_CHECK_LAUNCH("k_raster");
+    ctx->launches += 4;
+    return IVM_OK;
+}
+
+int ivm_known_clear(ivm_ctx *ctx, int32_t env, ivm_stream_t stream) {
+    if (!ctx || ctx->cfg.mode != 1 || env < 0 || env >= ctx->cfg.max_envs) return IVM_E_INVALID;
+    k_known_reset_env<<<1, 1, 0, (cudaStream_t)stream>>>(ctx->P, env, 0, 0, 0);
+    ctx->launches += 1;
+    IVM_CHECK_LAUNCH("k_known_reset_env");
+    return IVM_OK;
+}
+
+int ivm_known_load(ivm_ctx *ctx, int32_t env, int64_t n, const float *xyz, const uint8_t *sem, int32_t origin_row,
+                   int32_t origin_col, ivm_stream_t stream) {
+    if (!ctx || ctx->cfg.mode != 1 || env < 0 || env >= ctx->cfg.max_envs) return IVM_E_INVALID;
+    if (n < 0 || n > ctx->cfg.known_capacity || (n > 0 && (!xyz || !sem))) return IVM_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const IvmParams &P = ctx->P;
+    const size_t ncell1 = ctx->kcells + 1;
+    uint32_t *off = P.koff + (size_t)env * ncell1;
+    cudaError_t e = cudaMemsetAsync(off, 0, ncell1 * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "known_load memset off");
+    e = cudaMemsetAsync(ctx->kfill, 0, ctx->kcells * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "known_load memset fill");
+    k_known_reset_env<<<1, 1, 0, st>>>(P, env, n, origin_row, origin_col);
+    if (n > 0) {
+        const int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+        k_known_hist<<<blocks, 256, 0, st>>>(P, env, n, xyz, origin_row, origin_col, off);
+        const int nb = (int)((ncell1 + 4095) / 4096);
+        k_scan_local<<<nb, 1024, 0, st>>>(off, ncell1, ctx->ktotals);
+        k_scan_totals<<<1, 1024, 0, st>>>(ctx->ktotals, nb);
+        k_scan_add<<<nb, 1024, 0, st>>>(off, ncell1, ctx->ktotals);
+        k_known_scatter<<<blocks, 256, 0, st>>>(P, env, n, xyz, sem, origin_row, origin_col, off, ctx->kfill);
+        ctx->launches += 5;
+    }
+    ctx->launches += 1;
+    IVM_CHECK_LAUNCH("known_load");
+    return IVM_OK;
+}
+
+int ivm_step_known(ivm_ctx *ctx, int32_t num_envs, const float *pose, const float *cs, uint8_t *occ, uint8_t *sem,
+                   ivm_stream_t stream) {
+    if (!ctx || ctx->cfg.mode != 1) return IVM_E_INVALID;
+    if (num_envs < 1 || num_envs > ctx->cfg.max_envs || !pose || !cs || !occ || !sem) return IVM_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    IvmParams P = ctx->P;
+    P.B = num_envs; P.pose = pose; P.cs = cs; P.occ = occ; P.sem = sem;
+    const int slot = timing_slot(ctx);
+    T_BEGIN(4);
+    launch_raster(ctx, P, st, true);
+    T_END(4);
+    IVM_CHECK_LAUNCH("k_raster<known>");
+    return IVM_OK;
+}
+
+int ivm_export_world(ivm_ctx *ctx, int32_t num_envs, int64_t cap, int64_t *env_out, float *xyz_out, uint8_t *label_out,
+                     uint64_t *key_out, uint64_t *count_dev, ivm_stream_t stream) {
+    if (!ctx || ctx->cfg.mode != 0 || num_envs < 1 || num_envs > ctx->cfg.max_envs) return IVM_E_INVALID;
+    if (!env_out || !xyz_out || !label_out || !key_out || !count_dev || cap < 0) return IVM_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    IvmParams P = ctx->P;
+    P.B = num_envs;
+    const int rows = num_envs * P.SR;
+    const int blocks = (rows * 32 + 255) / 256;
+    k_export_count<<<blocks, 256, 0, st>>>(P, ctx->rowlive);
+    const int nb = (rows + 4095) / 4096;
+    k_scan_local<<<nb, 1024, 0, st>>>(ctx->rowlive, (size_t)rows, ctx->rowtotals);
+    k_scan_totals<<<1, 1024, 0, st>>>(ctx->rowtotals, nb);
+    k_scan_add<<<nb, 1024, 0, st>>>(ctx->rowlive, (size_t)rows, ctx->rowtotals);
+    k_export_write<<<blocks, 256, 0, st>>>(P, ctx->rowlive, cap, (long long *)env_out, xyz_out, label_out,
+                                           (unsigned long long *)key_out, (unsigned long long *)count_dev);
+    ctx->launches += 5;
+    IVM_CHECK_LAUNCH("export_world");
+    return IVM_OK;
+}
+
+int ivm_read_status(ivm_ctx *ctx, ivm_status *host_out, ivm_stream_t stream) {
+    if (!ctx || !host_out) return IVM_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    IvmGlobal g;
+    cudaError_t e = cudaMemcpyAsync(&g, ctx->P.g, sizeof(g), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "read_status memcpy");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "read_status sync");
+    host_out->error_flags = g.err;
+    host_out->pad = 0;
+    for (int i = 0; i < 8; ++i) host_out->stats[i] = g.stats[i];
+    return IVM_OK;
+}
+
+int ivm_rebase_stamps(ivm_ctx *ctx, ivm_stream_t stream) {
+    if (!ctx || ctx->cfg.mode != 0) return IVM_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_rebase<<<148 * 8, 256, 0, st>>>(ctx->P);
+    k_rebase_env<<<(ctx->P.maxB + 255) / 256, 256, 0, st>>>(ctx->P);
+    ctx->launches += 2;
+    ctx->step = 1;
+    IVM_CHECK_LAUNCH("rebase");
+    return IVM_OK;
+}
+
+}  // extern "C"
