@@ -121,6 +121,12 @@ int64_t ivm_kernel_launches(const ivm_ctx *ctx);
 /* Rewrites all live stamps to 1 (call when IVM_E_STEP_OVERFLOW is returned). */
 int ivm_rebase_stamps(ivm_ctx *ctx, ivm_stream_t stream);
 
+/* Copies the whole map state of `src` into `dst` (same config except dst.max_envs >=
+ * src.max_envs; dst freshly created over a zero-filled workspace).  Lets the host grow the
+ * batch without losing the world stores (the reference's world cloud survives a batch
+ * grow, mapper.py:146-162, 533-553). */
+int ivm_copy_state(ivm_ctx *dst, const ivm_ctx *src, ivm_stream_t stream);
+
 const char *ivm_last_cuda_error(const ivm_ctx *ctx);
 const char *ivm_version(void);
 

@@ -801,6 +801,38 @@ int ivm_read_status(ivm_ctx *ctx, ivm_status *host_out, ivm_stream_t stream) {
     return IVM_OK;
 }
 
+int ivm_copy_state(ivm_ctx *dst, const ivm_ctx *src, ivm_stream_t stream) {
+    if (!dst || !src) return IVM_E_INVALID;
+    const ivm_config &a = dst->cfg, &b = src->cfg;
+    if (a.max_envs < b.max_envs || a.mode != b.mode || a.store_rows != b.store_rows || a.store_cols != b.store_cols ||
+        a.height != b.height || a.width != b.width || a.known_capacity != b.known_capacity)
+        return IVM_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = b.max_envs, SR = b.store_rows, SC = b.store_cols;
+    ivm_ctx *ctx = dst;
+#define IVM_COPY(dptr, sptr, bytes)                                                              \
+    do {                                                                                         \
+        cudaError_t _e = cudaMemcpyAsync((void *)(dptr), (const void *)(sptr), (bytes), cudaMemcpyDeviceToDevice, st); \
+        if (_e != cudaSuccess) return cuda_fail(ctx, _e, "copy_state");                          \
+    } while (0)
+    IVM_COPY(dst->P.g, src->P.g, sizeof(IvmGlobal));
+    IVM_COPY(dst->P.env, src->P.env, sizeof(IvmEnv) * B);
+    IVM_COPY(dst->P.xs, src->P.xs, sizeof(float) * (b.width > 0 ? b.width : 1));
+    IVM_COPY(dst->P.ys, src->P.ys, sizeof(float) * (b.height > 0 ? b.height : 1));
+    IVM_COPY(dst->P.rowcount, src->P.rowcount, sizeof(int32_t) * B * SR);
+    IVM_COPY(dst->P.colcount, src->P.colcount, sizeof(int32_t) * B * SC);
+    if (b.mode == 0) {
+        IVM_COPY(dst->P.store, src->P.store, sizeof(IvmRecord) * B * SR * SC);
+    } else {
+        IVM_COPY(dst->P.kpts, src->P.kpts, sizeof(IvmRecord) * B * (size_t)b.known_capacity);
+        IVM_COPY(dst->P.koff, src->P.koff, sizeof(uint32_t) * B * (SR * SC + 1));
+    }
+#undef IVM_COPY
+    dst->step = src->step;
+    dst->hi_water = src->hi_water;
+    return IVM_OK;
+}
+
 int ivm_rebase_stamps(ivm_ctx *ctx, ivm_stream_t stream) {
     if (!ctx || ctx->cfg.mode != 0) return IVM_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;

@@ -1,0 +1,582 @@
+"""Host-side mirror of the reference mapping module's interface.
+
+Same names, argument meaning, tensor layouts and error behaviour as
+`ivlnce_baselines/common/mapping_module/mapper.py` (reference), so that the
+IVLN-CE trainers and the obs-transform plugin (`obs_transforms.py:89-103`)
+can call it unchanged:
+
+    mapper = create_gt_semantics_iterative_mapper(device, camera_parameters, map_dimensions)
+    maps = mapper(episodes_info, observations, robot_current_state)
+    maps.occupancy, maps.semantic        # uint8 [B, num_rows, num_cols], views of internal buffers
+
+Everything below the dataclasses is different: the world state is a dense
+per-env half-cell store in HBM and every step is five CUDA kernel launches
+through the C ABI of libivlnmap.so (include/ivln_map.h).  There is no CPU
+implementation in this package.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .geometry import camera_scale_tables, camera_to_world_rows, ego_rotation
+
+DEFAULT_STORE_CELLS = 2048       # half-cells per side of an env's world store
+DEFAULT_KNOWN_CAPACITY = 1 << 22  # points per env in known-map mode
+
+
+# ----------------------------------------------------------------------------
+# Interface dataclasses (reference mapper.py:61-138, 195-200, 336-340)
+@dataclass
+class EpisodesInfo:
+    """reference mapper.py:61-86: `not_done_masks` [B,1]; 0 = episode (or tour) finished."""
+    not_done_masks: torch.Tensor
+    env_names: Sequence[str]
+    EPISODE_FINISHED: int = field(default=0, init=False)
+    EPISODE_UNFINISHED: int = field(default=1, init=False)
+
+    def __post_init__(self):
+        self.env_names = np.asarray(self.env_names)
+        self.not_done_masks = self.not_done_masks.squeeze(1)
+        self.indices = torch.arange(self.not_done_masks.shape[0], device=self.not_done_masks.device)
+
+    def finished(self) -> torch.Tensor:
+        return self.not_done_masks == self.EPISODE_FINISHED
+
+    def unfinished(self) -> torch.Tensor:
+        return self.not_done_masks == self.EPISODE_UNFINISHED
+
+    def finished_indices(self) -> torch.Tensor:
+        return self.indices[self.finished()]
+
+    @property
+    def num_envs(self) -> int:
+        return len(self.not_done_masks)
+
+
+@dataclass
+class MapDimensions:
+    """reference mapper.py:89-114."""
+    height_meters: float
+    width_meters: float
+    resolution_meters: float
+    num_rows: int = field(init=False)
+    num_cols: int = field(init=False)
+
+    def __post_init__(self):
+        self.num_rows = math.ceil(self.height_meters / self.resolution_meters)
+        self.num_cols = math.ceil(self.width_meters / self.resolution_meters)
+
+
+@dataclass
+class CameraParameters:
+    """reference mapper.py:336-340 (`height_clip` is plumbed but unused on this path)."""
+    vertical_fov_radians: float
+    features_spatial_dimensions: tuple
+    height_clip: float = 0.0
+
+
+@dataclass
+class Observations:
+    """reference mapper.py:195-200; NCHW views of the sensor tensors."""
+    semantics: Optional[torch.Tensor]
+    depth_normalized: Optional[torch.Tensor]
+    rgb: Optional[torch.Tensor]
+
+
+@dataclass
+class State:
+    pose: Optional[torch.Tensor] = None
+    elevation: Optional[torch.Tensor] = None
+    heading: Optional[torch.Tensor] = None
+
+
+class RobotCurrentState(State):
+    """reference mapper.py:127-138."""
+
+    @property
+    def height(self):
+        return self.pose[:, 1]
+
+    def get_camera_matrix(self) -> torch.Tensor:
+        """f32 [B,4,4] camera->world matrix (projector/core.py:6-37 with elevation + pi)."""
+        rows = camera_to_world_rows(self.pose, self.elevation, self.heading)
+        T = torch.zeros(rows.shape[0], 4, 4, dtype=torch.float32, device=rows.device)
+        T[:, :3, :] = rows.view(-1, 3, 4)
+        T[:, 3, 3] = 1
+        return T
+
+
+class RobotStartState(State):
+    """reference mapper.py:141-178: pose of each env at its last reset (kept for API parity; nothing reads it)."""
+
+    def __init__(self):
+        super().__init__()
+        self.batch_size = None
+
+    def update(self, episodes_info: EpisodesInfo, current_state: RobotCurrentState):
+        B, dev = episodes_info.num_envs, current_state.pose.device
+        if self.batch_size != B:
+            if self.batch_size is None or B > self.batch_size:
+                self.pose = torch.zeros((B, 3), device=dev)
+                self.elevation = torch.zeros((B,), device=dev)
+                self.heading = torch.zeros((B,), device=dev)
+            else:
+                self.pose, self.elevation, self.heading = self.pose[:B], self.elevation[:B], self.heading[:B]
+            self.batch_size = B
+        done = episodes_info.finished()
+        self.pose = torch.where(done.unsqueeze(1), current_state.pose.to(self.pose.dtype), self.pose)
+
+
+class LocalizeRobot:
+    """reference mapper.py:180-192."""
+
+    def __init__(self):
+        self.current_state = RobotCurrentState()
+        self.start_state = RobotStartState()
+
+    def __call__(self, episodes_info: EpisodesInfo, robot_current_state: RobotCurrentState):
+        self.current_state = robot_current_state
+        self.start_state.update(episodes_info, robot_current_state)
+        return self
+
+
+@dataclass
+class SemanticPointcloud:
+    """reference mapper.py:203-281 (read-only view handed out by get_world_semantic_pointcloud)."""
+    batch_indices: Optional[torch.Tensor] = None
+    xyz: Optional[torch.Tensor] = None
+    semantics: Optional[torch.Tensor] = None
+
+    def __len__(self):
+        return 0 if self.xyz is None else self.xyz.shape[0]
+
+
+class OccupancySemanticMapMemory:
+    """reference mapper.py:620-648: `.occupancy` / `.semantic` are the live uint8 [B,R,C]
+    buffers; they are overwritten by the next forward call."""
+
+    def __init__(self):
+        self._occ: Optional[torch.Tensor] = None
+        self._sem: Optional[torch.Tensor] = None
+
+    @property
+    def occupancy(self) -> torch.Tensor:
+        return self._occ
+
+    @property
+    def semantic(self) -> torch.Tensor:
+        return self._sem
+
+    @property
+    def data(self) -> torch.Tensor:
+        # the reference property (mapper.py:646-648) references undefined attributes; this is what it means
+        return torch.stack((self._occ, self._sem), 1)
+
+
+# ----------------------------------------------------------------------------
+# Semantics front ends (reference mapper.py:651-800)
+class ComputeSemantics(nn.Module):
+    pass
+
+
+class GTSemantics(ComputeSemantics):
+    def forward(self, observations: Observations) -> Observations:
+        if observations.semantics is None:
+            raise Exception("Semantic Sensor not in use")
+        return observations
+
+
+class PredictSemantics(ComputeSemantics):
+    """reference mapper.py:703-800.  The segmentation network itself (RedNet, cuDNN) is outside
+    this repository's scope; `model` is any callable (rgb_normalized [B,3,H,W], depth_normalized
+    [B,1,H,W]) -> class scores f32 [B,Cls,H,W].  The reference's tail
+    `scores.argmax(1, keepdims=True).to(uint8)` (mapper.py:795-798) is NOT done here: the scores
+    go straight into the fused ingest kernel, which does the argmax while streaming the planes."""
+
+    def __init__(self, model: Optional[Callable] = None):
+        super().__init__()
+        self.model = model
+        self._rgb_mean = self._rgb_std = None
+
+    def preprocess(self, observations: Observations):
+        """mapper.py:715-736, 788-793 (torch ops; next-scope row f-4 of SURVEY.md section 8)."""
+        depth = observations.depth_normalized
+        if self._rgb_mean is None:
+            dev = observations.rgb.device
+            self._rgb_mean = torch.as_tensor([0.485, 0.456, 0.406], device=dev)[None, :, None, None]
+            self._rgb_std = torch.as_tensor([0.229, 0.224, 0.225], device=dev)[None, :, None, None]
+        rgb = torch.nn.functional.interpolate(observations.rgb.float() / 255.0, size=tuple(depth.shape[2:]), mode="bilinear")
+        rgb = (rgb - self._rgb_mean) / self._rgb_std
+        d = (depth - 0.213) / 0.285
+        return rgb, d
+
+    def scores(self, observations: Observations) -> torch.Tensor:
+        if observations.rgb is None:
+            raise Exception("RGB Sensor not in use")
+        if self.model is None:
+            raise Exception("PredictSemantics needs a segmentation model (callable returning class scores)")
+        with torch.no_grad():
+            rgb, d = self.preprocess(observations)
+            return self.model(rgb, d)
+
+    def forward(self, observations: Observations) -> Observations:
+        observations.semantics = self.scores(observations).argmax(1, keepdims=True).to(torch.uint8)
+        return observations
+
+
+class PrecomputedScores(PredictSemantics):
+    """Front end for callers that already hold the class scores (benchmarks, tests, an
+    external segmentation service): `observations.rgb` carries the f32 [B,Cls,H,W] scores."""
+
+    def scores(self, observations: Observations) -> torch.Tensor:
+        if observations.rgb is None:
+            raise Exception("RGB Sensor not in use")
+        return observations.rgb
+
+
+# ----------------------------------------------------------------------------
+class _MapEngine:
+    """Owns one libivlnmap context + its device workspace and output buffers."""
+
+    def __init__(self, device: torch.device, map_dimensions: MapDimensions, camera: Optional[CameraParameters],
+                 mode: str, max_envs: int, store_cells: int, known_capacity: int, tile: int = 0):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.MapLibraryError(
+                f"the B200 mapping module runs on CUDA devices only (got {device}); there is no CPU fallback")
+        self.lib = _lib.load()
+        self.device = device
+        self.md = map_dimensions
+        self.camera = camera
+        self.mode = mode
+        self.store_cells = int(store_cells)
+        self.known_capacity = int(known_capacity)
+        self.tile = int(tile)
+        self.ctx = None
+        self.workspace = None
+        self.max_envs = 0
+        self._create(max_envs)
+
+    # -- context lifetime
+    def _config(self, max_envs: int) -> _lib.IvmConfig:
+        md = self.md
+        H, W = (self.camera.features_spatial_dimensions if self.camera is not None else (0, 0))
+        return _lib.IvmConfig(
+            max_envs=max_envs, height=int(H), width=int(W), map_rows=md.num_rows, map_cols=md.num_cols,
+            res=np.float32(md.resolution_meters), half_res=np.float32(md.resolution_meters / 2),
+            half_h=np.float32(md.height_meters / 2), half_w=np.float32(md.width_meters / 2),
+            store_rows=self.store_cells, store_cols=self.store_cells, mode=0 if self.mode == "iterative" else 1,
+            known_capacity=self.known_capacity if self.mode == "known" else 0,
+            tile_rows=self.tile, tile_cols=self.tile)
+
+    def _create(self, max_envs: int):
+        cfg = self._config(max_envs)
+        nbytes = self.lib.ivm_workspace_bytes(ctypes.byref(cfg))
+        if nbytes == 0:
+            raise _lib.MapLibraryError("invalid map configuration")
+        with torch.cuda.device(self.device):
+            workspace = torch.zeros(nbytes + 256, dtype=torch.uint8, device=self.device)
+            base = workspace.data_ptr()
+            aligned = (base + 255) & ~255
+            ctx = ctypes.c_void_p()
+            _lib.check(self.lib.ivm_create(ctypes.byref(cfg), aligned, nbytes, ctypes.byref(ctx)), None, "ivm_create")
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            old = self.ctx
+            if old is not None:
+                _lib.check(self.lib.ivm_copy_state(ctx, old, stream), ctx, "ivm_copy_state")
+                torch.cuda.current_stream(self.device).synchronize()
+                self.lib.ivm_destroy(old)
+            elif self.camera is not None:
+                H, W = self.camera.features_spatial_dimensions
+                xs, ys = camera_scale_tables(int(H), int(W), float(self.camera.vertical_fov_radians), self.device)
+                _lib.check(self.lib.ivm_set_camera(ctx, xs.data_ptr(), ys.data_ptr(), stream), ctx, "ivm_set_camera")
+                self._tables = (xs, ys)
+            self.ctx, self.workspace, self.max_envs = ctx, workspace, max_envs
+            R, C = self.md.num_rows, self.md.num_cols
+            self.occ = torch.zeros((max_envs, R, C), dtype=torch.uint8, device=self.device)
+            self.sem = torch.zeros((max_envs, R, C), dtype=torch.uint8, device=self.device)
+            if self.mode == "iterative":
+                H, W = self.camera.features_spatial_dimensions
+                self.labels_out = torch.zeros((max_envs, int(H), int(W)), dtype=torch.uint8, device=self.device)
+
+    def ensure_capacity(self, num_envs: int):
+        if num_envs > self.max_envs:
+            self._create(max(num_envs, 2 * self.max_envs))
+
+    def close(self):
+        if self.ctx is not None:
+            self.lib.ivm_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def status(self) -> Tuple[int, List[int]]:
+        st = _lib.IvmStatus()
+        _lib.check(self.lib.ivm_read_status(self.ctx, ctypes.byref(st), self.stream()), self.ctx, "ivm_read_status")
+        return int(st.error_flags), [int(v) for v in st.stats]
+
+
+def _as_u8_masks(masks: torch.Tensor, device) -> torch.Tensor:
+    m = masks.to(device=device, non_blocking=True)
+    if m.dtype != torch.uint8:
+        m = (m != 0).to(torch.uint8)
+    return m.contiguous()
+
+
+class MappingModule(nn.Module):
+    """Drop-in for reference `MappingModule` (mapper.py:904-947): same forward signature, returns an
+    object with `.occupancy` / `.semantic` uint8 [B, num_rows, num_cols] on the input device.
+
+    mode "iterative": world state built from depth + semantics every step (episodic or iterative
+    depending on which masks the caller passes, base_il_trainer.py:746-753);
+    mode "known": scene clouds `{maps_location}/{env_name}.npz` loaded on reset (mapper.py:851-881).
+    """
+
+    def __init__(self, device, map_dimensions: MapDimensions, camera_parameters: Optional[CameraParameters] = None,
+                 compute_semantics: Optional[ComputeSemantics] = None, mode: str = "iterative",
+                 maps_location: Optional[str] = None, max_envs: Optional[int] = None,
+                 store_cells: int = DEFAULT_STORE_CELLS, known_capacity: int = DEFAULT_KNOWN_CAPACITY,
+                 host_trig: bool = False, raster_tile: int = 0):
+        super().__init__()
+        assert mode in ("iterative", "known")
+        self.device = torch.device(device)
+        self.map_dimensions = map_dimensions
+        self.camera_parameters = camera_parameters
+        self.compute_semantics = compute_semantics
+        self.mode = mode
+        self.maps_location = maps_location
+        self.localize_robot = LocalizeRobot()
+        self.map_memory = OccupancySemanticMapMemory()
+        self.host_trig = host_trig  # evaluate sin/cos on the host CPU (bit-identical to a CPU reference run)
+        self._engine_args = dict(store_cells=store_cells, known_capacity=known_capacity, tile=raster_tile)
+        self._engine: Optional[_MapEngine] = None
+        self._initial_max_envs = max_envs
+        self._num_envs = 0
+        self._known_cache: Dict[str, Tuple[torch.Tensor, torch.Tensor, int, int]] = {}
+        self._known_order: List[int] = []   # env indices in load order (world-cloud order in known mode)
+        self._known_loaded: Dict[int, str] = {}
+
+    # -- engine
+    def engine(self, num_envs: int) -> _MapEngine:
+        if self._engine is None:
+            n = max(num_envs, self._initial_max_envs or 0)
+            self._engine = _MapEngine(self.device, self.map_dimensions, self.camera_parameters, self.mode, n,
+                                      **self._engine_args)
+        self._engine.ensure_capacity(num_envs)
+        return self._engine
+
+    def _matrices(self, state: RobotCurrentState):
+        pose, elev, head = state.pose, state.elevation, state.heading
+        if self.host_trig:
+            p, e, h = pose.detach().cpu(), elev.detach().cpu(), head.detach().cpu()
+            T12 = camera_to_world_rows(p, e, h).to(self.device, non_blocking=True)
+            cs = ego_rotation(h).to(self.device, non_blocking=True)
+        else:
+            pose = pose.to(self.device, non_blocking=True)
+            elev = elev.to(self.device, non_blocking=True)
+            head = head.to(self.device, non_blocking=True)
+            T12 = camera_to_world_rows(pose, elev, head)
+            cs = ego_rotation(head)
+        pose32 = pose.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        return T12.contiguous(), cs.contiguous(), pose32
+
+    # -- forward
+    @torch.no_grad()
+    def forward(self, episodes_info: EpisodesInfo, observations: Observations,
+                robot_current_state: RobotCurrentState) -> OccupancySemanticMapMemory:
+        self.localize_robot(episodes_info, robot_current_state)
+        B = episodes_info.num_envs
+        eng = self.engine(B)
+        lib = eng.lib
+        with torch.cuda.device(self.device):
+            T12, cs, pose = self._matrices(robot_current_state)
+            if self.mode == "iterative":
+                self._forward_iterative(eng, B, episodes_info, observations, T12, cs, pose)
+            else:
+                self._forward_known(eng, B, episodes_info, cs, pose)
+        self._num_envs = B
+        self.map_memory._occ = eng.occ[:B]
+        self.map_memory._sem = eng.sem[:B]
+        return self.map_memory
+
+    def _forward_iterative(self, eng, B, episodes_info, observations, T12, cs, pose):
+        H, W = (int(v) for v in self.camera_parameters.features_spatial_dimensions)
+        sem_mod = self.compute_semantics
+        scores = None
+        if isinstance(sem_mod, PredictSemantics):
+            scores = sem_mod.scores(observations)
+        elif sem_mod is not None:
+            observations = sem_mod(observations)
+        depth = observations.depth_normalized
+        assert depth.shape[2] == H  # projector/point_cloud.py:68-69
+        assert depth.shape[3] == W
+        depth = depth.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        masks = _as_u8_masks(episodes_info.not_done_masks, self.device)
+        labels_ptr, logits_ptr, ncls = None, None, 0
+        if scores is not None:
+            scores = scores.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            assert scores.shape[0] == B and tuple(scores.shape[2:]) == (H, W)
+            logits_ptr, ncls = scores.data_ptr(), int(scores.shape[1])
+            # side effect of PredictSemantics.forward (mapper.py:796-798)
+            observations.semantics = eng.labels_out[:B].view(B, 1, H, W)
+        else:
+            labels = observations.semantics.to(device=self.device, non_blocking=True)
+            if labels.dtype != torch.uint8:
+                labels = labels.to(torch.uint8)
+            labels = labels.contiguous()
+            assert labels.numel() == B * H * W
+            labels_ptr = labels.data_ptr()
+        rc = eng.lib.ivm_step_iterative(eng.ctx, B, depth.data_ptr(), labels_ptr, logits_ptr, ncls,
+                                        eng.labels_out.data_ptr(), T12.data_ptr(), pose.data_ptr(), cs.data_ptr(),
+                                        masks.data_ptr(), eng.occ.data_ptr(), eng.sem.data_ptr(), eng.stream())
+        if rc == 4:  # 2^24 - 1 steps: rebase the stamps and retry once
+            _lib.check(eng.lib.ivm_rebase_stamps(eng.ctx, eng.stream()), eng.ctx, "ivm_rebase_stamps")
+            rc = eng.lib.ivm_step_iterative(eng.ctx, B, depth.data_ptr(), labels_ptr, logits_ptr, ncls,
+                                            eng.labels_out.data_ptr(), T12.data_ptr(), pose.data_ptr(), cs.data_ptr(),
+                                            masks.data_ptr(), eng.occ.data_ptr(), eng.sem.data_ptr(), eng.stream())
+        _lib.check(rc, eng.ctx, "ivm_step_iterative")
+
+    # -- known-map mode
+    def get_map_file(self, env_name: str) -> str:
+        return os.path.join(self.maps_location, f"{env_name}.npz")
+
+    def _known_cloud(self, env_name: str):
+        if env_name not in self._known_cache:
+            with np.load(self.get_map_file(env_name)) as f:  # SemanticPointcloud.from_npz_file, mapper.py:283-294
+                xyz = np.ascontiguousarray(f["xyz"], dtype=np.float32)
+                sem = np.ascontiguousarray(np.asarray(f["semantics"]).astype(np.int64).astype(np.uint8))
+            hr = np.float32(self.map_dimensions.resolution_meters / 2)
+            if xyz.shape[0]:
+                o_r = int(np.floor(float(xyz[:, 2].min()) / float(hr))) - 2
+                o_c = int(np.floor(float(xyz[:, 0].min()) / float(hr))) - 2
+            else:
+                o_r = o_c = 0
+            self._known_cache[env_name] = (torch.from_numpy(xyz).to(self.device), torch.from_numpy(sem).to(self.device),
+                                           o_r, o_c)
+        return self._known_cache[env_name]
+
+    def _forward_known(self, eng, B, episodes_info, cs, pose):
+        lib, st = eng.lib, eng.stream()
+        for b in [b for b in self._known_order if b >= B]:      # clear_paused_episodes, mapper.py:315-318
+            _lib.check(lib.ivm_known_clear(eng.ctx, b, st), eng.ctx, "ivm_known_clear")
+            self._known_order.remove(b)
+            self._known_loaded.pop(b, None)
+        finished = episodes_info.finished_indices().tolist()     # host sync, as the reference does (mapper.py:873-878)
+        for b in finished:
+            name = str(episodes_info.env_names[b])
+            xyz, sem, o_r, o_c = self._known_cloud(name)
+            _lib.check(lib.ivm_known_load(eng.ctx, b, xyz.shape[0], xyz.data_ptr(), sem.data_ptr(), o_r, o_c, st),
+                       eng.ctx, "ivm_known_load")
+            if b in self._known_order:
+                self._known_order.remove(b)
+            self._known_order.append(b)
+            self._known_loaded[b] = name
+        _lib.check(lib.ivm_step_known(eng.ctx, B, pose.data_ptr(), cs.data_ptr(), eng.occ.data_ptr(),
+                                      eng.sem.data_ptr(), st), eng.ctx, "ivm_step_known")
+
+    # -- inspection
+    def get_world_semantic_pointcloud(self) -> SemanticPointcloud:
+        """reference mapper.py:946-947: the world cloud (batch_indices i64 [P], xyz f32 [P,3],
+        semantics u8 [P]) in the reference's list order."""
+        if self._engine is None or self._num_envs == 0:
+            return SemanticPointcloud()
+        eng, B = self._engine, self._num_envs
+        if self.mode == "known":
+            bs, xs, ss = [], [], []
+            for b in self._known_order:
+                xyz, sem, _, _ = self._known_cloud(self._known_loaded[b])
+                bs.append(torch.full((xyz.shape[0],), b, dtype=torch.long, device=self.device))
+                xs.append(xyz)
+                ss.append(sem)
+            if not xs:
+                return SemanticPointcloud()
+            return SemanticPointcloud(torch.cat(bs), torch.cat(xs), torch.cat(ss))
+        with torch.cuda.device(self.device):
+            _, stats = eng.status()
+            cap = max(int(stats[2]), 1)
+            env = torch.zeros(cap, dtype=torch.int64, device=self.device)
+            xyz = torch.zeros((cap, 3), dtype=torch.float32, device=self.device)
+            lab = torch.zeros(cap, dtype=torch.uint8, device=self.device)
+            key = torch.zeros(cap, dtype=torch.int64, device=self.device)
+            cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+            _lib.check(eng.lib.ivm_export_world(eng.ctx, B, cap, env.data_ptr(), xyz.data_ptr(), lab.data_ptr(),
+                                                key.data_ptr(), cnt.data_ptr(), eng.stream()), eng.ctx, "ivm_export_world")
+            n = int(cnt.item())
+            assert n <= cap, (n, cap)
+            order = torch.sort(key[:n], stable=True).indices
+            return SemanticPointcloud(env[:n][order], xyz[:n][order], lab[:n][order])
+
+    def status(self):
+        """(error_flags, stats) of the last step; synchronises the stream."""
+        if self._engine is None:
+            return 0, [0] * 8
+        return self._engine.status()
+
+    def check_errors(self):
+        flags, _ = self.status()
+        if flags & _lib.ERR_STORE_OVERFLOW:
+            raise _lib.MapLibraryError("a point fell outside an env's world store window (raise store_cells)")
+        if flags & _lib.ERR_EDGE_OVERFLOW:
+            raise _lib.MapLibraryError("edge list capacity exceeded")
+        if flags & _lib.ERR_KNOWN_OVERFLOW:
+            raise _lib.MapLibraryError("known-map cloud outside the store window / over capacity")
+
+    def kernel_launches(self) -> int:
+        return 0 if self._engine is None else int(self._engine.lib.ivm_kernel_launches(self._engine.ctx))
+
+    def set_timing(self, enabled: bool):
+        _lib.check(self._engine.lib.ivm_set_timing(self._engine.ctx, 1 if enabled else 0))
+
+    def stage_times(self, reset: bool = True):
+        ms = (ctypes.c_float * 5)()
+        n = (ctypes.c_int32 * 5)()
+        _lib.check(self._engine.lib.ivm_stage_times(self._engine.ctx, ms, n, 1 if reset else 0))
+        return list(ms), list(n)
+
+
+# ----------------------------------------------------------------------------
+# Factories (reference mapper.py:950-1028); extra keyword arguments are optional.
+def create_iterative_mapper(device, camera_parameters: CameraParameters, map_dimensions: MapDimensions,
+                            semantics_module: ComputeSemantics, **kw) -> MappingModule:
+    return MappingModule(device, map_dimensions, camera_parameters, semantics_module, mode="iterative", **kw)
+
+
+def create_known_mapper(device, map_dimensions: MapDimensions, maps_location, **kw) -> MappingModule:
+    return MappingModule(device, map_dimensions, None, None, mode="known", maps_location=maps_location, **kw)
+
+
+def create_gt_semantics_iterative_mapper(device, camera_parameters: CameraParameters,
+                                         map_dimensions: MapDimensions, **kw) -> MappingModule:
+    return create_iterative_mapper(device, camera_parameters, map_dimensions, GTSemantics(), **kw)
+
+
+def create_predicted_semantics_iterative_mapper(device, camera_parameters: CameraParameters,
+                                                map_dimensions: MapDimensions, semantics_module=None,
+                                                **kw) -> MappingModule:
+    return create_iterative_mapper(device, camera_parameters, map_dimensions,
+                                   semantics_module if semantics_module is not None else PredictSemantics(), **kw)
+
+
+def create_gt_semantics_known_mapper(device, map_dimensions: MapDimensions, **kw) -> MappingModule:
+    return create_known_mapper(device, map_dimensions, kw.pop("maps_location", "data/known_maps/gt_semantics"), **kw)
+
+
+def create_predicted_semantics_known_mapper(device, map_dimensions: MapDimensions, **kw) -> MappingModule:
+    return create_known_mapper(device, map_dimensions,
+                               kw.pop("maps_location", "data/known_maps/predicted_semantics"), **kw)

@@ -1,0 +1,123 @@
+"""GPU parity tests: the CUDA path (through the public MappingModule -> C ABI) against the
+golden fixtures of the unmodified reference and against the CPU oracle.  Integer state
+(cell indices, labels, occupancy) must be bit-exact; float map values (the world records)
+are compared bitwise as well, which is stricter than the 1e-5 the north star asks for."""
+import numpy as np
+import pytest
+import torch
+
+from golden_io import golden_names, load_golden
+from scenarios import run_mapper
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_cuda(scn, **kw):
+    from cuda_stepper import CudaStepper
+
+    pred = "logits" in scn
+    cs = CudaStepper(scn["cfg"], known_clouds=scn.get("known"), pred=pred, max_envs=int(scn["num_envs"].max()), **kw)
+    T = scn["masks"].shape[0]
+    outs, sizes = [], []
+    for t in range(T):
+        B = int(scn["num_envs"][t])
+        k = {}
+        if scn["cfg"]["mode"] == "iterative":
+            k["depth"] = scn["depth"][t, :B]
+            if pred:
+                k["logits"] = scn["logits"][t, :B]
+            else:
+                k["labels"] = scn["labels"][t, :B]
+        else:
+            k["env_names"] = scn["env_names"][t][:B]
+        o, s = cs.step(scn["masks"][t, :B], scn["pose"][t, :B], scn["orientation"][t, :B], **k)
+        outs.append((o, s))
+        if pred:
+            lab = cs.last_obs.semantics.cpu().numpy().reshape(B, *scn["labels_for_map"].shape[2:])
+            assert np.array_equal(lab, scn["labels_for_map"][t, :B]), f"argmax labels differ at step {t}"
+        if scn["cfg"]["mode"] == "iterative":
+            sizes.append(len(cs.world()[0]))
+    return cs, outs, sizes
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_matches_reference_golden(name):
+    scn = load_golden(name)
+    cs, outs, sizes = _run_cuda(scn)
+    for t, (o, s) in enumerate(outs):
+        B = o.shape[0]
+        assert np.array_equal(o, scn["ref_occupancy"][t, :B]), f"occupancy differs at step {t}"
+        assert np.array_equal(s, scn["ref_semantic"][t, :B]), f"semantic differs at step {t}"
+    cs.mm.check_errors()
+    if scn["cfg"]["mode"] == "iterative":
+        assert sizes == scn["ref_world_sizes"].tolist()
+    b, xyz, sem = cs.world()
+    assert np.array_equal(b, scn["ref_world_b"])
+    assert np.array_equal(xyz.view(np.uint32), scn["ref_world_xyz"].view(np.uint32))
+    assert np.array_equal(sem, scn["ref_world_sem"])
+
+
+@pytest.mark.parametrize("tile", [8, 16, 64])
+def test_raster_tile_sizes(tile):
+    scn = load_golden("iid_f32_res005")
+    cs, outs, _ = _run_cuda(scn, raster_tile=tile)
+    for t, (o, s) in enumerate(outs):
+        assert np.array_equal(o, scn["ref_occupancy"][t]) and np.array_equal(s, scn["ref_semantic"][t])
+
+
+def test_device_trig_f64_matches():
+    """sin/cos evaluated by torch on the GPU in float64 round to the same float32 matrices."""
+    scn = load_golden("iid_f64")
+    cs, outs, _ = _run_cuda(scn, host_trig=False)
+    for t, (o, s) in enumerate(outs):
+        assert np.array_equal(o, scn["ref_occupancy"][t]) and np.array_equal(s, scn["ref_semantic"][t])
+
+
+def test_full_size_against_oracle():
+    """BASELINE config 1 shape (256x256 depth, 27 labels, 0.05 m cells) on 3 envs, 8 steps."""
+    from ivlnce_b200.synthetic import ScenarioConfig, make_scenario
+    from oracle.oracle import OracleMapper
+    from scenarios import _wrap
+
+    c = ScenarioConfig(num_envs=3, height=256, width=256, steps=8, resolution=0.05, num_labels=27,
+                       reset_steps={5: [2]}, seed=77)
+    scn = _wrap(c, make_scenario(c))
+    orc = OracleMapper(c.height, c.width, c.vfov_radians, c.map_meters, c.map_meters, c.resolution)
+    ref_outs, _ = run_mapper(orc.step, scn)
+    cs, outs, _ = _run_cuda(scn)
+    for t in range(c.steps):
+        assert np.array_equal(outs[t][0], ref_outs[t][0]), t
+        assert np.array_equal(outs[t][1], ref_outs[t][1]), t
+    b1, x1, s1 = orc.world()
+    b2, x2, s2 = cs.world()
+    assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(s1, s2)
+    cs.mm.check_errors()
+
+
+def test_batch_grow_keeps_world():
+    """Growing the batch beyond the context capacity re-creates the context and copies the stores."""
+    scn = load_golden("batch_shrink_grow")
+    from cuda_stepper import CudaStepper
+
+    cs = CudaStepper(scn["cfg"], max_envs=1)  # forces two grows (1 -> 2 -> 4)
+    T = scn["masks"].shape[0]
+    for t in range(T):
+        B = int(scn["num_envs"][t])
+        o, s = cs.step(scn["masks"][t, :B], scn["pose"][t, :B], scn["orientation"][t, :B],
+                       depth=scn["depth"][t, :B], labels=scn["labels"][t, :B])
+        assert np.array_equal(o, scn["ref_occupancy"][t, :B]) and np.array_equal(s, scn["ref_semantic"][t, :B]), t
+
+
+def test_store_overflow_is_reported():
+    from ivlnce_b200._lib import MapLibraryError
+
+    scn = load_golden("iid_f32_res005")
+    cs, outs, _ = _run_cuda(scn, store_cells=256)  # 6.4 m window: far points fall outside
+    with pytest.raises(MapLibraryError):
+        cs.mm.check_errors()
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+
+    g.smoke()
