@@ -81,13 +81,16 @@ int ivm_set_camera(ivm_ctx *ctx, const float *xs_dev, const float *ys_dev, ivm_s
  *   T12     f32 [B,12]    rows 0..2 of the camera->world matrix (core.py:6-37)
  *   pose    f32 [B,3]     world_robot_pose
  *   cs      f32 [B,2]     cos(-heading), sin(-heading) as f32 (mapper.py:38-48,264-266)
+ *   orientation [B,2]     (elevation, heading) as f64 or f32 (world_robot_orientation).  When
+ *                         given, T12 and cs may be NULL: they are then derived on the device in
+ *                         the angles' dtype (same libdevice sin/cos torch's CUDA ops use).
  *   masks   u8  [B]       not_done_masks; 0 wipes that env first (mapper.py:320-326)
  *   occ,sem u8  [B,R,C]   outputs (OccupancySemanticMapMemory.occupancy / .semantic)
  * Envs with index >= num_envs are dropped (mapper.py:315-318). */
 int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const uint8_t *labels,
                        const float *logits, int32_t num_classes, uint8_t *labels_out, const float *T12,
-                       const float *pose, const float *cs, const uint8_t *masks, uint8_t *occ, uint8_t *sem,
-                       ivm_stream_t stream);
+                       const float *pose, const float *cs, const void *orientation, int32_t orientation_is_f64,
+                       const uint8_t *masks, uint8_t *occ, uint8_t *sem, ivm_stream_t stream);
 
 /* Known-map mode.  ivm_known_load replaces env `env`'s scene cloud
  * (xyz f32 [n,3], sem u8 [n], device pointers; list order = npz order);
@@ -95,8 +98,8 @@ int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const
 int ivm_known_load(ivm_ctx *ctx, int32_t env, int64_t n, const float *xyz, const uint8_t *sem, int32_t origin_row,
                    int32_t origin_col, ivm_stream_t stream);
 int ivm_known_clear(ivm_ctx *ctx, int32_t env, ivm_stream_t stream);
-int ivm_step_known(ivm_ctx *ctx, int32_t num_envs, const float *pose, const float *cs, uint8_t *occ, uint8_t *sem,
-                   ivm_stream_t stream);
+int ivm_step_known(ivm_ctx *ctx, int32_t num_envs, const float *pose, const float *cs, const void *orientation,
+                   int32_t orientation_is_f64, uint8_t *occ, uint8_t *sem, ivm_stream_t stream);
 
 /* Compacts the live world records into (env i64, xyz f32 x3, label u8, list key u64)
  * arrays of capacity `cap`; *count_dev (u64, device) receives the number of records.

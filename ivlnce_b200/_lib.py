@@ -62,10 +62,11 @@ def load() -> ctypes.CDLL:
     L.ivm_create.argtypes = [ctypes.POINTER(IvmConfig), _vp, ctypes.c_size_t, ctypes.POINTER(_vp)]
     L.ivm_destroy.argtypes = [_vp]
     L.ivm_set_camera.argtypes = [_vp, _vp, _vp, _vp]
-    L.ivm_step_iterative.argtypes = [_vp, ctypes.c_int32, _vp, _vp, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.ivm_step_iterative.argtypes = [_vp, ctypes.c_int32, _vp, _vp, _vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp,
+                                     ctypes.c_int32, _vp, _vp, _vp, _vp]
     L.ivm_known_load.argtypes = [_vp, ctypes.c_int32, ctypes.c_int64, _vp, _vp, ctypes.c_int32, ctypes.c_int32, _vp]
     L.ivm_known_clear.argtypes = [_vp, ctypes.c_int32, _vp]
-    L.ivm_step_known.argtypes = [_vp, ctypes.c_int32, _vp, _vp, _vp, _vp, _vp]
+    L.ivm_step_known.argtypes = [_vp, ctypes.c_int32, _vp, _vp, _vp, ctypes.c_int32, _vp, _vp, _vp]
     L.ivm_export_world.argtypes = [_vp, ctypes.c_int32, ctypes.c_int64, _vp, _vp, _vp, _vp, _vp, _vp]
     L.ivm_read_status.argtypes = [_vp, ctypes.POINTER(IvmStatus), _vp]
     L.ivm_set_timing.argtypes = [_vp, ctypes.c_int32]

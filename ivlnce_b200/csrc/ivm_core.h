@@ -134,6 +134,7 @@ struct IvmParams {
     unsigned long long *hxord;    // first list position among the best
     uint32_t hmask;
     const float *xs, *ys;         // camera scale tables [W], [H]
+    float *T12_buf, *cs_buf;      // [maxB][12], [maxB][2]: matrices derived in K0 when the caller passes angles
     // known-map mode (CSR store)
     IvmRecord *kpts;              // [maxB][kcap] points sorted by half-cell
     uint32_t *koff;               // [maxB][SR*SC+1]
@@ -147,6 +148,8 @@ struct IvmParams {
     const float *pose;            // [B][3]
     const float *cs;              // [B][2] cos(-heading), sin(-heading)
     const uint8_t *masks;         // [B] 0 = reset this env before ingesting
+    const void *orient;           // [B][2] (elevation, heading), f64 or f32; NULL if T12/cs are given
+    int32_t orient_f64;
     uint8_t *occ, *sem;           // [B][R][C]
 };
 
@@ -293,6 +296,35 @@ IVM_HD void ivm_prep_env(const IvmParams &P, int b, int tid, int nthreads, bool 
             e->origin_r = (fabsf(pr) < 1.0e9f ? (int32_t)pr : 0) - P.SR / 2;
             e->origin_c = (fabsf(pc) < 1.0e9f ? (int32_t)pc : 0) - P.SC / 2;
         }
+    }
+}
+
+// Pose matrices of one env from (elevation, heading): rows 0..2 of Rx(elevation+pi)*Ry(heading)|pose
+// (projector/core.py:6-37 as called by mapper.py:132-138) and (cos,sin)(-heading) (mapper.py:38-48,
+// 264-266).  Trig and products are evaluated in the angles' dtype and rounded to f32 when stored,
+// exactly like the reference's assignments into float32 tensors; on the GPU these are the same
+// libdevice sin/cos that torch's CUDA kernels call.
+IVM_HD double ivm_cos(double a) { return cos(a); }
+IVM_HD double ivm_sin(double a) { return sin(a); }
+IVM_HD float ivm_cos(float a) { return cosf(a); }
+IVM_HD float ivm_sin(float a) { return sinf(a); }
+template <class F>
+IVM_HD void ivm_pose_matrices_t(const float *pose, F elevation, F heading, float *T, float *cs) {
+    const F ex = elevation + (F)3.141592653589793238462643383279502884;
+    const F cx = ivm_cos(ex), sx = ivm_sin(ex), cy = ivm_cos(heading), sy = ivm_sin(heading);
+    T[0] = (float)cy; T[1] = (float)(sx * sy); T[2] = (float)(cx * sy); T[3] = pose[0];
+    T[4] = 0.0f;      T[5] = (float)cx;        T[6] = (float)(-sx);     T[7] = pose[1];
+    T[8] = (float)(-sy); T[9] = (float)(cy * sx); T[10] = (float)(cy * cx); T[11] = pose[2];
+    const F a = -heading;
+    cs[0] = (float)ivm_cos(a); cs[1] = (float)ivm_sin(a);
+}
+IVM_HD void ivm_pose_matrices(const IvmParams &P, int b) {
+    if (P.orient_f64) {
+        const double *o = (const double *)P.orient;
+        ivm_pose_matrices_t<double>(P.pose + 3 * b, o[2 * b], o[2 * b + 1], P.T12_buf + 12 * b, P.cs_buf + 2 * b);
+    } else {
+        const float *o = (const float *)P.orient;
+        ivm_pose_matrices_t<float>(P.pose + 3 * b, o[2 * b], o[2 * b + 1], P.T12_buf + 12 * b, P.cs_buf + 2 * b);
     }
 }
 

@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(IVM_THREADS) k_prep(IvmParams P, int first_cal
             P.hkeys[i] = IVM_EMPTY_KEY; P.hxord[i] = IVM_EMPTY_KEY; P.hbest[i] = 0u;
         }
     }
+    if (P.orient != nullptr && b < P.B && threadIdx.x == 32) ivm_pose_matrices(P, b);
     if (b < P.maxB) {
         // an env that holds nothing can be re-centred freely (first use, or back from a pause)
         __shared__ int s_empty;
@@ -285,6 +286,11 @@ __global__ void __launch_bounds__(IVM_THREADS) k_raster(IvmParams P) {
     if (wn && (threadIdx.x & 31) == 0) atomicAdd(&P.g->stats[IVM_STAT_IN], (unsigned long long)wn);
 }
 
+__global__ void k_pose(IvmParams P) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < P.B) ivm_pose_matrices(P, b);
+}
+
 // ------------------------------------------------------------------ known-map store build
 __global__ void k_known_reset_env(IvmParams P, int b, long long n, int origin_r, int origin_c) {
     IvmEnv *e = &P.env[b];
@@ -494,6 +500,8 @@ static void carve(const ivm_config *c, void *ws, IvmParams *P, ivm_ctx *ctx, siz
     float *xs = cv.take<float>(c->width > 0 ? c->width : 1);
     float *ys = cv.take<float>(c->height > 0 ? c->height : 1);
     q.xs = xs; q.ys = ys;
+    q.T12_buf = cv.take<float>(12 * B);
+    q.cs_buf = cv.take<float>(2 * B);
     q.rowcount = cv.take<int32_t>(B * SR);
     q.colcount = cv.take<int32_t>(B * SC);
     q.segs = cv.take<int32_t>(16 * B);
@@ -662,18 +670,22 @@ static void launch_raster(ivm_ctx *ctx, const IvmParams &P, cudaStream_t st, boo
 
 int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const uint8_t *labels, const float *logits,
                        int32_t num_classes, uint8_t *labels_out, const float *T12, const float *pose, const float *cs,
-                       const uint8_t *masks, uint8_t *occ, uint8_t *sem, ivm_stream_t stream) {
+                       const void *orientation, int32_t orientation_is_f64, const uint8_t *masks, uint8_t *occ,
+                       uint8_t *sem, ivm_stream_t stream) {
     if (!ctx || ctx->cfg.mode != 0) return IVM_E_INVALID;
     if (num_envs < 1 || num_envs > ctx->cfg.max_envs) return IVM_E_INVALID;
-    if (!depth || !T12 || !pose || !cs || !masks || !occ || !sem) return IVM_E_INVALID;
+    if (!depth || !pose || !masks || !occ || !sem) return IVM_E_INVALID;
+    if (!orientation && (!T12 || !cs)) return IVM_E_INVALID;
     if (!labels && !(logits && labels_out && num_classes >= 1 && num_classes <= 256)) return IVM_E_INVALID;
     int rc = next_step(ctx);
     if (rc != IVM_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     IvmParams P = ctx->P;
     P.B = num_envs; P.step = ctx->step;
-    P.depth = depth; P.labels = labels ? labels : labels_out; P.T12 = T12; P.pose = pose; P.cs = cs; P.masks = masks;
+    P.depth = depth; P.labels = labels ? labels : labels_out; P.pose = pose; P.masks = masks;
     P.occ = occ; P.sem = sem;
+    if (orientation) { P.orient = orientation; P.orient_f64 = orientation_is_f64; P.T12 = P.T12_buf; P.cs = P.cs_buf; }
+    else { P.orient = nullptr; P.T12 = T12; P.cs = cs; }
     const int slot = timing_slot(ctx);
 
     const int nprep = num_envs > ctx->hi_water ? num_envs : ctx->hi_water;
@@ -751,14 +763,22 @@ int ivm_known_load(ivm_ctx *ctx, int32_t env, int64_t n, const float *xyz, const
     return IVM_OK;
 }
 
-int ivm_step_known(ivm_ctx *ctx, int32_t num_envs, const float *pose, const float *cs, uint8_t *occ, uint8_t *sem,
-                   ivm_stream_t stream) {
+int ivm_step_known(ivm_ctx *ctx, int32_t num_envs, const float *pose, const float *cs, const void *orientation,
+                   int32_t orientation_is_f64, uint8_t *occ, uint8_t *sem, ivm_stream_t stream) {
     if (!ctx || ctx->cfg.mode != 1) return IVM_E_INVALID;
-    if (num_envs < 1 || num_envs > ctx->cfg.max_envs || !pose || !cs || !occ || !sem) return IVM_E_INVALID;
+    if (num_envs < 1 || num_envs > ctx->cfg.max_envs || !pose || !occ || !sem) return IVM_E_INVALID;
+    if (!orientation && !cs) return IVM_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
     IvmParams P = ctx->P;
     P.B = num_envs; P.pose = pose; P.cs = cs; P.occ = occ; P.sem = sem;
     const int slot = timing_slot(ctx);
+    if (orientation) {
+        P.orient = orientation; P.orient_f64 = orientation_is_f64; P.cs = P.cs_buf;
+        T_BEGIN(0);
+        k_pose<<<(num_envs + 127) / 128, 128, 0, st>>>(P);
+        T_END(0);
+        ctx->launches += 1;
+    }
     T_BEGIN(4);
     launch_raster(ctx, P, st, true);
     T_END(4);

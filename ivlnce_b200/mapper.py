@@ -46,7 +46,10 @@ class EpisodesInfo:
     def __post_init__(self):
         self.env_names = np.asarray(self.env_names)
         self.not_done_masks = self.not_done_masks.squeeze(1)
-        self.indices = torch.arange(self.not_done_masks.shape[0], device=self.not_done_masks.device)
+
+    @property
+    def indices(self) -> torch.Tensor:  # built on demand: the hot path never needs it
+        return torch.arange(self.not_done_masks.shape[0], device=self.not_done_masks.device)
 
     def finished(self) -> torch.Tensor:
         return self.not_done_masks == self.EPISODE_FINISHED
@@ -352,7 +355,8 @@ class MappingModule(nn.Module):
                  compute_semantics: Optional[ComputeSemantics] = None, mode: str = "iterative",
                  maps_location: Optional[str] = None, max_envs: Optional[int] = None,
                  store_cells: int = DEFAULT_STORE_CELLS, known_capacity: int = DEFAULT_KNOWN_CAPACITY,
-                 host_trig: bool = False, raster_tile: int = 0):
+                 trig: str = "kernel", host_trig: bool = False, raster_tile: int = 0,
+                 track_start_state: bool = False):
         super().__init__()
         assert mode in ("iterative", "known")
         self.device = torch.device(device)
@@ -363,7 +367,13 @@ class MappingModule(nn.Module):
         self.maps_location = maps_location
         self.localize_robot = LocalizeRobot()
         self.map_memory = OccupancySemanticMapMemory()
-        self.host_trig = host_trig  # evaluate sin/cos on the host CPU (bit-identical to a CPU reference run)
+        # where sin/cos of the pose angles are evaluated:
+        #   "kernel": inside the prep kernel, in the angles' dtype (no torch launches per step);
+        #   "torch" : torch ops on the tensors' device (what the reference does on a GPU);
+        #   "host"  : torch ops on the host CPU (bit-identical to a CPU run of the reference; syncs).
+        self.trig = "host" if host_trig else trig
+        assert self.trig in ("kernel", "torch", "host")
+        self.track_start_state = track_start_state
         self._engine_args = dict(store_cells=store_cells, known_capacity=known_capacity, tile=raster_tile)
         self._engine: Optional[_MapEngine] = None
         self._initial_max_envs = max_envs
@@ -383,7 +393,20 @@ class MappingModule(nn.Module):
 
     def _matrices(self, state: RobotCurrentState):
         pose, elev, head = state.pose, state.elevation, state.heading
-        if self.host_trig:
+        if self.trig == "kernel":
+            pose32 = pose.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            if elev.dtype != head.dtype or head.dtype not in (torch.float32, torch.float64):
+                elev, head = elev.to(torch.float64), head.to(torch.float64)
+            n = elev.shape[0]
+            interleaved = (elev.device == self.device and head.device == self.device and elev.dim() == 1
+                           and head.data_ptr() - elev.data_ptr() == elev.element_size()
+                           and (n == 1 or (elev.stride(0) == 2 and head.stride(0) == 2)))
+            if interleaved:
+                orient = elev  # the two views of the [B,2] world_robot_orientation tensor: use it in place
+            else:
+                orient = torch.stack((elev, head), 1).to(self.device, non_blocking=True).contiguous()
+            return None, None, pose32, orient
+        if self.trig == "host":
             p, e, h = pose.detach().cpu(), elev.detach().cpu(), head.detach().cpu()
             T12 = camera_to_world_rows(p, e, h).to(self.device, non_blocking=True)
             cs = ego_rotation(h).to(self.device, non_blocking=True)
@@ -394,28 +417,32 @@ class MappingModule(nn.Module):
             T12 = camera_to_world_rows(pose, elev, head)
             cs = ego_rotation(head)
         pose32 = pose.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
-        return T12.contiguous(), cs.contiguous(), pose32
+        return T12.contiguous(), cs.contiguous(), pose32, None
 
     # -- forward
     @torch.no_grad()
     def forward(self, episodes_info: EpisodesInfo, observations: Observations,
                 robot_current_state: RobotCurrentState) -> OccupancySemanticMapMemory:
-        self.localize_robot(episodes_info, robot_current_state)
+        if self.track_start_state:
+            self.localize_robot(episodes_info, robot_current_state)
+        else:
+            self.localize_robot.current_state = robot_current_state
         B = episodes_info.num_envs
         eng = self.engine(B)
         lib = eng.lib
         with torch.cuda.device(self.device):
-            T12, cs, pose = self._matrices(robot_current_state)
+            T12, cs, pose, orient = self._matrices(robot_current_state)
+            self._keepalive = (T12, cs, pose, orient)
             if self.mode == "iterative":
-                self._forward_iterative(eng, B, episodes_info, observations, T12, cs, pose)
+                self._forward_iterative(eng, B, episodes_info, observations, T12, cs, pose, orient)
             else:
-                self._forward_known(eng, B, episodes_info, cs, pose)
+                self._forward_known(eng, B, episodes_info, cs, pose, orient)
         self._num_envs = B
         self.map_memory._occ = eng.occ[:B]
         self.map_memory._sem = eng.sem[:B]
         return self.map_memory
 
-    def _forward_iterative(self, eng, B, episodes_info, observations, T12, cs, pose):
+    def _forward_iterative(self, eng, B, episodes_info, observations, T12, cs, pose, orient):
         H, W = (int(v) for v in self.camera_parameters.features_spatial_dimensions)
         sem_mod = self.compute_semantics
         scores = None
@@ -442,14 +469,15 @@ class MappingModule(nn.Module):
             labels = labels.contiguous()
             assert labels.numel() == B * H * W
             labels_ptr = labels.data_ptr()
-        rc = eng.lib.ivm_step_iterative(eng.ctx, B, depth.data_ptr(), labels_ptr, logits_ptr, ncls,
-                                        eng.labels_out.data_ptr(), T12.data_ptr(), pose.data_ptr(), cs.data_ptr(),
-                                        masks.data_ptr(), eng.occ.data_ptr(), eng.sem.data_ptr(), eng.stream())
+        args = (eng.ctx, B, depth.data_ptr(), labels_ptr, logits_ptr, ncls, eng.labels_out.data_ptr(),
+                None if T12 is None else T12.data_ptr(), pose.data_ptr(), None if cs is None else cs.data_ptr(),
+                None if orient is None else orient.data_ptr(),
+                1 if (orient is not None and orient.dtype == torch.float64) else 0,
+                masks.data_ptr(), eng.occ.data_ptr(), eng.sem.data_ptr(), eng.stream())
+        rc = eng.lib.ivm_step_iterative(*args)
         if rc == 4:  # 2^24 - 1 steps: rebase the stamps and retry once
             _lib.check(eng.lib.ivm_rebase_stamps(eng.ctx, eng.stream()), eng.ctx, "ivm_rebase_stamps")
-            rc = eng.lib.ivm_step_iterative(eng.ctx, B, depth.data_ptr(), labels_ptr, logits_ptr, ncls,
-                                            eng.labels_out.data_ptr(), T12.data_ptr(), pose.data_ptr(), cs.data_ptr(),
-                                            masks.data_ptr(), eng.occ.data_ptr(), eng.sem.data_ptr(), eng.stream())
+            rc = eng.lib.ivm_step_iterative(*args)
         _lib.check(rc, eng.ctx, "ivm_step_iterative")
 
     # -- known-map mode
@@ -471,7 +499,7 @@ class MappingModule(nn.Module):
                                            o_r, o_c)
         return self._known_cache[env_name]
 
-    def _forward_known(self, eng, B, episodes_info, cs, pose):
+    def _forward_known(self, eng, B, episodes_info, cs, pose, orient):
         lib, st = eng.lib, eng.stream()
         for b in [b for b in self._known_order if b >= B]:      # clear_paused_episodes, mapper.py:315-318
             _lib.check(lib.ivm_known_clear(eng.ctx, b, st), eng.ctx, "ivm_known_clear")
@@ -487,8 +515,10 @@ class MappingModule(nn.Module):
                 self._known_order.remove(b)
             self._known_order.append(b)
             self._known_loaded[b] = name
-        _lib.check(lib.ivm_step_known(eng.ctx, B, pose.data_ptr(), cs.data_ptr(), eng.occ.data_ptr(),
-                                      eng.sem.data_ptr(), st), eng.ctx, "ivm_step_known")
+        _lib.check(lib.ivm_step_known(eng.ctx, B, pose.data_ptr(), None if cs is None else cs.data_ptr(),
+                                      None if orient is None else orient.data_ptr(),
+                                      1 if (orient is not None and orient.dtype == torch.float64) else 0,
+                                      eng.occ.data_ptr(), eng.sem.data_ptr(), st), eng.ctx, "ivm_step_known")
 
     # -- inspection
     def get_world_semantic_pointcloud(self) -> SemanticPointcloud:

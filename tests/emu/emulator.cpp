@@ -28,7 +28,7 @@ struct Emu {
     std::vector<IvmEdge> e1, e2;
     std::vector<unsigned long long> hkeys, hxord;
     std::vector<uint32_t> hbest;
-    std::vector<float> xs, ys;
+    std::vector<float> xs, ys, T12_buf, cs_buf;
     std::vector<IvmRecord> kpts;
     std::vector<uint32_t> koff;
 };
@@ -74,6 +74,8 @@ Emu *emu_create(int H, int W, const float *xs, const float *ys, float res, float
     P.e1 = m->e1.data(); P.e2 = m->e2.data(); P.ecap = ecap; P.segs = m->segs.data();
     P.hkeys = m->hkeys.data(); P.hbest = m->hbest.data(); P.hxord = m->hxord.data(); P.hmask = hs - 1;
     P.xs = m->xs.data(); P.ys = m->ys.data();
+    m->T12_buf.assign((size_t)12 * maxB, 0.f); m->cs_buf.assign((size_t)2 * maxB, 0.f);
+    P.T12_buf = m->T12_buf.data(); P.cs_buf = m->cs_buf.data();
     P.kpts = m->kpts.data(); P.koff = m->koff.data();
     return m;
 }
@@ -160,12 +162,18 @@ static void emu_raster(Emu *m, const IvmParams &P, bool known) {
 }
 
 int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels, const float *T12, const float *pose,
-                       const float *cs, const uint8_t *masks, uint8_t *occ, uint8_t *sem) {
+                       const float *cs, const void *orient, int orient_f64, const uint8_t *masks, uint8_t *occ,
+                       uint8_t *sem) {
     if (m->step >= 0xFFFFFFu) return 4;
     m->step += 1;
     IvmParams P = m->P;
     P.B = B; P.step = m->step; P.depth = depth; P.labels = labels; P.T12 = T12; P.pose = pose; P.cs = cs; P.masks = masks;
     P.occ = occ; P.sem = sem;
+    if (orient) {  // the K0 path that derives the matrices from the angles
+        P.orient = orient; P.orient_f64 = orient_f64; P.T12 = P.T12_buf; P.cs = P.cs_buf;
+        for (int b = 0; b < B; ++b) ivm_pose_matrices(P, b);
+        T12 = P.T12; cs = P.cs;
+    }
     // K0
     ivm_prep_global(P);
     const int nprep = B > m->hi_water ? B : m->hi_water;

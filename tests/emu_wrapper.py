@@ -36,7 +36,7 @@ def lib():
         L.emu_create.argtypes = [ctypes.c_int, ctypes.c_int, f32p, f32p] + [ctypes.c_float] * 4 + [ctypes.c_int] * 8 + [ctypes.c_longlong]
         L.emu_destroy.argtypes = [ctypes.c_void_p]
         L.emu_set_order.argtypes = [ctypes.c_void_p, ctypes.c_int]
-        L.emu_step_iterative.argtypes = [ctypes.c_void_p, ctypes.c_int, f32p, u8p, f32p, f32p, f32p, u8p, u8p, u8p]
+        L.emu_step_iterative.argtypes = [ctypes.c_void_p, ctypes.c_int, f32p, u8p, f32p, f32p, f32p, ctypes.c_void_p, ctypes.c_int, u8p, u8p, u8p]
         L.emu_known_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, f32p, u8p, ctypes.c_int, ctypes.c_int]
         L.emu_known_clear.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.emu_step_known.argtypes = [ctypes.c_void_p, ctypes.c_int, f32p, f32p, u8p, u8p]
@@ -55,7 +55,8 @@ def _p(a, ct):
 
 class EmuMapper:
     def __init__(self, height, width, vfov, map_m, resolution, max_envs, mode="iterative", store=1024,
-                 tile=32, known_clouds=None, known_capacity=1 << 16, order=0):
+                 tile=32, known_clouds=None, known_capacity=1 << 16, order=0, kernel_trig=False):
+        self.kernel_trig = kernel_trig
         self.H, self.W = height, width
         self.R = math.ceil(map_m / resolution)
         self.C = math.ceil(map_m / resolution)
@@ -96,8 +97,11 @@ class EmuMapper:
             T12 = np.ascontiguousarray(camera_to_world_rows(torch.from_numpy(pose), ori[:, 0], ori[:, 1]).numpy())
             depth = np.ascontiguousarray(depth, dtype=np.float32)
             labels = np.ascontiguousarray(labels, dtype=np.uint8)
+            o = np.ascontiguousarray(orientation)
             rc = L.emu_step_iterative(self._h, B, _p(depth, ctypes.c_float), _p(labels, ctypes.c_uint8),
                                       _p(T12, ctypes.c_float), _p(pose, ctypes.c_float), _p(cs, ctypes.c_float),
+                                      o.ctypes.data_as(ctypes.c_void_p) if self.kernel_trig else None,
+                                      1 if o.dtype == np.float64 else 0,
                                       _p(masks, ctypes.c_uint8), _p(occ, ctypes.c_uint8), _p(sem, ctypes.c_uint8))
             assert rc == 0
         else:

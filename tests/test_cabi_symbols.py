@@ -41,7 +41,7 @@ def test_workspace_size_and_argument_checks():
     ctx = ctypes.c_void_p()
     assert L.ivm_create(ctypes.byref(cfg), None, n, ctypes.byref(ctx)) == 1       # IVM_E_INVALID: no workspace
     assert L.ivm_create(ctypes.byref(cfg), 4096 + 8, n, ctypes.byref(ctx)) == 2   # IVM_E_WORKSPACE: misaligned
-    assert L.ivm_step_iterative(None, 1, None, None, None, 0, None, None, None, None, None, None, None, None) == 1
+    assert L.ivm_step_iterative(None, 1, None, None, None, 0, None, None, None, None, None, 0, None, None, None, None) == 1
 
 
 def test_config_struct_matches_header_layout():
