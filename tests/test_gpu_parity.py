@@ -73,6 +73,17 @@ def test_device_trig_f64_matches():
         assert np.array_equal(o, scn["ref_occupancy"][t]) and np.array_equal(s, scn["ref_semantic"][t])
 
 
+@pytest.mark.parametrize("name", ["iid_f64", "scene_overlap", "single_long", "identical_envs", "degenerate", "known_map"])
+def test_kernel_trig_f64_matches(name):
+    """Default mode: pose matrices derived inside the prep kernel from the float64 angles."""
+    scn = load_golden(name)
+    assert scn["orientation"].dtype == np.float64
+    cs, outs, _ = _run_cuda(scn, trig="kernel")
+    for t, (o, s) in enumerate(outs):
+        B = o.shape[0]
+        assert np.array_equal(o, scn["ref_occupancy"][t, :B]) and np.array_equal(s, scn["ref_semantic"][t, :B]), t
+
+
 def test_full_size_against_oracle():
     """BASELINE config 1 shape (256x256 depth, 27 labels, 0.05 m cells) on 3 envs, 8 steps."""
     from ivlnce_b200.synthetic import ScenarioConfig, make_scenario
