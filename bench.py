@@ -62,12 +62,15 @@ def parse_args():
 
 # ------------------------------------------------------------------------------------------ inputs
 def make_poses(cfg, steps, seed):
-    """Random walk of 0.25 m forward steps / 15 degree turns per env; envs start
-    40 m apart.  pose f32 [S,B,3], orientation f64 [S,B,2], masks u8 [S,B] (0 only at t = 0)."""
+    """Random walk of 0.25 m forward steps / 15 degree turns per env, kept within 8 m
+    of its start (a house-sized area).  Every env lives in its own scene, and scene coordinates all lie near
+    the origin (as in MP3D), so the envs' world coordinates overlap -- this keeps the reference's de-dup key
+    space (batch-global bbox x envs, mapper.py:468-469) at a realistic size.
+    pose f32 [S,B,3], orientation f64 [S,B,2], masks u8 [S,B] (0 only at t = 0)."""
     from ivlnce_b200.synthetic import ScenarioConfig, random_walk, reset_masks
 
     sc = ScenarioConfig(num_envs=cfg["envs"], height=cfg["H"], width=cfg["W"], steps=steps, resolution=cfg["res"],
-                        map_meters=cfg["map_m"], num_labels=cfg["classes"], seed=seed)
+                        map_meters=cfg["map_m"], num_labels=cfg["classes"], seed=seed, env_spacing=0.0, roam_radius=8.0)
     pose, orient = random_walk(sc, np.random.default_rng(seed))
     return pose, orient, reset_masks(sc)
 

@@ -44,6 +44,7 @@ class ScenarioConfig:
     turn_degrees: float = 15.0
     sensor_height: float = 1.25
     elevation: float = 0.0
+    roam_radius: Optional[float] = None  # keep the walk within this distance of its start (a house-sized area)
     seed: int = 1000
 
 
@@ -151,6 +152,7 @@ def random_walk(cfg: ScenarioConfig, rng: np.random.Generator, rooms=None):
                     break
                 x = rng.uniform(-room.half[0] + 0.5, room.half[0] - 0.5)
                 z = rng.uniform(-room.half[1] + 0.5, room.half[1] - 0.5)
+        x0, z0 = x, z
         for t in range(T):
             pose[t, b] = (x + ox, cfg.sensor_height, z + oz)
             heading[t, b] = h
@@ -158,7 +160,10 @@ def random_walk(cfg: ScenarioConfig, rng: np.random.Generator, rooms=None):
             if a <= 1:
                 nx = x - math.sin(h) * cfg.forward_step
                 nz = z - math.cos(h) * cfg.forward_step
-                if room is None or room.inside_free_space(nx, nz):
+                inside = True
+                if cfg.roam_radius is not None:
+                    inside = (nx - x0) ** 2 + (nz - z0) ** 2 <= cfg.roam_radius ** 2
+                if inside and (room is None or room.inside_free_space(nx, nz)):
                     x, z = nx, nz
                 else:
                     h += 2 * turn
