@@ -124,7 +124,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -266,14 +266,20 @@ def main():
 
     # ---- device-resident throughput ("value")
     t = 0
-    for _ in range(max(Wm, 3)):
-        step(t); t += 1
+    sampler = ClockSampler(local_rank)
+    sampler.start()   # sampled from the warm-up through the timed region (the timed region alone lasts ~tens of ms)
+    t_w = time.perf_counter()
+    while True:       # at least Wm warm-up steps and ~0.4 s of load so that clocks settle and are sampled
+        for _ in range(max(Wm, 3)):
+            step(t % (Wm + 8)); t += 1
+        torch.cuda.synchronize(dev)
+        if time.perf_counter() - t_w > 0.4:
+            break
+    t = Wm + 8
     mm.check_errors()
     launches0 = mm.kernel_launches()
-    sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler.start()
     ev0.record()
     for _ in range(K):
         step(t); t += 1

@@ -109,7 +109,8 @@ struct IvmGlobal {
     uint32_t any_dirty;
     uint32_t n_seg;
     uint32_t pad1[3];
-    unsigned long long stats[IVM_NSTATS];
+    unsigned long long acc_valid, acc_local;  // per-step accumulators (K1 / K2+F), published and zeroed by F
+    unsigned long long stats[IVM_NSTATS];     // published figures of the last step; stats[IN] accumulates in K4
 };
 
 struct IvmParams {
@@ -235,8 +236,9 @@ IVM_HD unsigned long long ivm_cand_key(float y, uint32_t pix) {
     return ((unsigned long long)ivm_orderable(y) << 32) | (unsigned long long)(0xFFFFFFFFu - pix);
 }
 
-IVM_HD bool ivm_store_index(const IvmParams &P, const IvmEnv &e, int b, int32_t r, int32_t c, size_t &idx) {
-    const int32_t rr = r - e.origin_r, cc = c - e.origin_c;
+IVM_HD bool ivm_store_index(const IvmParams &P, int32_t origin_r, int32_t origin_c, int b, int32_t r, int32_t c,
+                            size_t &idx) {
+    const int32_t rr = r - origin_r, cc = c - origin_c;
     if (rr < 0 || rr >= P.SR || cc < 0 || cc >= P.SC) return false;
     idx = ((size_t)b * P.SR + (size_t)rr) * P.SC + (size_t)cc;
     return true;
@@ -248,14 +250,33 @@ IVM_HD unsigned long long ivm_list_key(int b, int32_t r, int32_t c, int32_t rmin
     return (unsigned long long)((long long)b * (Rx * Cx) + (long long)(r - rmin) * Cx + (long long)(c - cmin));
 }
 
+// Per-thread accumulator of newly occupied cells (flushed to the env's count / bbox by the caller:
+// warp + block reduction on the device, so that a step issues a handful of same-address atomics
+// per CTA instead of five per new cell).
+struct IvmBoxAcc {
+    int32_t rmin, rmax, cmin, cmax, n;
+    IVM_HD void clear() { rmin = INT32_MAX; rmax = INT32_MIN; cmin = INT32_MAX; cmax = INT32_MIN; n = 0; }
+    IVM_HD void add(int32_t r, int32_t c) {
+        rmin = r < rmin ? r : rmin; rmax = r > rmax ? r : rmax;
+        cmin = c < cmin ? c : cmin; cmax = c > cmax ? c : cmax; ++n;
+    }
+};
+template <class A>
+IVM_HD void ivm_box_flush(IvmEnv *e, const IvmBoxAcc &a) {
+    if (a.n <= 0) return;
+    A::add_i(&e->count, a.n);
+    A::min_i(&e->rmin, a.rmin); A::max_i(&e->rmax, a.rmax);
+    A::min_i(&e->cmin, a.cmin); A::max_i(&e->cmax, a.cmax);
+}
+
 // Insert the frame/edge survivor into the world store ("world.concatenate(local)" +
 // second keep_highest for a cell that does not collide): the older record wins ties
 // because world points precede local points in the list (mapper.py:226-230, 299-308).
 template <class A>
 IVM_HD void ivm_merge_into_world(const IvmParams &P, int b, size_t idx, int32_t r, int32_t c, float x, float y, float z,
-                                 uint32_t label) {
-    IvmEnv *e = &P.env[b];
-    IvmRecord old = P.store[idx];
+                                 uint32_t label, IvmBoxAcc &acc) {
+    const IvmEnv *e = &P.env[b];
+    const IvmRecord old = P.store[idx];
     const bool live = ivm_live(old.meta, e->reset_stamp);
     if (live && !(y > old.y)) return;
     IvmRecord rec;
@@ -264,24 +285,39 @@ IVM_HD void ivm_merge_into_world(const IvmParams &P, int b, size_t idx, int32_t 
     if (!live) {
         A::add_i(&P.rowcount[(size_t)b * P.SR + (r - e->origin_r)], 1);
         A::add_i(&P.colcount[(size_t)b * P.SC + (c - e->origin_c)], 1);
-        A::add_i(&e->count, 1);
-        A::min_i(&e->rmin, r); A::max_i(&e->rmax, r);
-        A::min_i(&e->cmin, c); A::max_i(&e->cmax, c);
+        acc.add(r, c);
     }
 }
 
 // ---------------------------------------------------------------------------
-// K0: per-env preparation.  Envs whose mask is 0 (episode/tour finished,
-// mapper.py:320-326) or whose index is >= B (paused, mapper.py:315-318) are
-// wiped in O(1) by advancing reset_stamp; the store window is re-centred on the
-// pose of a reset env.  Called by every thread of the env's CTA.
+// Per-env preparation, folded into the head of the ingest-scatter kernel.  Envs whose mask is 0
+// (episode/tour finished, mapper.py:320-326), whose index is >= B (paused, mapper.py:315-318) or
+// that hold nothing are wiped in O(1) by advancing reset_stamp, and the store window is
+// re-centred on the pose.  Every CTA of an env DECIDES locally (same inputs, same answer);
+// only the env's first CTA PUBLISHES the new state, which nobody reads before the next kernel.
+struct IvmEnvPrep {
+    int32_t reset;
+    int32_t origin_r, origin_c;
+};
+IVM_HD IvmEnvPrep ivm_env_decide(const IvmParams &P, int b) {  // b < P.B
+    const IvmEnv *e = &P.env[b];
+    IvmEnvPrep q;
+    q.reset = (P.masks[b] == 0) || (e->count <= 0);
+    if (q.reset) {
+        const float pr = rintf(ivm_div(P.pose[3 * b + 2], P.half_res));
+        const float pc = rintf(ivm_div(P.pose[3 * b + 0], P.half_res));
+        q.origin_r = (fabsf(pr) < 1.0e9f ? (int32_t)pr : 0) - P.SR / 2;
+        q.origin_c = (fabsf(pc) < 1.0e9f ? (int32_t)pc : 0) - P.SC / 2;
+    } else {
+        q.origin_r = e->origin_r; q.origin_c = e->origin_c;
+    }
+    return q;
+}
+// called by all `nthreads` threads of the publishing CTA; for b >= P.B the env is simply wiped
 template <class A>
-IVM_HD void ivm_prep_env(const IvmParams &P, int b, int tid, int nthreads, bool empty) {
-    // `empty`: the env holds no record (first use, or back from a pause); its window may be
-    // re-centred freely.  Must be evaluated by the caller BEFORE any thread runs this function.
+IVM_HD void ivm_env_publish(const IvmParams &P, int b, const IvmEnvPrep &q, int tid, int nthreads) {
     const bool dropped = b >= P.B;
-    const bool reset = dropped || empty || P.masks[b] == 0;
-    if (!reset) return;
+    if (!dropped && !q.reset) return;
     for (int i = tid; i < P.SR; i += nthreads) P.rowcount[(size_t)b * P.SR + i] = 0;
     for (int i = tid; i < P.SC; i += nthreads) P.colcount[(size_t)b * P.SC + i] = 0;
     if (tid == 0) {
@@ -290,12 +326,7 @@ IVM_HD void ivm_prep_env(const IvmParams &P, int b, int tid, int nthreads, bool 
         e->count = 0;
         e->rmin = INT32_MAX; e->rmax = INT32_MIN; e->cmin = INT32_MAX; e->cmax = INT32_MIN;
         e->dirty = 0;
-        if (!dropped) {
-            const float pr = rintf(ivm_div(P.pose[3 * b + 2], P.half_res));
-            const float pc = rintf(ivm_div(P.pose[3 * b + 0], P.half_res));
-            e->origin_r = (fabsf(pr) < 1.0e9f ? (int32_t)pr : 0) - P.SR / 2;
-            e->origin_c = (fabsf(pc) < 1.0e9f ? (int32_t)pc : 0) - P.SC / 2;
-        }
+        if (!dropped) { e->origin_r = q.origin_r; e->origin_c = q.origin_c; }
     }
 }
 
@@ -318,22 +349,23 @@ IVM_HD void ivm_pose_matrices_t(const float *pose, F elevation, F heading, float
     const F a = -heading;
     cs[0] = (float)ivm_cos(a); cs[1] = (float)ivm_sin(a);
 }
-IVM_HD void ivm_pose_matrices(const IvmParams &P, int b) {
+IVM_HD void ivm_pose_matrices(const IvmParams &P, int b, float *T, float *cs) {
     if (P.orient_f64) {
         const double *o = (const double *)P.orient;
-        ivm_pose_matrices_t<double>(P.pose + 3 * b, o[2 * b], o[2 * b + 1], P.T12_buf + 12 * b, P.cs_buf + 2 * b);
+        ivm_pose_matrices_t<double>(P.pose + 3 * b, o[2 * b], o[2 * b + 1], T, cs);
     } else {
         const float *o = (const float *)P.orient;
-        ivm_pose_matrices_t<float>(P.pose + 3 * b, o[2 * b], o[2 * b + 1], P.T12_buf + 12 * b, P.cs_buf + 2 * b);
+        ivm_pose_matrices_t<float>(P.pose + 3 * b, o[2 * b], o[2 * b + 1], T, cs);
     }
 }
 
-IVM_HD void ivm_prep_global(const IvmParams &P) {
-    IvmGlobal *g = P.g;
+// Per-step scratch of IvmGlobal: reset once at context start and then by the fix-up program at
+// the end of every step (so that no kernel has to run before the ingest of the next step).
+IVM_HD void ivm_reset_step_globals(IvmGlobal *g) {
     g->loc[0] = INT32_MAX; g->loc[1] = INT32_MIN; g->loc[2] = INT32_MAX; g->loc[3] = INT32_MIN;
     g->n_e1 = 0; g->n_e2 = 0; g->n_seg = 0; g->any_dirty = 0;
-    g->stats[IVM_STAT_VALID] = 0; g->stats[IVM_STAT_LOCAL] = 0; g->stats[IVM_STAT_IN] = 0;
-    g->stats[IVM_STAT_E1] = 0; g->stats[IVM_STAT_E2] = 0;
+    g->acc_valid = 0; g->acc_local = 0;
+    g->stats[IVM_STAT_IN] = 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -344,15 +376,14 @@ IVM_HD void ivm_prep_global(const IvmParams &P) {
 // merged into the world store directly.  Returns 1 if the pixel was a
 // non-edge winner (for the LOCAL statistic).
 template <class A>
-IVM_HD int ivm_resolve_pixel(const IvmParams &P, int b, uint32_t pix, const IvmPoint &p, uint32_t label) {
-    const IvmEnv &e = P.env[b];
+IVM_HD int ivm_resolve_pixel(const IvmParams &P, int b, uint32_t pix, const IvmPoint &p, uint32_t label,
+                             const int32_t *loc, int32_t origin_r, int32_t origin_c, IvmBoxAcc &acc) {
     size_t idx;
-    if (!ivm_store_index(P, e, b, p.r, p.c, idx)) return 0;  // overflow was flagged in K1a
+    if (!ivm_store_index(P, origin_r, origin_c, b, p.r, p.c, idx)) return 0;  // overflow was flagged by the scatter
     const unsigned long long cand = P.cand[idx];
     if ((uint32_t)(cand & 0xFFFFFFFFull) != 0xFFFFFFFFu - pix || (uint32_t)(cand >> 32) != ivm_orderable(p.y)) return 0;
     P.cand[idx] = 0ull;  // leave the scratch plane clean for the next step
-    const IvmGlobal *g = P.g;
-    const bool edge = p.r == g->loc[0] || p.r == g->loc[1] || p.c == g->loc[2] || p.c == g->loc[3];
+    const bool edge = p.r == loc[0] || p.r == loc[1] || p.c == loc[2] || p.c == loc[3];
     if (edge) {
         const uint32_t k = A::add_u(&P.g->n_e1, 1u);
         if (k >= P.ecap) { A::or_u(&P.g->err, IVM_ERR_EDGE_OVERFLOW); return 0; }
@@ -364,7 +395,7 @@ IVM_HD int ivm_resolve_pixel(const IvmParams &P, int b, uint32_t pix, const IvmP
         P.e1[k] = ed;
         return 0;
     }
-    ivm_merge_into_world<A>(P, b, idx, p.r, p.c, p.x, p.y, p.z, label);
+    ivm_merge_into_world<A>(P, b, idx, p.r, p.c, p.x, p.y, p.z, label, acc);
     return 1;
 }
 
@@ -378,10 +409,39 @@ IVM_HD uint32_t ivm_mix(unsigned long long k) {
     return (uint32_t)k;
 }
 
+// Block-shared scratch of the fix-up program (shared memory on the device, plain arrays in the
+// emulator).  key/ord/xo serve the small-class fast path.
+struct IvmFixScratch {
+    unsigned long long *key, *xo;  // [cap]
+    uint32_t *ord;                 // [cap]
+    uint32_t cap;
+    int32_t *ibuf;                 // [8]: 0..3 world bbox, 4 segment count, 5 any-dirty
+    unsigned long long *lbuf;      // [2]: 0 live-record total
+};
+
 // on return E[i].slot = 0xFFFFFFFF for losers, anything else for winners
 template <class A>
 IVM_HD void ivm_resolve_classes(const IvmParams &P, IvmEdge *E, uint32_t n, int32_t rmin, int32_t cmin, long long Rx,
-                                long long Cx, int tid, int nthreads) {
+                                long long Cx, const IvmFixScratch &S, int tid, int nthreads) {
+    if (n <= S.cap) {
+        // few entries (the usual case: a bbox edge holds a handful of points): all-pairs in block memory
+        for (uint32_t i = tid; i < n; i += nthreads) {
+            S.key[i] = ivm_list_key(E[i].b, E[i].r, E[i].c, rmin, cmin, Rx, Cx);
+            S.ord[i] = ivm_orderable(E[i].y);
+            S.xo[i] = E[i].xorder;
+        }
+        A::sync();
+        for (uint32_t i = tid; i < n; i += nthreads) {
+            const unsigned long long ki = S.key[i], xi = S.xo[i];
+            const uint32_t oi = S.ord[i];
+            bool lose = false;
+            for (uint32_t j = 0; j < n; ++j)
+                if (S.key[j] == ki && (S.ord[j] > oi || (S.ord[j] == oi && S.xo[j] < xi))) { lose = true; break; }
+            E[i].slot = lose ? 0xFFFFFFFFu : 0u;
+        }
+        A::sync();
+        return;
+    }
     for (uint32_t i = tid; i < n; i += nthreads) {
         const unsigned long long k = ivm_list_key(E[i].b, E[i].r, E[i].c, rmin, cmin, Rx, Cx);
         uint32_t s = ivm_mix(k) & P.hmask;
@@ -415,10 +475,10 @@ IVM_HD void ivm_resolve_classes(const IvmParams &P, IvmEdge *E, uint32_t n, int3
 
 // scan one store cell of an edge line; live records join the stage-2 edge list
 template <class A>
-IVM_HD void ivm_scan_edge_cell(const IvmParams &P, int b, int32_t r, int32_t c) {
+IVM_HD void ivm_scan_edge_cell(const IvmParams &P, int b, int32_t r, int32_t c, const int32_t *loc) {
     const IvmEnv &e = P.env[b];
     size_t idx;
-    if (!ivm_store_index(P, e, b, r, c, idx)) return;
+    if (!ivm_store_index(P, e.origin_r, e.origin_c, b, r, c, idx)) return;
     const IvmRecord rec = P.store[idx];
     if (!ivm_live(rec.meta, e.reset_stamp)) return;
     const uint32_t k = A::add_u(&P.g->n_e2, 1u);
@@ -432,8 +492,7 @@ IVM_HD void ivm_scan_edge_cell(const IvmParams &P, int b, int32_t r, int32_t c) 
     // the order of the previous sort (previous stage-2 key), fresh ones follow in
     // frame-key order (mapper.py:226-230, 471-474).
     if (fresh)
-        ed.xorder = (1ull << 62) | ivm_list_key(b, r, c, g->loc[0], g->loc[2], (long long)g->loc[1] - g->loc[0],
-                                                (long long)g->loc[3] - g->loc[2]);
+        ed.xorder = (1ull << 62) | ivm_list_key(b, r, c, loc[0], loc[2], (long long)loc[1] - loc[0], (long long)loc[3] - loc[2]);
     else
         ed.xorder = ivm_list_key(b, r, c, g->prev_rmin, g->prev_cmin, g->prev_R, g->prev_C);
     P.e2[k] = ed;
@@ -441,116 +500,131 @@ IVM_HD void ivm_scan_edge_cell(const IvmParams &P, int b, int32_t r, int32_t c) 
 
 // F: the edge fix-up of both de-dup stages + bbox bookkeeping, one thread block.
 template <class A>
-IVM_HD void ivm_fixup_program(const IvmParams &P, int tid, int nthreads) {
+IVM_HD void ivm_fixup_program(const IvmParams &P, const IvmFixScratch &S, int tid, int nthreads) {
     IvmGlobal *g = P.g;
-    // ---- stage 1: collisions on the frame bbox edge (mapper.py:840-842)
     const uint32_t n1 = g->n_e1 < P.ecap ? g->n_e1 : P.ecap;
+    const int32_t loc[4] = {g->loc[0], g->loc[1], g->loc[2], g->loc[3]};
+    if (tid == 0) {
+        S.ibuf[0] = INT32_MAX; S.ibuf[1] = INT32_MIN; S.ibuf[2] = INT32_MAX; S.ibuf[3] = INT32_MIN;
+        S.ibuf[4] = 0; S.ibuf[5] = 0; S.lbuf[0] = 0ull;
+    }
+    // ---- stage 1: collisions on the frame bbox edge (mapper.py:840-842)
     if (n1 > 0) {
-        ivm_resolve_classes<A>(P, P.e1, n1, g->loc[0], g->loc[2], (long long)g->loc[1] - g->loc[0],
-                               (long long)g->loc[3] - g->loc[2], tid, nthreads);
+        ivm_resolve_classes<A>(P, P.e1, n1, loc[0], loc[2], (long long)loc[1] - loc[0], (long long)loc[3] - loc[2], S, tid,
+                               nthreads);
         for (uint32_t i = tid; i < n1; i += nthreads) {
             const IvmEdge ed = P.e1[i];
             if (ed.slot == 0xFFFFFFFFu) continue;
-            A::add_ull(&g->stats[IVM_STAT_LOCAL], 1ull);
-            ivm_merge_into_world<A>(P, ed.b, (size_t)ed.addr, ed.r, ed.c, ed.x, ed.y, ed.z, ed.label);
+            A::add_ull(&g->acc_local, 1ull);
+            IvmBoxAcc acc;
+            acc.clear();
+            ivm_merge_into_world<A>(P, ed.b, (size_t)ed.addr, ed.r, ed.c, ed.x, ed.y, ed.z, ed.label, acc);
+            ivm_box_flush<A>(&P.env[ed.b], acc);
         }
-        if (tid == 0) g->stats[IVM_STAT_E1] = n1;
     }
     A::sync();
-    // ---- stage-2 bbox over all live records of all envs (mapper.py:461-469 on world+local)
-    if (tid == 0) { g->glob[0] = INT32_MAX; g->glob[1] = INT32_MIN; g->glob[2] = INT32_MAX; g->glob[3] = INT32_MIN; }
-    A::sync();
+    // ---- stage-2 bbox over all live records of all envs (mapper.py:461-469 on world + frame survivors)
     for (int b = tid; b < P.B; b += nthreads) {
         const IvmEnv &e = P.env[b];
         if (e.count > 0) {
-            A::min_i(&g->glob[0], e.rmin); A::max_i(&g->glob[1], e.rmax);
-            A::min_i(&g->glob[2], e.cmin); A::max_i(&g->glob[3], e.cmax);
+            A::min_i(&S.ibuf[0], e.rmin); A::max_i(&S.ibuf[1], e.rmax);
+            A::min_i(&S.ibuf[2], e.cmin); A::max_i(&S.ibuf[3], e.cmax);
         }
     }
     A::sync();
-    const int32_t grmin = g->glob[0], grmax = g->glob[1], gcmin = g->glob[2], gcmax = g->glob[3];
-    if (grmin > grmax) {  // nothing alive: the reference skips keep_highest on an empty cloud
-        if (tid == 0) { g->prev_valid = 0; g->stats[IVM_STAT_WORLD] = 0; }
-        return;
-    }
-    // ---- which edge lines hold records?  an env has cells on a global edge line only
-    //      if its own bbox touches that line.
-    for (int b = tid; b < P.B; b += nthreads) {
-        const IvmEnv &e = P.env[b];
-        if (e.count <= 0) continue;
-        const bool t0 = e.rmin == grmin, t1 = e.rmax == grmax && grmax != grmin;
-        const bool t2 = e.cmin == gcmin, t3 = e.cmax == gcmax && gcmax != gcmin;
-        const int lines[4] = {grmin, grmax, gcmin, gcmax};
-        const bool touch[4] = {t0, t1, t2, t3};
-        for (int s = 0; s < 4; ++s)
-            if (touch[s]) {
-                const uint32_t k = A::add_u(&g->n_seg, 1u);
-                P.segs[4 * k + 0] = b; P.segs[4 * k + 1] = s >> 1; P.segs[4 * k + 2] = lines[s]; P.segs[4 * k + 3] = 0;
-            }
-    }
-    A::sync();
-    const uint32_t nseg = g->n_seg;
-    for (uint32_t q = 0; q < nseg; ++q) {
-        const int b = P.segs[4 * q + 0], is_col = P.segs[4 * q + 1], line = P.segs[4 * q + 2];
-        const IvmEnv &e = P.env[b];
-        if (!is_col) {
-            for (int32_t c = e.cmin + tid; c <= e.cmax; c += nthreads) ivm_scan_edge_cell<A>(P, b, line, c);
-        } else {
-            for (int32_t r = e.rmin + tid; r <= e.rmax; r += nthreads)
-                if (r != grmin && r != grmax) ivm_scan_edge_cell<A>(P, b, r, line);  // corners belong to the row scans
-        }
-    }
-    A::sync();
-    // ---- stage 2: collisions on the world bbox edge (mapper.py:844-847)
-    const uint32_t n2 = g->n_e2 < P.ecap ? g->n_e2 : P.ecap;
-    if (n2 > 1) {
-        ivm_resolve_classes<A>(P, P.e2, n2, grmin, gcmin, (long long)grmax - grmin, (long long)gcmax - gcmin, tid, nthreads);
-        for (uint32_t i = tid; i < n2; i += nthreads) {
-            const IvmEdge ed = P.e2[i];
-            if (ed.slot != 0xFFFFFFFFu) continue;
-            IvmEnv *e = &P.env[ed.b];
-            P.store[(size_t)ed.addr].meta = 0u;  // merged away for good
-            A::add_i(&P.rowcount[(size_t)ed.b * P.SR + (ed.r - e->origin_r)], -1);
-            A::add_i(&P.colcount[(size_t)ed.b * P.SC + (ed.c - e->origin_c)], -1);
-            A::add_i(&e->count, -1);
-            e->dirty = 1;
-            g->any_dirty = 1u;
-            A::add_ull(&g->stats[IVM_STAT_MERGED], 1ull);
-        }
-    }
-    A::sync();
-    if (tid == 0) g->stats[IVM_STAT_E2] = n2;
-    // ---- rebuild the bbox of envs that lost records
-    if (g->any_dirty) {
+    const int32_t grmin = S.ibuf[0], grmax = S.ibuf[1], gcmin = S.ibuf[2], gcmax = S.ibuf[3];
+    const bool alive = grmin <= grmax;  // else nothing alive: the reference skips keep_highest on an empty cloud
+    uint32_t n2 = 0;
+    if (alive) {
+        // ---- which edge lines hold records?  an env has cells on a global edge line only if its own
+        //      bbox touches that line.
         for (int b = tid; b < P.B; b += nthreads) {
-            IvmEnv *e = &P.env[b];
-            if (e->dirty) { e->rmin = INT32_MAX; e->rmax = INT32_MIN; e->cmin = INT32_MAX; e->cmax = INT32_MIN; }
+            const IvmEnv &e = P.env[b];
+            if (e.count <= 0) continue;
+            const int lines[4] = {grmin, grmax, gcmin, gcmax};
+            const bool touch[4] = {e.rmin == grmin, e.rmax == grmax && grmax != grmin, e.cmin == gcmin,
+                                   e.cmax == gcmax && gcmax != gcmin};
+            for (int s = 0; s < 4; ++s)
+                if (touch[s]) {
+                    const int k = (int)A::add_u((uint32_t *)&S.ibuf[4], 1u);
+                    P.segs[4 * k + 0] = b; P.segs[4 * k + 1] = s >> 1; P.segs[4 * k + 2] = lines[s]; P.segs[4 * k + 3] = 0;
+                }
         }
         A::sync();
-        const long long per_env = (long long)P.SR + P.SC;
-        for (long long i = tid; i < per_env * P.B; i += nthreads) {
-            const int b = (int)(i / per_env);
-            IvmEnv *e = &P.env[b];
-            if (!e->dirty) continue;
-            const int j = (int)(i - (long long)b * per_env);
-            if (j < P.SR) {
-                if (P.rowcount[(size_t)b * P.SR + j] > 0) { A::min_i(&e->rmin, e->origin_r + j); A::max_i(&e->rmax, e->origin_r + j); }
+        const int nseg = S.ibuf[4];
+        for (int q = 0; q < nseg; ++q) {
+            const int b = P.segs[4 * q + 0], is_col = P.segs[4 * q + 1], line = P.segs[4 * q + 2];
+            const IvmEnv &e = P.env[b];
+            if (!is_col) {
+                for (int32_t c = e.cmin + tid; c <= e.cmax; c += nthreads) ivm_scan_edge_cell<A>(P, b, line, c, loc);
             } else {
-                const int jc = j - P.SR;
-                if (P.colcount[(size_t)b * P.SC + jc] > 0) { A::min_i(&e->cmin, e->origin_c + jc); A::max_i(&e->cmax, e->origin_c + jc); }
+                for (int32_t r = e.rmin + tid; r <= e.rmax; r += nthreads)
+                    if (r != grmin && r != grmax) ivm_scan_edge_cell<A>(P, b, r, line, loc);  // corners belong to the row scans
             }
         }
         A::sync();
-        for (int b = tid; b < P.B; b += nthreads) P.env[b].dirty = 0;
+        // ---- stage 2: collisions on the world bbox edge (mapper.py:844-847)
+        n2 = g->n_e2 < P.ecap ? g->n_e2 : P.ecap;
+        if (n2 > 1) {
+            ivm_resolve_classes<A>(P, P.e2, n2, grmin, gcmin, (long long)grmax - grmin, (long long)gcmax - gcmin, S, tid,
+                                   nthreads);
+            for (uint32_t i = tid; i < n2; i += nthreads) {
+                const IvmEdge ed = P.e2[i];
+                if (ed.slot != 0xFFFFFFFFu) continue;
+                IvmEnv *e = &P.env[ed.b];
+                P.store[(size_t)ed.addr].meta = 0u;  // merged away for good
+                A::add_i(&P.rowcount[(size_t)ed.b * P.SR + (ed.r - e->origin_r)], -1);
+                A::add_i(&P.colcount[(size_t)ed.b * P.SC + (ed.c - e->origin_c)], -1);
+                A::add_i(&e->count, -1);
+                e->dirty = 1;
+                S.ibuf[5] = 1;
+                A::add_ull(&g->stats[IVM_STAT_MERGED], 1ull);
+            }
+            A::sync();
+            // ---- rebuild the bbox of envs that lost records
+            if (S.ibuf[5]) {
+                for (int b = tid; b < P.B; b += nthreads) {
+                    IvmEnv *e = &P.env[b];
+                    if (e->dirty) { e->rmin = INT32_MAX; e->rmax = INT32_MIN; e->cmin = INT32_MAX; e->cmax = INT32_MIN; }
+                }
+                A::sync();
+                const long long per_env = (long long)P.SR + P.SC;
+                for (long long i = tid; i < per_env * P.B; i += nthreads) {
+                    const int b = (int)(i / per_env);
+                    IvmEnv *e = &P.env[b];
+                    if (!e->dirty) continue;
+                    const int j = (int)(i - (long long)b * per_env);
+                    if (j < P.SR) {
+                        if (P.rowcount[(size_t)b * P.SR + j] > 0) { A::min_i(&e->rmin, e->origin_r + j); A::max_i(&e->rmax, e->origin_r + j); }
+                    } else {
+                        const int jc = j - P.SR;
+                        if (P.colcount[(size_t)b * P.SC + jc] > 0) { A::min_i(&e->cmin, e->origin_c + jc); A::max_i(&e->cmax, e->origin_c + jc); }
+                    }
+                }
+                A::sync();
+                for (int b = tid; b < P.B; b += nthreads) P.env[b].dirty = 0;
+            }
+        }
+        for (int b = tid; b < P.B; b += nthreads) {
+            const int32_t c = P.env[b].count;
+            if (c > 0) A::add_ull(&S.lbuf[0], (unsigned long long)c);
+        }
     }
     A::sync();
-    // ---- remember this step's list order (the next step's tie-breaks need it)
+    // ---- publish the step's figures, remember its list order (the next step's tie-breaks need
+    //      it), and reset the per-step scratch for the next step's ingest
     if (tid == 0) {
-        g->prev_valid = 1; g->prev_rmin = grmin; g->prev_cmin = gcmin;
-        g->prev_R = (long long)grmax - grmin; g->prev_C = (long long)gcmax - gcmin;
-        unsigned long long total = 0;
-        for (int b = 0; b < P.B; ++b) total += (unsigned long long)(P.env[b].count > 0 ? P.env[b].count : 0);
-        g->stats[IVM_STAT_WORLD] = total;
+        g->prev_valid = alive ? 1 : 0;
+        if (alive) {
+            g->prev_rmin = grmin; g->prev_cmin = gcmin;
+            g->prev_R = (long long)grmax - grmin; g->prev_C = (long long)gcmax - gcmin;
+        }
+        g->stats[IVM_STAT_VALID] = g->acc_valid;
+        g->stats[IVM_STAT_LOCAL] = g->acc_local;
+        g->stats[IVM_STAT_WORLD] = S.lbuf[0];
+        g->stats[IVM_STAT_E1] = n1;
+        g->stats[IVM_STAT_E2] = n2;
+        ivm_reset_step_globals(g);
     }
 }
 

@@ -1,14 +1,14 @@
 // ivm_kernels.cu -- sm_100a kernels + C ABI of the semantic-map update.
 //
 // Step pipeline (iterative mode), all on the caller's stream:
-//   K0 k_prep            per-env O(1) reset / store re-centring            (mapper.py:310-326)
-//   K1 k_ingest_scatter  [argmax ->] unproject -> transform -> filter -> half-cell ->
+//   K1 k_ingest_scatter  per-env O(1) reset / store re-centring / pose matrices (mapper.py:310-326, 127-138), then
+//      (_bulk)           [argmax ->] unproject -> transform -> filter -> half-cell ->
 //                        64-bit atomicMax into the frame-candidate plane   (mapper.py:381-474, core.py:117-230)
 //   K2 k_ingest_resolve  the owning pixel of each candidate merges into the world store
 //   K3 k_fixup           edge-collision fix-up of both de-dup stages        (mapper.py:461-474 quirk)
 //   K4 k_raster          band filter -> ego transform -> cell -> smem max/or -> u8 maps (mapper.py:555-617, 884-901)
-// No point cloud is ever written to HBM; the only per-pixel state is the 8-byte
-// candidate word of the touched half-cells.
+// Four launches per step.  No point cloud is ever written to HBM; the only per-pixel state is
+// the 8-byte candidate word of the touched half-cells.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -17,6 +17,7 @@
 #include "ivm_core.h"
 
 #define IVM_THREADS 256
+#define IVM_RASTER_THREADS 128
 #define IVM_NSTAGES 5
 #define IVM_EVPOOL 64
 
@@ -27,118 +28,70 @@ __device__ __forceinline__ unsigned warp_sum(unsigned v) { return __reduce_add_s
 
 __device__ __forceinline__ float4 ld_stream4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
 
-// ------------------------------------------------------------------ K0
-__global__ void __launch_bounds__(IVM_THREADS) k_prep(IvmParams P, int first_call) {
-    const int b = blockIdx.x;
-    if (b == 0 && threadIdx.x == 0) ivm_prep_global(P);
-    if (first_call) {  // one-time init of the class hash (workspace arrives zero-filled)
-        const size_t n = (size_t)P.hmask + 1;
-        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-            P.hkeys[i] = IVM_EMPTY_KEY; P.hxord[i] = IVM_EMPTY_KEY; P.hbest[i] = 0u;
-        }
+// ------------------------------------------------------------------ one-time init
+__global__ void k_init(IvmParams P) {
+    const size_t n = (size_t)P.hmask + 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        P.hkeys[i] = IVM_EMPTY_KEY; P.hxord[i] = IVM_EMPTY_KEY; P.hbest[i] = 0u;
     }
-    if (P.orient != nullptr && b < P.B && threadIdx.x == 32) ivm_pose_matrices(P, b);
-    if (b < P.maxB) {
-        // an env that holds nothing can be re-centred freely (first use, or back from a pause)
-        __shared__ int s_empty;
-        if (threadIdx.x == 0) s_empty = (b < P.B) && (P.env[b].count <= 0);
-        __syncthreads();
-        ivm_prep_env<IvmAtomics>(P, b, threadIdx.x, blockDim.x, s_empty != 0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ivm_reset_step_globals(P.g);
+}
+
+// ------------------------------------------------------------------ K1: prep + scatter
+// Head of every ingest CTA: decide the env's reset / store origin locally, get the pose matrices
+// (derived here from the angles, or loaded), and -- in the env's first CTA only -- publish the
+// new env state for the kernels that follow.
+struct K1Shared {
+    float T[12];
+    float cs[2];
+    int32_t origin_r, origin_c, reset;
+    int32_t bb[4];
+    unsigned valid;
+};
+
+__device__ __forceinline__ void k1_prologue(const IvmParams &P, int b, K1Shared &sh, bool publisher) {
+    if (threadIdx.x == 0) {
+        const IvmEnvPrep q = ivm_env_decide(P, b);
+        sh.origin_r = q.origin_r; sh.origin_c = q.origin_c; sh.reset = q.reset;
+        sh.bb[0] = INT32_MAX; sh.bb[1] = INT32_MIN; sh.bb[2] = INT32_MAX; sh.bb[3] = INT32_MIN;
+        sh.valid = 0;
+    }
+    if (P.orient != nullptr) {
+        if (threadIdx.x == 32) ivm_pose_matrices(P, b, sh.T, sh.cs);
+    } else if (threadIdx.x >= 32 && threadIdx.x < 44) {
+        sh.T[threadIdx.x - 32] = P.T12[12 * b + threadIdx.x - 32];
+    }
+    __syncthreads();
+    if (publisher) {
+        IvmEnvPrep q;
+        q.reset = sh.reset; q.origin_r = sh.origin_r; q.origin_c = sh.origin_c;
+        ivm_env_publish<IvmAtomics>(P, b, q, threadIdx.x, blockDim.x);
+        if (P.orient != nullptr) {
+            if (threadIdx.x < 12) P.T12_buf[12 * b + threadIdx.x] = sh.T[threadIdx.x];
+            if (threadIdx.x < 2) P.cs_buf[2 * b + threadIdx.x] = sh.cs[threadIdx.x];
+        }
     }
 }
 
-// ------------------------------------------------------------------ K1: scatter
-// One thread = VEC consecutive pixels of one image row (128-bit loads for VEC=4).
-template <bool PRED, int VEC>
-__global__ void __launch_bounds__(IVM_THREADS)
-k_ingest_scatter(IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out) {
-    const int b = blockIdx.y;
-    const int pix0 = (blockIdx.x * IVM_THREADS + threadIdx.x) * VEC;
-    __shared__ float sT[12];
-    __shared__ int sbb[4];
-    __shared__ unsigned s_valid;
-    if (threadIdx.x < 12) sT[threadIdx.x] = P.T12[12 * b + threadIdx.x];
-    if (threadIdx.x == 0) { sbb[0] = INT32_MAX; sbb[1] = INT32_MIN; sbb[2] = INT32_MAX; sbb[3] = INT32_MIN; s_valid = 0; }
-    __syncthreads();
+// unproject VEC pixels of one image row, scatter their candidates, fold the frame bbox
+template <int VEC>
+__device__ __forceinline__ void k1_scatter_pixels(const IvmParams &P, int b, int pix0, const float *d, K1Shared &sh) {
     int rmin = INT32_MAX, rmax = INT32_MIN, cmin = INT32_MAX, cmax = INT32_MIN;
     unsigned nvalid = 0;
     if (pix0 < P.HW) {
-        const size_t base = (size_t)b * P.HW + pix0;
-        float d[VEC];
-        if (VEC == 4) {
-            const float4 v = ld_stream4(P.depth + base);
-            d[0] = v.x; d[1 % VEC] = v.y; d[2 % VEC] = v.z; d[3 % VEC] = v.w;
-        } else {
-            d[0] = P.depth[base];
-        }
-        if (PRED) {
-            // PredictSemantics tail (mapper.py:795-798): argmax over class planes, first max wins,
-            // NaN counts as maximal (torch.argmax).  Planes are streamed with evict-first loads.
-            const float *lp = logits + (size_t)b * ncls * P.HW + pix0;
-            float best[VEC];
-            int arg[VEC];
-            if (VEC == 4) {
-                const float4 v = ld_stream4(lp);
-                best[0] = v.x; best[1 % VEC] = v.y; best[2 % VEC] = v.z; best[3 % VEC] = v.w;
-            } else {
-                best[0] = __ldcs(lp);
-            }
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) arg[j] = 0;
-            int k = 1;
-            constexpr int U = 8;
-            for (; k + U <= ncls; k += U) {
-                float vals[U][VEC];
-#pragma unroll
-                for (int q = 0; q < U; ++q) {
-                    if (VEC == 4) {
-                        const float4 v = ld_stream4(lp + (size_t)(k + q) * P.HW);
-                        vals[q][0] = v.x; vals[q][1 % VEC] = v.y; vals[q][2 % VEC] = v.z; vals[q][3 % VEC] = v.w;
-                    } else {
-                        vals[q][0] = __ldcs(lp + (size_t)(k + q) * P.HW);
-                    }
-                }
-#pragma unroll
-                for (int q = 0; q < U; ++q)
-#pragma unroll
-                    for (int j = 0; j < VEC; ++j) {
-                        const float v = vals[q][j];
-                        if ((v > best[j]) || (v != v && best[j] == best[j])) { best[j] = v; arg[j] = k + q; }
-                    }
-            }
-            for (; k < ncls; ++k) {
-                float vals[VEC];
-                if (VEC == 4) {
-                    const float4 v = ld_stream4(lp + (size_t)k * P.HW);
-                    vals[0] = v.x; vals[1 % VEC] = v.y; vals[2 % VEC] = v.z; vals[3 % VEC] = v.w;
-                } else {
-                    vals[0] = __ldcs(lp + (size_t)k * P.HW);
-                }
-#pragma unroll
-                for (int j = 0; j < VEC; ++j) {
-                    const float v = vals[j];
-                    if ((v > best[j]) || (v != v && best[j] == best[j])) { best[j] = v; arg[j] = k; }
-                }
-            }
-            if (VEC == 4) {
-                uchar4 o;
-                o.x = (uint8_t)arg[0]; o.y = (uint8_t)arg[1 % VEC]; o.z = (uint8_t)arg[2 % VEC]; o.w = (uint8_t)arg[3 % VEC];
-                *reinterpret_cast<uchar4 *>(labels_out + base) = o;
-            } else {
-                labels_out[base] = (uint8_t)arg[0];
-            }
-        }
-        const IvmEnv &e = P.env[b];
         const float h = P.pose[3 * b + 1];
         const int v = pix0 / P.W, u0 = pix0 - v * P.W;
         const float ysv = P.ys[v];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             IvmPoint p;
-            const int ok = ivm_unproject(d[j], P.xs[u0 + j], ysv, sT, h, P.half_res, p);
+            const int ok = ivm_unproject(d[j], P.xs[u0 + j], ysv, sh.T, h, P.half_res, p);
             if (ok == 0) continue;
             size_t idx;
-            if (ok == 2 || !ivm_store_index(P, e, b, p.r, p.c, idx)) { atomicOr(&P.g->err, IVM_ERR_STORE_OVERFLOW); continue; }
+            if (ok == 2 || !ivm_store_index(P, sh.origin_r, sh.origin_c, b, p.r, p.c, idx)) {
+                atomicOr(&P.g->err, IVM_ERR_STORE_OVERFLOW);
+                continue;
+            }
             atomicMax(&P.cand[idx], ivm_cand_key(p.y, (uint32_t)(pix0 + j)));
             rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
             ++nvalid;
@@ -149,16 +102,207 @@ k_ingest_scatter(IvmParams P, const float *__restrict__ logits, int ncls, uint8_
     if (wv) {  // warp-uniform
         rmin = warp_min(rmin); rmax = warp_max(rmax); cmin = warp_min(cmin); cmax = warp_max(cmax);
         if ((threadIdx.x & 31) == 0) {
-            atomicMin(&sbb[0], rmin); atomicMax(&sbb[1], rmax); atomicMin(&sbb[2], cmin); atomicMax(&sbb[3], cmax);
-            atomicAdd(&s_valid, wv);
+            atomicMin(&sh.bb[0], rmin); atomicMax(&sh.bb[1], rmax); atomicMin(&sh.bb[2], cmin); atomicMax(&sh.bb[3], cmax);
+            atomicAdd(&sh.valid, wv);
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && s_valid) {
-        atomicMin(&P.g->loc[0], sbb[0]); atomicMax(&P.g->loc[1], sbb[1]);
-        atomicMin(&P.g->loc[2], sbb[2]); atomicMax(&P.g->loc[3], sbb[3]);
-        atomicAdd(&P.g->stats[IVM_STAT_VALID], (unsigned long long)s_valid);
+    if (threadIdx.x == 0 && sh.valid) {
+        atomicMin(&P.g->loc[0], sh.bb[0]); atomicMax(&P.g->loc[1], sh.bb[1]);
+        atomicMin(&P.g->loc[2], sh.bb[2]); atomicMax(&P.g->loc[3], sh.bb[3]);
+        atomicAdd(&P.g->acc_valid, (unsigned long long)sh.valid);
     }
+}
+
+__device__ __forceinline__ float4 ld_cs_v4(const float *p) {  // volatile: keeps the batch of loads together
+    float4 v;
+    asm volatile("ld.global.cs.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+
+#define IVM_ARGMAX_STEP(v, k, best, arg) \
+    if (((v) > (best)) || ((v) != (v) && (best) == (best))) { (best) = (v); (arg) = (k); }
+
+// One thread = VEC consecutive pixels of one image row (128-bit loads for VEC=4).
+template <bool PRED, int VEC>
+__global__ void __launch_bounds__(IVM_THREADS)
+k_ingest_scatter(IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out) {
+    const int b = blockIdx.y;
+    __shared__ K1Shared sh;
+    if (b >= P.B) {  // paused env (mapper.py:315-318): the first CTA wipes it, the rest have nothing to do
+        if (blockIdx.x == 0) { IvmEnvPrep q; q.reset = 1; q.origin_r = 0; q.origin_c = 0; ivm_env_publish<IvmAtomics>(P, b, q, threadIdx.x, blockDim.x); }
+        return;
+    }
+    const int pix0 = (blockIdx.x * IVM_THREADS + threadIdx.x) * VEC;
+    // issue the depth load before the prologue's barrier
+    float d[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) d[j] = 2.0f;
+    const size_t base = (size_t)b * P.HW + pix0;
+    if (pix0 < P.HW) {
+        if (VEC == 4) {
+            const float4 v = ld_stream4(P.depth + base);
+            d[0] = v.x; d[1 % VEC] = v.y; d[2 % VEC] = v.z; d[3 % VEC] = v.w;
+        } else {
+            d[0] = P.depth[base];
+        }
+    }
+    k1_prologue(P, b, sh, blockIdx.x == 0);
+    if (PRED && pix0 < P.HW) {
+        // PredictSemantics tail (mapper.py:795-798): argmax over class planes, first max wins,
+        // NaN counts as maximal (torch.argmax).  Planes are streamed with evict-first loads,
+        // 8 independent 128-bit loads in flight per thread.
+        const float *lp = logits + (size_t)b * ncls * P.HW + pix0;
+        float best[VEC];
+        int arg[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { best[j] = 0.f; arg[j] = 0; }
+        if (VEC == 4) {
+            const float4 v = ld_cs_v4(lp);
+            best[0] = v.x; best[1 % VEC] = v.y; best[2 % VEC] = v.z; best[3 % VEC] = v.w;
+        } else {
+            best[0] = __ldcs(lp);
+        }
+        int k = 1;
+        constexpr int U = 8;
+        for (; k + U <= ncls; k += U) {
+            if (VEC == 4) {
+                float4 vals[U];
+#pragma unroll
+                for (int q = 0; q < U; ++q) vals[q] = ld_cs_v4(lp + (size_t)(k + q) * P.HW);
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    IVM_ARGMAX_STEP(vals[q].x, k + q, best[0], arg[0]);
+                    IVM_ARGMAX_STEP(vals[q].y, k + q, best[1 % VEC], arg[1 % VEC]);
+                    IVM_ARGMAX_STEP(vals[q].z, k + q, best[2 % VEC], arg[2 % VEC]);
+                    IVM_ARGMAX_STEP(vals[q].w, k + q, best[3 % VEC], arg[3 % VEC]);
+                }
+            } else {
+                float vals[U];
+#pragma unroll
+                for (int q = 0; q < U; ++q) vals[q] = __ldcs(lp + (size_t)(k + q) * P.HW);
+#pragma unroll
+                for (int q = 0; q < U; ++q) { IVM_ARGMAX_STEP(vals[q], k + q, best[0], arg[0]); }
+            }
+        }
+        for (; k < ncls; ++k) {
+            if (VEC == 4) {
+                const float4 v = ld_cs_v4(lp + (size_t)k * P.HW);
+                IVM_ARGMAX_STEP(v.x, k, best[0], arg[0]);
+                IVM_ARGMAX_STEP(v.y, k, best[1 % VEC], arg[1 % VEC]);
+                IVM_ARGMAX_STEP(v.z, k, best[2 % VEC], arg[2 % VEC]);
+                IVM_ARGMAX_STEP(v.w, k, best[3 % VEC], arg[3 % VEC]);
+            } else {
+                const float v = __ldcs(lp + (size_t)k * P.HW);
+                IVM_ARGMAX_STEP(v, k, best[0], arg[0]);
+            }
+        }
+        if (VEC == 4) {
+            uchar4 o;
+            o.x = (uint8_t)arg[0]; o.y = (uint8_t)arg[1 % VEC]; o.z = (uint8_t)arg[2 % VEC]; o.w = (uint8_t)arg[3 % VEC];
+            *reinterpret_cast<uchar4 *>(labels_out + base) = o;
+        } else {
+            labels_out[base] = (uint8_t)arg[0];
+        }
+    }
+    k1_scatter_pixels<VEC>(P, b, pix0, d, sh);
+}
+
+// ---- bulk-async variant of the predicted-semantics ingest (the default when the image tiles evenly):
+// the score planes are staged through a 4-deep shared-memory ring by cp.async.bulk (the TMA engine's
+// 1-D bulk copy, SASS UBLKCP) completing on mbarriers, so ~64 KB per CTA are in flight without
+// holding registers; threads read their 4 pixels per plane from shared memory with LDS.128.
+#define IVM_BULK_TILE 1024   // pixels per CTA (= 256 threads x 4)
+#define IVM_BULK_SP 4        // planes per stage (16 KB)
+#define IVM_BULK_NSTAGE 4    // ring depth (64 KB)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+
+__global__ void __launch_bounds__(IVM_THREADS)
+k_ingest_scatter_bulk(IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float(*ring)[IVM_BULK_SP][IVM_BULK_TILE] = reinterpret_cast<float(*)[IVM_BULK_SP][IVM_BULK_TILE]>(smem_raw);
+    __shared__ __align__(8) uint64_t full[IVM_BULK_NSTAGE];
+    __shared__ K1Shared sh;
+    const int b = blockIdx.y;
+    if (b >= P.B) {
+        if (blockIdx.x == 0) { IvmEnvPrep q; q.reset = 1; q.origin_r = 0; q.origin_c = 0; ivm_env_publish<IvmAtomics>(P, b, q, threadIdx.x, blockDim.x); }
+        return;
+    }
+    const int tile0 = blockIdx.x * IVM_BULK_TILE;
+    const int pix0 = tile0 + threadIdx.x * 4;
+    const float *lp = logits + (size_t)b * ncls * P.HW + tile0;
+    const int nchunks = (ncls + IVM_BULK_SP - 1) / IVM_BULK_SP;
+    uint64_t policy = 0;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < IVM_BULK_NSTAGE; ++s) mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    }
+    const size_t base = (size_t)b * P.HW + pix0;
+    const float4 dv = ld_stream4(P.depth + base);
+    __syncthreads();  // barriers initialised
+    auto issue = [&](int ch) {
+        const int slot = ch % IVM_BULK_NSTAGE;
+        const int p0 = ch * IVM_BULK_SP;
+        const int np = min(IVM_BULK_SP, ncls - p0);
+        mbar_expect_tx(&full[slot], (uint32_t)(np * IVM_BULK_TILE * sizeof(float)));
+        for (int p = 0; p < np; ++p)
+            bulk_g2s(&ring[slot][p][0], lp + (size_t)(p0 + p) * P.HW, IVM_BULK_TILE * sizeof(float), &full[slot], policy);
+    };
+    if (threadIdx.x == 0)
+        for (int ch = 0; ch < IVM_BULK_NSTAGE && ch < nchunks; ++ch) issue(ch);
+    k1_prologue(P, b, sh, blockIdx.x == 0);
+    float best0 = 0.f, best1 = 0.f, best2 = 0.f, best3 = 0.f;
+    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int slot = ch % IVM_BULK_NSTAGE;
+        mbar_wait(&full[slot], (uint32_t)((ch / IVM_BULK_NSTAGE) & 1));
+        const int p0 = ch * IVM_BULK_SP;
+        const int np = min(IVM_BULK_SP, ncls - p0);
+#pragma unroll
+        for (int p = 0; p < IVM_BULK_SP; ++p) {
+            if (p < np) {
+                const float4 v = *reinterpret_cast<const float4 *>(&ring[slot][p][threadIdx.x * 4]);
+                const int k = p0 + p;
+                if (k == 0) {
+                    best0 = v.x; best1 = v.y; best2 = v.z; best3 = v.w;
+                } else {
+                    IVM_ARGMAX_STEP(v.x, k, best0, a0);
+                    IVM_ARGMAX_STEP(v.y, k, best1, a1);
+                    IVM_ARGMAX_STEP(v.z, k, best2, a2);
+                    IVM_ARGMAX_STEP(v.w, k, best3, a3);
+                }
+            }
+        }
+        __syncthreads();  // every thread is done with this slot
+        if (threadIdx.x == 0 && ch + IVM_BULK_NSTAGE < nchunks) issue(ch + IVM_BULK_NSTAGE);
+    }
+    uchar4 o;
+    o.x = (uint8_t)a0; o.y = (uint8_t)a1; o.z = (uint8_t)a2; o.w = (uint8_t)a3;
+    *reinterpret_cast<uchar4 *>(labels_out + base) = o;
+    const float d[4] = {dv.x, dv.y, dv.z, dv.w};
+    k1_scatter_pixels<4>(P, b, pix0, d, sh);
 }
 
 // ------------------------------------------------------------------ K2: resolve
@@ -167,11 +311,16 @@ __global__ void __launch_bounds__(IVM_THREADS) k_ingest_resolve(IvmParams P) {
     const int b = blockIdx.y;
     const int pix0 = (blockIdx.x * IVM_THREADS + threadIdx.x) * VEC;
     __shared__ float sT[12];
+    __shared__ int32_t sloc[4];
+    __shared__ int32_t sbox[5];   // rmin, rmax, cmin, cmax, n of the cells this CTA newly occupied
     __shared__ unsigned s_local;
     if (threadIdx.x < 12) sT[threadIdx.x] = P.T12[12 * b + threadIdx.x];
-    if (threadIdx.x == 0) s_local = 0;
+    if (threadIdx.x >= 32 && threadIdx.x < 36) sloc[threadIdx.x - 32] = P.g->loc[threadIdx.x - 32];
+    if (threadIdx.x == 64) { sbox[0] = INT32_MAX; sbox[1] = INT32_MIN; sbox[2] = INT32_MAX; sbox[3] = INT32_MIN; sbox[4] = 0; s_local = 0; }
     __syncthreads();
     unsigned nlocal = 0;
+    IvmBoxAcc acc;
+    acc.clear();
     if (pix0 < P.HW) {
         const size_t base = (size_t)b * P.HW + pix0;
         float d[VEC];
@@ -185,6 +334,8 @@ __global__ void __launch_bounds__(IVM_THREADS) k_ingest_resolve(IvmParams P) {
             d[0] = P.depth[base];
             lab[0] = P.labels[base];
         }
+        const IvmEnv *e = &P.env[b];
+        const int32_t origin_r = e->origin_r, origin_c = e->origin_c;
         const float h = P.pose[3 * b + 1];
         const int v = pix0 / P.W, u0 = pix0 - v * P.W;
         const float ysv = P.ys[v];
@@ -192,25 +343,66 @@ __global__ void __launch_bounds__(IVM_THREADS) k_ingest_resolve(IvmParams P) {
         for (int j = 0; j < VEC; ++j) {
             IvmPoint p;
             if (ivm_unproject(d[j], P.xs[u0 + j], ysv, sT, h, P.half_res, p) != 1) continue;
-            nlocal += (unsigned)ivm_resolve_pixel<IvmAtomics>(P, b, (uint32_t)(pix0 + j), p, lab[j]);
+            nlocal += (unsigned)ivm_resolve_pixel<IvmAtomics>(P, b, (uint32_t)(pix0 + j), p, lab[j], sloc, origin_r,
+                                                              origin_c, acc);
+        }
+    }
+    // newly occupied cells: warp -> block -> 5 global atomics per CTA
+    const unsigned wn = warp_sum((unsigned)acc.n);
+    if (wn) {
+        const int r0 = warp_min(acc.rmin), r1 = warp_max(acc.rmax), c0 = warp_min(acc.cmin), c1 = warp_max(acc.cmax);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&sbox[0], r0); atomicMax(&sbox[1], r1); atomicMin(&sbox[2], c0); atomicMax(&sbox[3], c1);
+            atomicAdd(&sbox[4], (int)wn);
         }
     }
     const unsigned wl = warp_sum(nlocal);
     if (wl && (threadIdx.x & 31) == 0) atomicAdd(&s_local, wl);
     __syncthreads();
-    if (threadIdx.x == 0 && s_local) atomicAdd(&P.g->stats[IVM_STAT_LOCAL], (unsigned long long)s_local);
+    if (threadIdx.x == 0) {
+        if (sbox[4] > 0) {
+            IvmBoxAcc t;
+            t.rmin = sbox[0]; t.rmax = sbox[1]; t.cmin = sbox[2]; t.cmax = sbox[3]; t.n = sbox[4];
+            ivm_box_flush<IvmAtomics>(&P.env[b], t);
+        }
+        if (s_local) atomicAdd(&P.g->acc_local, (unsigned long long)s_local);
+    }
 }
 
 // ------------------------------------------------------------------ K3: fix-up
+#define IVM_FIX_SMALL 512
 __global__ void __launch_bounds__(1024) k_fixup(IvmParams P) {
-    ivm_fixup_program<IvmAtomics>(P, threadIdx.x, blockDim.x);
+    __shared__ unsigned long long s_key[IVM_FIX_SMALL], s_xo[IVM_FIX_SMALL], s_l[2];
+    __shared__ uint32_t s_ord[IVM_FIX_SMALL];
+    __shared__ int32_t s_i[8];
+    IvmFixScratch S;
+    S.key = s_key; S.xo = s_xo; S.ord = s_ord; S.cap = IVM_FIX_SMALL; S.ibuf = s_i; S.lbuf = s_l;
+    ivm_fixup_program<IvmAtomics>(P, S, threadIdx.x, blockDim.x);
 }
 
 // ------------------------------------------------------------------ K4: raster
-// One CTA = one ego tile of one env.  Warps walk the half-rows of the world store
-// under the (rotated) tile; lanes read 16-byte records along the row span.
+// One CTA = one ego tile of one env (output-stationary).  The store half-rows under the rotated
+// tile are cut into 32-record chunks; warps take chunks round-robin, two at a time, so that
+// every lane has two independent 16-byte loads in flight.
+__device__ __forceinline__ void raster_record(const IvmParams &P, const uint4 raw, bool have, uint32_t reset_stamp, float px,
+                                              float h, float pz, float c, float s, int r0, int r1, int c0, int c1, int tc,
+                                              uint32_t cell, uint32_t *skey, uint8_t *socc, unsigned &n_in) {
+    if (!have || !ivm_live(raw.w, reset_stamp)) return;
+    int row, col;
+    if (!ivm_ego_cell(P, __uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), px, h, pz, c, s, row, col))
+        return;
+    if (row < r0 || row >= r1 || col < c0 || col >= c1) return;
+    ++n_in;
+    const int t = (row - r0) * tc + (col - c0);
+    socc[t] = 1;  // OccupancyStatus.OCCUPIED
+    const uint32_t label = raw.w & 0xFFu;
+    // last point in list order wins (mapper.py:569-571); list order within an env is (half-row,
+    // half-col) lexicographic; labels 0 are excluded (mapper.py:611)
+    if (label) atomicMax(&skey[t], (cell << 8) | label);
+}
+
 template <bool KNOWN>
-__global__ void __launch_bounds__(IVM_THREADS) k_raster(IvmParams P) {
+__global__ void __launch_bounds__(IVM_RASTER_THREADS) k_raster(IvmParams P) {
     extern __shared__ uint32_t skey[];
     const int tr = P.tile_r, tc = P.tile_c;
     uint8_t *socc = reinterpret_cast<uint8_t *>(skey + tr * tc);
@@ -229,32 +421,47 @@ __global__ void __launch_bounds__(IVM_THREADS) k_raster(IvmParams P) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
         const int row_lo = max(G.row_lo, KNOWN ? e.origin_r : e.rmin);
         const int row_hi = min(G.row_hi, KNOWN ? e.origin_r + P.SR - 1 : e.rmax);
-        for (int rr = row_lo + warp; rr <= row_hi; rr += nwarps) {
-            int clo, chi;
-            ivm_row_span(G, rr, clo, chi);
-            clo = max(clo, KNOWN ? e.origin_c : e.cmin);
-            chi = min(chi, KNOWN ? e.origin_c + P.SC - 1 : e.cmax);
-            if (clo > chi) continue;
-            const size_t rowbase = ((size_t)b * P.SR + (size_t)(rr - e.origin_r)) * P.SC;
-            if (!KNOWN) {
-                for (int cc = clo + lane; cc <= chi; cc += 32) {
-                    const int ccr = cc - e.origin_c;
-                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(P.store + rowbase + ccr));
-                    if (!ivm_live(raw.w, e.reset_stamp)) continue;
-                    int row, col;
-                    if (!ivm_ego_cell(P, __uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), px, h, pz,
-                                      c, s, row, col))
-                        continue;
-                    if (row < r0 || row >= r1 || col < c0 || col >= c1) continue;
-                    ++n_in;
-                    const int t = (row - r0) * tc + (col - c0);
-                    socc[t] = 1;  // OccupancyStatus.OCCUPIED
-                    const uint32_t label = raw.w & 0xFFu;
-                    // last point in list order wins (mapper.py:569-571); list order within an env is
-                    // (half-row, half-col) lexicographic, labels 0 are excluded (mapper.py:611)
-                    if (label) atomicMax(&skey[t], ((uint32_t)((rr - e.origin_r) * P.SC + ccr) << 8) | label);
+        const int col_lo = KNOWN ? e.origin_c : e.cmin, col_hi = KNOWN ? e.origin_c + P.SC - 1 : e.cmax;
+        if (!KNOWN) {
+            // widest possible span of a row (diagonal of the tile in half-cells) -> chunks per row
+            const float diag = sqrtf((float)((r1 - r0) * (r1 - r0) + (c1 - c0) * (c1 - c0))) * (P.res / P.half_res);
+            const int CH = ((int)diag + 8 + 31) / 32;
+            const int nslots = (row_hi - row_lo + 1) * CH;
+            for (int sl = warp; sl < nslots; sl += 2 * nwarps) {
+                uint4 raw[2];
+                bool have[2];
+                uint32_t cell[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int slot = sl + u * nwarps;
+                    have[u] = false;
+                    raw[u] = make_uint4(0, 0, 0, 0);
+                    cell[u] = 0;
+                    if (slot < nslots) {
+                        const int rr = row_lo + slot / CH, k = slot - (slot / CH) * CH;
+                        int clo, chi;
+                        ivm_row_span(G, rr, clo, chi);
+                        clo = max(clo, col_lo); chi = min(chi, col_hi);
+                        const int cc = clo + 32 * k + lane;
+                        if (cc <= chi) {
+                            const uint32_t rrel = (uint32_t)(rr - e.origin_r), crel = (uint32_t)(cc - e.origin_c);
+                            cell[u] = rrel * (uint32_t)P.SC + crel;
+                            raw[u] = __ldg(reinterpret_cast<const uint4 *>(P.store + (size_t)b * P.SR * P.SC + cell[u]));
+                            have[u] = true;
+                        }
+                    }
                 }
-            } else {
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    raster_record(P, raw[u], have[u], e.reset_stamp, px, h, pz, c, s, r0, r1, c0, c1, tc, cell[u], skey, socc,
+                                  n_in);
+            }
+        } else {
+            for (int rr = row_lo + warp; rr <= row_hi; rr += nwarps) {
+                int clo, chi;
+                ivm_row_span(G, rr, clo, chi);
+                clo = max(clo, col_lo); chi = min(chi, col_hi);
+                if (clo > chi) continue;
                 const uint32_t *off = P.koff + (size_t)b * ((size_t)P.SR * P.SC + 1) + (size_t)(rr - e.origin_r) * P.SC;
                 const uint32_t p0 = off[clo - e.origin_c], p1 = off[chi - e.origin_c + 1];
                 const IvmRecord *pts = P.kpts + (size_t)b * P.kcap;
@@ -288,7 +495,7 @@ __global__ void __launch_bounds__(IVM_THREADS) k_raster(IvmParams P) {
 
 __global__ void k_pose(IvmParams P) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < P.B) ivm_pose_matrices(P, b);
+    if (b < P.B) ivm_pose_matrices(P, b, P.T12_buf + 12 * b, P.cs_buf + 2 * b);
 }
 
 // ------------------------------------------------------------------ known-map store build
@@ -455,6 +662,7 @@ struct ivm_ctx {
     uint32_t step;     // 24-bit stamp of the last call
     int hi_water;      // envs [0, hi_water) may hold records
     int first_call;
+    int bulk_attr_set;
     int64_t launches;
     // known-mode scratch
     uint32_t *kfill, *ktotals;
@@ -569,7 +777,7 @@ int ivm_create(const ivm_config *cfg, void *workspace_dev, size_t workspace_byte
     P.res = cfg->res; P.half_res = cfg->half_res; P.half_h = cfg->half_h; P.half_w = cfg->half_w;
     P.SR = cfg->store_rows; P.SC = cfg->store_cols; P.maxB = cfg->max_envs;
     int tr = cfg->tile_rows, tc = cfg->tile_cols;
-    if (tr <= 0 || tc <= 0) { tr = 32; tc = 32; }
+    if (tr <= 0 || tc <= 0) { tr = 16; tc = 16; }
     if (tr > P.R) tr = P.R;
     if (tc > P.C) tc = P.C;
     P.tile_r = tr; P.tile_c = tc;
@@ -663,8 +871,8 @@ static int next_step(ivm_ctx *ctx) {
 static void launch_raster(ivm_ctx *ctx, const IvmParams &P, cudaStream_t st, bool known) {
     dim3 grid((P.C + P.tile_c - 1) / P.tile_c, (P.R + P.tile_r - 1) / P.tile_r, P.B);
     const size_t smem = (size_t)P.tile_r * P.tile_c * 5 + 16;
-    if (known) k_raster<true><<<grid, IVM_THREADS, smem, st>>>(P);
-    else k_raster<false><<<grid, IVM_THREADS, smem, st>>>(P);
+    if (known) k_raster<true><<<grid, IVM_RASTER_THREADS, smem, st>>>(P);
+    else k_raster<false><<<grid, IVM_RASTER_THREADS, smem, st>>>(P);
     ctx->launches += 1;
 }
 
@@ -688,20 +896,30 @@ int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const
     else { P.orient = nullptr; P.T12 = T12; P.cs = cs; }
     const int slot = timing_slot(ctx);
 
-    const int nprep = num_envs > ctx->hi_water ? num_envs : ctx->hi_water;
-    T_BEGIN(0);
-    k_prep<<<nprep, IVM_THREADS, 0, st>>>(P, ctx->first_call);
-    T_END(0);
-    IVM_CHECK_LAUNCH("k_prep");
-    ctx->first_call = 0;
+    if (ctx->first_call) {
+        k_init<<<64, 256, 0, st>>>(P);
+        IVM_CHECK_LAUNCH("k_init");
+        ctx->first_call = 0;
+        ctx->launches += 1;
+    }
+    const int nenv = num_envs > ctx->hi_water ? num_envs : ctx->hi_water;  // envs >= num_envs get wiped
     ctx->hi_water = num_envs;
 
     const bool vec4 = (P.W % 4 == 0) && (((uintptr_t)depth & 15) == 0) && (((uintptr_t)P.labels & 3) == 0) &&
                       (!logits || ((uintptr_t)logits & 15) == 0);
     const int vec = vec4 ? 4 : 1;
-    dim3 grid((P.HW + IVM_THREADS * vec - 1) / (IVM_THREADS * vec), num_envs);
+    dim3 grid((P.HW + IVM_THREADS * vec - 1) / (IVM_THREADS * vec), nenv);
+    const bool bulk = logits && vec4 && (P.HW % IVM_BULK_TILE == 0) && ctx->cfg.reserved[0] != 1;
     T_BEGIN(1);
-    if (logits) {
+    if (bulk) {
+        const size_t smem = (size_t)IVM_BULK_NSTAGE * IVM_BULK_SP * IVM_BULK_TILE * sizeof(float);
+        if (!ctx->bulk_attr_set) {
+            cudaError_t e = cudaFuncSetAttribute(k_ingest_scatter_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(k_ingest_scatter_bulk)");
+            ctx->bulk_attr_set = 1;
+        }
+        k_ingest_scatter_bulk<<<dim3(P.HW / IVM_BULK_TILE, nenv), IVM_THREADS, smem, st>>>(P, logits, num_classes, labels_out);
+    } else if (logits) {
         if (vec4) k_ingest_scatter<true, 4><<<grid, IVM_THREADS, 0, st>>>(P, logits, num_classes, labels_out);
         else k_ingest_scatter<true, 1><<<grid, IVM_THREADS, 0, st>>>(P, logits, num_classes, labels_out);
     } else {
@@ -710,6 +928,7 @@ int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const
     }
     T_END(1);
     IVM_CHECK_LAUNCH("k_ingest_scatter");
+    grid.y = num_envs;
     T_BEGIN(2);
     if (vec4) k_ingest_resolve<4><<<grid, IVM_THREADS, 0, st>>>(P);
     else k_ingest_resolve<1><<<grid, IVM_THREADS, 0, st>>>(P);
@@ -723,7 +942,7 @@ int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const
     launch_raster(ctx, P, st, false);
     T_END(4);
     IVM_CHECK_LAUNCH("k_raster");
-    ctx->launches += 4;
+    ctx->launches += 3;
     return IVM_OK;
 }
 

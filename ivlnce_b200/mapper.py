@@ -251,7 +251,8 @@ class _MapEngine:
     """Owns one libivlnmap context + its device workspace and output buffers."""
 
     def __init__(self, device: torch.device, map_dimensions: MapDimensions, camera: Optional[CameraParameters],
-                 mode: str, max_envs: int, store_cells: int, known_capacity: int, tile: int = 0):
+                 mode: str, max_envs: int, store_cells: int, known_capacity: int, tile: int = 0,
+                 scatter_variant: int = 0):
         device = torch.device(device)
         if device.type != "cuda":
             raise _lib.MapLibraryError(
@@ -264,6 +265,7 @@ class _MapEngine:
         self.store_cells = int(store_cells)
         self.known_capacity = int(known_capacity)
         self.tile = int(tile)
+        self.scatter_variant = int(scatter_variant)  # 0 = auto (bulk-async ingest when it applies), 1 = register-staged
         self.ctx = None
         self.workspace = None
         self.max_envs = 0
@@ -273,8 +275,9 @@ class _MapEngine:
     def _config(self, max_envs: int) -> _lib.IvmConfig:
         md = self.md
         H, W = (self.camera.features_spatial_dimensions if self.camera is not None else (0, 0))
+        reserved = (ctypes.c_int32 * 4)(self.scatter_variant, 0, 0, 0)
         return _lib.IvmConfig(
-            max_envs=max_envs, height=int(H), width=int(W), map_rows=md.num_rows, map_cols=md.num_cols,
+            reserved=reserved, max_envs=max_envs, height=int(H), width=int(W), map_rows=md.num_rows, map_cols=md.num_cols,
             res=np.float32(md.resolution_meters), half_res=np.float32(md.resolution_meters / 2),
             half_h=np.float32(md.height_meters / 2), half_w=np.float32(md.width_meters / 2),
             store_rows=self.store_cells, store_cols=self.store_cells, mode=0 if self.mode == "iterative" else 1,
@@ -356,7 +359,7 @@ class MappingModule(nn.Module):
                  maps_location: Optional[str] = None, max_envs: Optional[int] = None,
                  store_cells: int = DEFAULT_STORE_CELLS, known_capacity: int = DEFAULT_KNOWN_CAPACITY,
                  trig: str = "kernel", host_trig: bool = False, raster_tile: int = 0,
-                 track_start_state: bool = False):
+                 track_start_state: bool = False, scatter_variant: int = 0):
         super().__init__()
         assert mode in ("iterative", "known")
         self.device = torch.device(device)
@@ -374,7 +377,8 @@ class MappingModule(nn.Module):
         self.trig = "host" if host_trig else trig
         assert self.trig in ("kernel", "torch", "host")
         self.track_start_state = track_start_state
-        self._engine_args = dict(store_cells=store_cells, known_capacity=known_capacity, tile=raster_tile)
+        self._engine_args = dict(store_cells=store_cells, known_capacity=known_capacity, tile=raster_tile,
+                                 scatter_variant=scatter_variant)
         self._engine: Optional[_MapEngine] = None
         self._initial_max_envs = max_envs
         self._num_envs = 0

@@ -20,6 +20,7 @@ struct Emu {
     uint32_t step;
     int hi_water;
     int order;  // 0 forward, 1 reverse, 2 strided
+    int fix_cap;  // capacity of the fix-up's small-class fast path (0 forces the hash path)
     std::vector<IvmRecord> store;
     std::vector<unsigned long long> cand;
     std::vector<IvmEnv> env;
@@ -40,7 +41,8 @@ Emu *emu_create(int H, int W, const float *xs, const float *ys, float res, float
     Emu *m = new Emu();
     memset(&m->P, 0, sizeof(m->P));
     memset(&m->g, 0, sizeof(m->g));
-    m->mode = mode; m->step = 0; m->hi_water = 0; m->order = 0;
+    m->mode = mode; m->step = 0; m->hi_water = 0; m->order = 0; m->fix_cap = 512;
+    ivm_reset_step_globals(&m->g);
     IvmParams &P = m->P;
     P.H = H; P.W = W; P.HW = H * W; P.R = R; P.C = C;
     P.res = res; P.half_res = half_res; P.half_h = half_h; P.half_w = half_w;
@@ -82,6 +84,7 @@ Emu *emu_create(int H, int W, const float *xs, const float *ys, float res, float
 
 void emu_destroy(Emu *m) { delete m; }
 void emu_set_order(Emu *m, int order) { m->order = order; }
+void emu_set_fix_cap(Emu *m, int cap) { m->fix_cap = cap < 1 ? 1 : cap; }
 
 static inline int visit(const Emu *m, int i, int n) {
     if (m->order == 1) return n - 1 - i;
@@ -171,16 +174,17 @@ int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels,
     P.occ = occ; P.sem = sem;
     if (orient) {  // the K0 path that derives the matrices from the angles
         P.orient = orient; P.orient_f64 = orient_f64; P.T12 = P.T12_buf; P.cs = P.cs_buf;
-        for (int b = 0; b < B; ++b) ivm_pose_matrices(P, b);
+        for (int b = 0; b < B; ++b) ivm_pose_matrices(P, b, P.T12_buf + 12 * b, P.cs_buf + 2 * b);
         T12 = P.T12; cs = P.cs;
     }
-    // K0
-    ivm_prep_global(P);
-    const int nprep = B > m->hi_water ? B : m->hi_water;
-    for (int b = 0; b < nprep; ++b) {
-        const bool empty = b < B && P.env[b].count <= 0;
-        ivm_prep_env<IvmAtomics>(P, b, 0, 1, empty);
+    // K1 head: every env decides its reset / origin; the "first CTA" publishes it (dropped envs are wiped)
+    const int nenv = B > m->hi_water ? B : m->hi_water;
+    std::vector<IvmEnvPrep> prep(nenv);
+    for (int b = 0; b < nenv; ++b) {
+        if (b < B) prep[b] = ivm_env_decide(P, b);
+        else { prep[b].reset = 1; prep[b].origin_r = 0; prep[b].origin_c = 0; }
     }
+    for (int b = 0; b < nenv; ++b) ivm_env_publish<IvmAtomics>(P, b, prep[b], 0, 1);
     m->hi_water = B;
     // K1: scatter
     const int n = B * P.HW;
@@ -192,23 +196,35 @@ int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels,
         const int ok = ivm_unproject(depth[gp], P.xs[u], P.ys[v], T12 + 12 * b, pose[3 * b + 1], P.half_res, p);
         if (ok == 0) continue;
         size_t idx;
-        if (ok == 2 || !ivm_store_index(P, P.env[b], b, p.r, p.c, idx)) { m->g.err |= IVM_ERR_STORE_OVERFLOW; continue; }
+        if (ok == 2 || !ivm_store_index(P, prep[b].origin_r, prep[b].origin_c, b, p.r, p.c, idx)) { m->g.err |= IVM_ERR_STORE_OVERFLOW; continue; }
         IvmAtomics::max_ull(&P.cand[idx], ivm_cand_key(p.y, (uint32_t)pix));
         IvmAtomics::min_i(&m->g.loc[0], p.r); IvmAtomics::max_i(&m->g.loc[1], p.r);
         IvmAtomics::min_i(&m->g.loc[2], p.c); IvmAtomics::max_i(&m->g.loc[3], p.c);
-        m->g.stats[IVM_STAT_VALID]++;
+        m->g.acc_valid++;
     }
-    // K2: resolve
+    // K2: resolve (one accumulator per simulated CTA of 1024 pixels, flushed like the kernel does)
     for (int i = 0; i < n; ++i) {
         const int gp = visit(m, n - 1 - i, n);
         const int b = gp / P.HW, pix = gp - b * P.HW;
         const int v = pix / P.W, u = pix - v * P.W;
         IvmPoint p;
         if (ivm_unproject(depth[gp], P.xs[u], P.ys[v], T12 + 12 * b, pose[3 * b + 1], P.half_res, p) != 1) continue;
-        m->g.stats[IVM_STAT_LOCAL] += (unsigned)ivm_resolve_pixel<IvmAtomics>(P, b, (uint32_t)pix, p, labels[gp]);
+        IvmBoxAcc acc;
+        acc.clear();
+        m->g.acc_local += (unsigned)ivm_resolve_pixel<IvmAtomics>(P, b, (uint32_t)pix, p, labels[gp], m->g.loc,
+                                                                  P.env[b].origin_r, P.env[b].origin_c, acc);
+        ivm_box_flush<IvmAtomics>(&P.env[b], acc);
     }
     // K3: fix-up
-    ivm_fixup_program<IvmAtomics>(P, 0, 1);
+    {
+        std::vector<unsigned long long> key(m->fix_cap), xo(m->fix_cap);
+        std::vector<uint32_t> ord(m->fix_cap);
+        int32_t ibuf[8];
+        unsigned long long lbuf[2];
+        IvmFixScratch S;
+        S.key = key.data(); S.xo = xo.data(); S.ord = ord.data(); S.cap = (uint32_t)m->fix_cap; S.ibuf = ibuf; S.lbuf = lbuf;
+        ivm_fixup_program<IvmAtomics>(P, S, 0, 1);
+    }
     // K4: raster
     emu_raster(m, P, false);
     return 0;

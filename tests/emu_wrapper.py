@@ -36,6 +36,7 @@ def lib():
         L.emu_create.argtypes = [ctypes.c_int, ctypes.c_int, f32p, f32p] + [ctypes.c_float] * 4 + [ctypes.c_int] * 8 + [ctypes.c_longlong]
         L.emu_destroy.argtypes = [ctypes.c_void_p]
         L.emu_set_order.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.emu_set_fix_cap.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.emu_step_iterative.argtypes = [ctypes.c_void_p, ctypes.c_int, f32p, u8p, f32p, f32p, f32p, ctypes.c_void_p, ctypes.c_int, u8p, u8p, u8p]
         L.emu_known_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, f32p, u8p, ctypes.c_int, ctypes.c_int]
         L.emu_known_clear.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -55,7 +56,7 @@ def _p(a, ct):
 
 class EmuMapper:
     def __init__(self, height, width, vfov, map_m, resolution, max_envs, mode="iterative", store=1024,
-                 tile=32, known_clouds=None, known_capacity=1 << 16, order=0, kernel_trig=False):
+                 tile=32, known_clouds=None, known_capacity=1 << 16, order=0, kernel_trig=False, fix_cap=None):
         self.kernel_trig = kernel_trig
         self.H, self.W = height, width
         self.R = math.ceil(map_m / resolution)
@@ -73,6 +74,8 @@ class EmuMapper:
                                    self.R, self.C, store, store, max_envs, tile, tile, 0 if mode == "iterative" else 1,
                                    known_capacity)
         lib().emu_set_order(self._h, order)
+        if fix_cap is not None:
+            lib().emu_set_fix_cap(self._h, fix_cap)
         self._B = 0
 
     def __del__(self):

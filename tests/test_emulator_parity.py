@@ -13,11 +13,11 @@ from oracle.oracle import OracleMapper
 from scenarios import run_mapper
 
 
-def _emu(scn, order=0, tile=32):
+def _emu(scn, order=0, tile=32, **kw):
     c = scn["cfg"]
     return EmuMapper(c["height"], c["width"], c["vfov"], c["map_m"], c["resolution"],
                      max_envs=scn["masks"].shape[1], mode=c["mode"], known_clouds=scn.get("known"),
-                     order=order, tile=tile, store=2048 if c["resolution"] < 0.1 else 1024)
+                     order=order, tile=tile, store=2048 if c["resolution"] < 0.1 else 1024, **kw)
 
 
 @pytest.mark.parametrize("order", [0, 2])
@@ -40,6 +40,22 @@ def test_emulator_matches_golden(name, order):
         assert np.array_equal(xyz.view(np.uint32), scn["ref_world_xyz"].view(np.uint32))  # same bits, same order
         assert np.array_equal(sem, scn["ref_world_sem"])
         assert emu.cand_nonzero() == 0  # scratch plane left clean
+
+
+@pytest.mark.parametrize("name", ["degenerate", "identical_envs", "scene_f32", "scene_overlap"])
+def test_emulator_hash_path_and_kernel_trig(name):
+    """Same goldens through the hash-based class resolution (the small-class fast path disabled) and
+    with the pose matrices derived by the K1 code path (ivm_pose_matrices) where angles are float64."""
+    scn = load_golden(name)
+    f64 = scn["orientation"].dtype == np.float64
+    emu = _emu(scn, order=1, fix_cap=1, kernel_trig=f64)
+    outs, sizes = run_mapper(emu.step, scn, world_fn=emu.world)
+    for t, (o, s) in enumerate(outs):
+        B = o.shape[0]
+        assert np.array_equal(o, scn["ref_occupancy"][t, :B]) and np.array_equal(s, scn["ref_semantic"][t, :B]), t
+    assert sizes == scn["ref_world_sizes"].tolist()
+    b, xyz, sem = emu.world()
+    assert np.array_equal(b, scn["ref_world_b"]) and np.array_equal(xyz.view(np.uint32), scn["ref_world_xyz"].view(np.uint32))
 
 
 def test_edge_collisions_are_exercised():

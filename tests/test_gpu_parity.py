@@ -65,6 +65,37 @@ def test_raster_tile_sizes(tile):
         assert np.array_equal(o, scn["ref_occupancy"][t]) and np.array_equal(s, scn["ref_semantic"][t])
 
 
+@pytest.mark.parametrize("variant", [0, 1])
+def test_predicted_ingest_variants(variant):
+    """Both ingest kernels of the predicted-semantics path (bulk-async ring / register-staged loads)."""
+    scn = load_golden("predicted")
+    cs, outs, _ = _run_cuda(scn, scatter_variant=variant)
+    for t, (o, s) in enumerate(outs):
+        assert np.array_equal(o, scn["ref_occupancy"][t]) and np.array_equal(s, scn["ref_semantic"][t]), t
+
+
+def test_predicted_full_size_against_oracle():
+    """BASELINE config 2 shape on 4 envs: 40-class score planes, 256x256, ties and NaNs included."""
+    from ivlnce_b200.synthetic import ScenarioConfig, make_scenario
+    from oracle.oracle import OracleMapper, argmax_labels
+    from scenarios import _wrap
+
+    c = ScenarioConfig(num_envs=4, height=256, width=256, steps=4, resolution=0.05, num_labels=40, seed=78)
+    scn = _wrap(c, make_scenario(c))
+    rng = np.random.default_rng(5)
+    lg = np.round(rng.standard_normal((c.steps, c.num_envs, 40, 256, 256)).astype(np.float32) * 4) / 4
+    lg[rng.random(lg.shape) < 1e-4] = np.nan
+    scn["logits"] = lg
+    scn["labels_for_map"] = np.stack([argmax_labels(lg[t]) for t in range(c.steps)])
+    orc = OracleMapper(c.height, c.width, c.vfov_radians, c.map_meters, c.map_meters, c.resolution)
+    ref_outs, _ = run_mapper(orc.step, scn)
+    for variant in (0, 1):
+        cs, outs, _ = _run_cuda(scn, scatter_variant=variant)
+        for t in range(c.steps):
+            assert np.array_equal(outs[t][0], ref_outs[t][0]) and np.array_equal(outs[t][1], ref_outs[t][1]), (variant, t)
+        cs.mm.check_errors()
+
+
 def test_device_trig_f64_matches():
     """sin/cos evaluated by torch on the GPU in float64 round to the same float32 matrices."""
     scn = load_golden("iid_f64")
