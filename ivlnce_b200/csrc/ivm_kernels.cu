@@ -208,13 +208,17 @@ k_ingest_scatter(IvmParams P, const float *__restrict__ logits, int ncls, uint8_
     k1_scatter_pixels<VEC>(P, b, pix0, d, sh);
 }
 
-// ---- bulk-async variant of the predicted-semantics ingest (the default when the image tiles evenly):
-// the score planes are staged through a 4-deep shared-memory ring by cp.async.bulk (the TMA engine's
-// 1-D bulk copy, SASS UBLKCP) completing on mbarriers, so ~64 KB per CTA are in flight without
-// holding registers; threads read their 4 pixels per plane from shared memory with LDS.128.
-#define IVM_BULK_TILE 1024   // pixels per CTA (= 256 threads x 4)
-#define IVM_BULK_SP 4        // planes per stage (16 KB)
-#define IVM_BULK_NSTAGE 4    // ring depth (64 KB)
+// ---- persistent bulk-async ingest of the predicted-semantics path (the default when the image
+// tiles evenly).  2 CTAs per SM stay resident and walk a contiguous range of 512-pixel tiles; the
+// score planes are staged through an 8-deep, 64 KB shared-memory ring by cp.async.bulk (the TMA
+// engine's 1-D bulk copy, SASS UBLKCP) completing on mbarriers.  The ring never drains between
+// tiles, so the loads of the next tile are in flight while a tile's labels are written and its
+// points are scattered: ~128 KB per SM outstanding at all times, no registers held by loads, no
+// wave tail.  Threads read their 2 pixels per plane from shared memory (LDS.64).
+#define IVM_BULK_TILE 512    // pixels per tile (= 256 threads x 2)
+#define IVM_BULK_SP 4        // planes per stage (8 KB)
+#define IVM_BULK_NSTAGE 8    // ring depth (64 KB)
+#define IVM_BULK_CTAS_PER_SM 2
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -238,74 +242,149 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
 }
 
-__global__ void __launch_bounds__(IVM_THREADS)
-k_ingest_scatter_bulk(IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out) {
+__global__ void __launch_bounds__(IVM_THREADS, IVM_BULK_CTAS_PER_SM)
+k_ingest_scatter_bulk(IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out,
+                      int nenv_total) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float(*ring)[IVM_BULK_SP][IVM_BULK_TILE] = reinterpret_cast<float(*)[IVM_BULK_SP][IVM_BULK_TILE]>(smem_raw);
     __shared__ __align__(8) uint64_t full[IVM_BULK_NSTAGE];
     __shared__ K1Shared sh;
-    const int b = blockIdx.y;
-    if (b >= P.B) {
-        if (blockIdx.x == 0) { IvmEnvPrep q; q.reset = 1; q.origin_r = 0; q.origin_c = 0; ivm_env_publish<IvmAtomics>(P, b, q, threadIdx.x, blockDim.x); }
-        return;
-    }
-    const int tile0 = blockIdx.x * IVM_BULK_TILE;
-    const int pix0 = tile0 + threadIdx.x * 4;
-    const float *lp = logits + (size_t)b * ncls * P.HW + tile0;
+    const int tpe = P.HW / IVM_BULK_TILE;                 // tiles per env
+    const long long total = (long long)P.B * tpe;
+    const int t0 = (int)((long long)blockIdx.x * total / gridDim.x);
+    const int t1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
     const int nchunks = (ncls + IVM_BULK_SP - 1) / IVM_BULK_SP;
+    const int my_chunks = (t1 - t0) * nchunks;
     uint64_t policy = 0;
+    auto issue = [&](int q) {  // thread 0 only
+        const int tile = t0 + q / nchunks, ch = q - (q / nchunks) * nchunks;
+        const int eb = tile / tpe, tp0 = (tile - eb * tpe) * IVM_BULK_TILE;
+        const int slot = q % IVM_BULK_NSTAGE;
+        const int p0 = ch * IVM_BULK_SP;
+        const int np = min(IVM_BULK_SP, ncls - p0);
+        const float *src = logits + ((size_t)eb * ncls + p0) * P.HW + tp0;
+        mbar_expect_tx(&full[slot], (uint32_t)(np * IVM_BULK_TILE * sizeof(float)));
+        for (int p = 0; p < np; ++p)
+            bulk_g2s(&ring[slot][p][0], src + (size_t)p * P.HW, IVM_BULK_TILE * sizeof(float), &full[slot], policy);
+    };
     if (threadIdx.x == 0) {
         for (int s = 0; s < IVM_BULK_NSTAGE; ++s) mbar_init(&full[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+        for (int q = 0; q < IVM_BULK_NSTAGE && q < my_chunks; ++q) issue(q);
     }
-    const size_t base = (size_t)b * P.HW + pix0;
-    const float4 dv = ld_stream4(P.depth + base);
+    // paused envs (mapper.py:315-318) are wiped by the last CTA
+    if (blockIdx.x == gridDim.x - 1)
+        for (int b = P.B; b < nenv_total; ++b) {
+            IvmEnvPrep q; q.reset = 1; q.origin_r = 0; q.origin_c = 0;
+            ivm_env_publish<IvmAtomics>(P, b, q, threadIdx.x, blockDim.x);
+        }
+    int rmin = INT32_MAX, rmax = INT32_MIN, cmin = INT32_MAX, cmax = INT32_MIN;
+    unsigned nvalid = 0;
+    int cur_env = -1;
     __syncthreads();  // barriers initialised
-    auto issue = [&](int ch) {
-        const int slot = ch % IVM_BULK_NSTAGE;
-        const int p0 = ch * IVM_BULK_SP;
-        const int np = min(IVM_BULK_SP, ncls - p0);
-        mbar_expect_tx(&full[slot], (uint32_t)(np * IVM_BULK_TILE * sizeof(float)));
-        for (int p = 0; p < np; ++p)
-            bulk_g2s(&ring[slot][p][0], lp + (size_t)(p0 + p) * P.HW, IVM_BULK_TILE * sizeof(float), &full[slot], policy);
-    };
-    if (threadIdx.x == 0)
-        for (int ch = 0; ch < IVM_BULK_NSTAGE && ch < nchunks; ++ch) issue(ch);
-    k1_prologue(P, b, sh, blockIdx.x == 0);
-    float best0 = 0.f, best1 = 0.f, best2 = 0.f, best3 = 0.f;
-    int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-    for (int ch = 0; ch < nchunks; ++ch) {
-        const int slot = ch % IVM_BULK_NSTAGE;
-        mbar_wait(&full[slot], (uint32_t)((ch / IVM_BULK_NSTAGE) & 1));
-        const int p0 = ch * IVM_BULK_SP;
-        const int np = min(IVM_BULK_SP, ncls - p0);
-#pragma unroll
-        for (int p = 0; p < IVM_BULK_SP; ++p) {
-            if (p < np) {
-                const float4 v = *reinterpret_cast<const float4 *>(&ring[slot][p][threadIdx.x * 4]);
-                const int k = p0 + p;
-                if (k == 0) {
-                    best0 = v.x; best1 = v.y; best2 = v.z; best3 = v.w;
-                } else {
-                    IVM_ARGMAX_STEP(v.x, k, best0, a0);
-                    IVM_ARGMAX_STEP(v.y, k, best1, a1);
-                    IVM_ARGMAX_STEP(v.z, k, best2, a2);
-                    IVM_ARGMAX_STEP(v.w, k, best3, a3);
-                }
+    for (int tile = t0; tile < t1; ++tile) {
+        const int b = tile / tpe, tp0 = (tile - b * tpe) * IVM_BULK_TILE;
+        const int pix0 = tp0 + threadIdx.x * 2;
+        const size_t base = (size_t)b * P.HW + pix0;
+        const float2 dv = __ldcs(reinterpret_cast<const float2 *>(P.depth + base));
+        if (b != cur_env) {  // block-uniform: at most twice per CTA (its tile range is contiguous)
+            __syncthreads();  // the previous env's matrices are no longer read
+            if (threadIdx.x == 0) {
+                const IvmEnvPrep q = ivm_env_decide(P, b);
+                sh.origin_r = q.origin_r; sh.origin_c = q.origin_c; sh.reset = q.reset;
+            }
+            if (P.orient != nullptr) {
+                if (threadIdx.x == 32) ivm_pose_matrices(P, b, sh.T, sh.cs);
+            } else if (threadIdx.x >= 32 && threadIdx.x < 44) {
+                sh.T[threadIdx.x - 32] = P.T12[12 * b + threadIdx.x - 32];
+            }
+            __syncthreads();
+            cur_env = b;
+        }
+        if (tp0 == 0) {  // the CTA that owns an env's first tile publishes the env's new state
+            IvmEnvPrep q;
+            q.reset = sh.reset; q.origin_r = sh.origin_r; q.origin_c = sh.origin_c;
+            ivm_env_publish<IvmAtomics>(P, b, q, threadIdx.x, blockDim.x);
+            if (P.orient != nullptr) {
+                if (threadIdx.x < 12) P.T12_buf[12 * b + threadIdx.x] = sh.T[threadIdx.x];
+                if (threadIdx.x < 2) P.cs_buf[2 * b + threadIdx.x] = sh.cs[threadIdx.x];
             }
         }
-        __syncthreads();  // every thread is done with this slot
-        if (threadIdx.x == 0 && ch + IVM_BULK_NSTAGE < nchunks) issue(ch + IVM_BULK_NSTAGE);
+        // PredictSemantics tail (mapper.py:795-798): running argmax over the planes, first max wins,
+        // NaN counts as maximal (torch.argmax)
+        float best0 = 0.f, best1 = 0.f;
+        int a0 = 0, a1 = 0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int q = (tile - t0) * nchunks + ch;
+            const int slot = q % IVM_BULK_NSTAGE;
+            mbar_wait(&full[slot], (uint32_t)((q / IVM_BULK_NSTAGE) & 1));
+            const int p0 = ch * IVM_BULK_SP;
+            const int np = min(IVM_BULK_SP, ncls - p0);
+#pragma unroll
+            for (int p = 0; p < IVM_BULK_SP; ++p) {
+                if (p < np) {
+                    const float2 v = *reinterpret_cast<const float2 *>(&ring[slot][p][threadIdx.x * 2]);
+                    const int k = p0 + p;
+                    if (k == 0) {
+                        best0 = v.x; best1 = v.y;
+                    } else {
+                        IVM_ARGMAX_STEP(v.x, k, best0, a0);
+                        IVM_ARGMAX_STEP(v.y, k, best1, a1);
+                    }
+                }
+            }
+            __syncthreads();  // every thread is done with this slot
+            if (threadIdx.x == 0 && q + IVM_BULK_NSTAGE < my_chunks) issue(q + IVM_BULK_NSTAGE);
+        }
+        uchar2 o;
+        o.x = (uint8_t)a0; o.y = (uint8_t)a1;
+        *reinterpret_cast<uchar2 *>(labels_out + base) = o;
+        // unproject + scatter this thread's two pixels (the next tile's planes are already in flight)
+        const float h = P.pose[3 * b + 1];
+        const int v = pix0 / P.W, u0 = pix0 - v * P.W;
+        const float ysv = P.ys[v];
+        const float dd[2] = {dv.x, dv.y};
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            IvmPoint p;
+            const int ok = ivm_unproject(dd[j], P.xs[u0 + j], ysv, sh.T, h, P.half_res, p);
+            if (ok == 0) continue;
+            size_t idx;
+            if (ok == 2 || !ivm_store_index(P, sh.origin_r, sh.origin_c, b, p.r, p.c, idx)) {
+                atomicOr(&P.g->err, IVM_ERR_STORE_OVERFLOW);
+                continue;
+            }
+            atomicMax(&P.cand[idx], ivm_cand_key(p.y, (uint32_t)(pix0 + j)));
+            rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
+            ++nvalid;
+        }
     }
-    uchar4 o;
-    o.x = (uint8_t)a0; o.y = (uint8_t)a1; o.z = (uint8_t)a2; o.w = (uint8_t)a3;
-    *reinterpret_cast<uchar4 *>(labels_out + base) = o;
-    const float d[4] = {dv.x, dv.y, dv.z, dv.w};
-    k1_scatter_pixels<4>(P, b, pix0, d, sh);
+    // frame bbox over ALL envs (mapper.py:465), one flush per CTA
+    __syncthreads();
+    if (threadIdx.x == 0) { sh.bb[0] = INT32_MAX; sh.bb[1] = INT32_MIN; sh.bb[2] = INT32_MAX; sh.bb[3] = INT32_MIN; sh.valid = 0; }
+    __syncthreads();
+    const unsigned wv = warp_sum(nvalid);
+    if (wv) {
+        rmin = warp_min(rmin); rmax = warp_max(rmax); cmin = warp_min(cmin); cmax = warp_max(cmax);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&sh.bb[0], rmin); atomicMax(&sh.bb[1], rmax); atomicMin(&sh.bb[2], cmin); atomicMax(&sh.bb[3], cmax);
+            atomicAdd(&sh.valid, wv);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && sh.valid) {
+        atomicMin(&P.g->loc[0], sh.bb[0]); atomicMax(&P.g->loc[1], sh.bb[1]);
+        atomicMin(&P.g->loc[2], sh.bb[2]); atomicMax(&P.g->loc[3], sh.bb[3]);
+        atomicAdd(&P.g->acc_valid, (unsigned long long)sh.valid);
+    }
 }
 
 // ------------------------------------------------------------------ K2: resolve
+// Only ~1 pixel in 4 survives the depth/height filters, scattered over the image, so the filters
+// are evaluated for all pixels first (cheap) and the survivors are compacted per warp through a
+// shared-memory queue; the expensive part (two IEEE divisions, candidate check, world-record
+// read-modify-write) then runs on dense warps.
 template <int VEC>
 __global__ void __launch_bounds__(IVM_THREADS) k_ingest_resolve(IvmParams P) {
     const int b = blockIdx.y;
@@ -314,17 +393,19 @@ __global__ void __launch_bounds__(IVM_THREADS) k_ingest_resolve(IvmParams P) {
     __shared__ int32_t sloc[4];
     __shared__ int32_t sbox[5];   // rmin, rmax, cmin, cmax, n of the cells this CTA newly occupied
     __shared__ unsigned s_local;
+    __shared__ uint32_t q_pix[IVM_THREADS / 32][32 * VEC];
+    __shared__ float q_d[IVM_THREADS / 32][32 * VEC];
+    __shared__ uint8_t q_lab[IVM_THREADS / 32][32 * VEC];
     if (threadIdx.x < 12) sT[threadIdx.x] = P.T12[12 * b + threadIdx.x];
     if (threadIdx.x >= 32 && threadIdx.x < 36) sloc[threadIdx.x - 32] = P.g->loc[threadIdx.x - 32];
     if (threadIdx.x == 64) { sbox[0] = INT32_MAX; sbox[1] = INT32_MIN; sbox[2] = INT32_MAX; sbox[3] = INT32_MIN; sbox[4] = 0; s_local = 0; }
-    __syncthreads();
-    unsigned nlocal = 0;
-    IvmBoxAcc acc;
-    acc.clear();
+    // issue the pixel loads before the barrier
+    float d[VEC];
+    uint8_t lab[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { d[j] = 2.0f; lab[j] = 0; }
     if (pix0 < P.HW) {
         const size_t base = (size_t)b * P.HW + pix0;
-        float d[VEC];
-        uint8_t lab[VEC];
         if (VEC == 4) {
             const float4 v = *reinterpret_cast<const float4 *>(P.depth + base);
             d[0] = v.x; d[1 % VEC] = v.y; d[2 % VEC] = v.z; d[3 % VEC] = v.w;
@@ -334,30 +415,60 @@ __global__ void __launch_bounds__(IVM_THREADS) k_ingest_resolve(IvmParams P) {
             d[0] = P.depth[base];
             lab[0] = P.labels[base];
         }
-        const IvmEnv *e = &P.env[b];
-        const int32_t origin_r = e->origin_r, origin_c = e->origin_c;
-        const float h = P.pose[3 * b + 1];
-        const int v = pix0 / P.W, u0 = pix0 - v * P.W;
+    }
+    const IvmEnv *e = &P.env[b];
+    const int32_t origin_r = e->origin_r, origin_c = e->origin_c;
+    const float h = P.pose[3 * b + 1];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // pass 1: filters only (depth band, then the height of the transformed point), compact survivors
+    int count = 0;
+    {
+        const int v = pix0 < P.HW ? pix0 / P.W : 0, u0 = pix0 - v * P.W;
         const float ysv = P.ys[v];
+        const float hlo = ivm_sub(h, 1.0f), hhi = ivm_add(h, 0.5f);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-            IvmPoint p;
-            if (ivm_unproject(d[j], P.xs[u0 + j], ysv, sT, h, P.half_res, p) != 1) continue;
-            nlocal += (unsigned)ivm_resolve_pixel<IvmAtomics>(P, b, (uint32_t)(pix0 + j), p, lab[j], sloc, origin_r,
-                                                              origin_c, acc);
+            bool ok = pix0 < P.HW && d[j] > 0.01f && d[j] < 0.99f;
+            if (ok) {
+                const float z = ivm_mul(d[j], 10.0f);
+                float acc = ivm_mul(sT[4], ivm_mul(z, P.xs[u0 + j]));
+                acc = ivm_fma(sT[5], ivm_mul(z, ysv), acc);
+                acc = ivm_fma(sT[6], z, acc);
+                acc = ivm_fma(sT[7], 1.0f, acc);
+                ok = acc > hlo && acc < hhi;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (ok) {
+                const int pos = count + __popc(m & ((1u << lane) - 1u));
+                q_pix[warp][pos] = (uint32_t)(pix0 + j); q_d[warp][pos] = d[j]; q_lab[warp][pos] = lab[j];
+            }
+            count += __popc(m);
         }
+    }
+    __syncwarp();
+    // pass 2: dense -- one queued pixel per lane
+    unsigned nlocal = 0;
+    IvmBoxAcc acc;
+    acc.clear();
+    for (int i = lane; i < count; i += 32) {
+        const uint32_t pix = q_pix[warp][i];
+        const int v = (int)pix / P.W, u = (int)pix - v * P.W;
+        IvmPoint p;
+        if (ivm_unproject(q_d[warp][i], P.xs[u], P.ys[v], sT, h, P.half_res, p) != 1) continue;
+        nlocal += (unsigned)ivm_resolve_pixel<IvmAtomics>(P, b, pix, p, q_lab[warp][i], sloc, origin_r, origin_c, acc);
     }
     // newly occupied cells: warp -> block -> 5 global atomics per CTA
     const unsigned wn = warp_sum((unsigned)acc.n);
     if (wn) {
         const int r0 = warp_min(acc.rmin), r1 = warp_max(acc.rmax), c0 = warp_min(acc.cmin), c1 = warp_max(acc.cmax);
-        if ((threadIdx.x & 31) == 0) {
+        if (lane == 0) {
             atomicMin(&sbox[0], r0); atomicMax(&sbox[1], r1); atomicMin(&sbox[2], c0); atomicMax(&sbox[3], c1);
             atomicAdd(&sbox[4], (int)wn);
         }
     }
     const unsigned wl = warp_sum(nlocal);
-    if (wl && (threadIdx.x & 31) == 0) atomicAdd(&s_local, wl);
+    if (wl && lane == 0) atomicAdd(&s_local, wl);
     __syncthreads();
     if (threadIdx.x == 0) {
         if (sbox[4] > 0) {
@@ -402,82 +513,91 @@ __device__ __forceinline__ void raster_record(const IvmParams &P, const uint4 ra
 }
 
 template <bool KNOWN>
-__global__ void __launch_bounds__(IVM_RASTER_THREADS) k_raster(IvmParams P) {
+__global__ void __launch_bounds__(IVM_RASTER_THREADS) k_raster(IvmParams P, int max_rows) {
     extern __shared__ uint32_t skey[];
     const int tr = P.tile_r, tc = P.tile_c;
-    uint8_t *socc = reinterpret_cast<uint8_t *>(skey + tr * tc);
+    int32_t *s_clo = reinterpret_cast<int32_t *>(skey + tr * tc);   // first store column of each half-row's span
+    int32_t *s_len = s_clo + max_rows;                              // span length (0 = nothing to read)
+    uint8_t *socc = reinterpret_cast<uint8_t *>(s_len + max_rows);
+    __shared__ int s_maxlen;
     const int b = blockIdx.z;
     const int r0 = blockIdx.y * tr, c0 = blockIdx.x * tc;
     const int r1 = min(r0 + tr, P.R), c1 = min(c0 + tc, P.C);
     for (int i = threadIdx.x; i < tr * tc; i += blockDim.x) { skey[i] = 0u; socc[i] = 0; }
-    __syncthreads();
+    if (threadIdx.x == 0) s_maxlen = 0;
     const IvmEnv e = P.env[b];
     const float px = P.pose[3 * b + 0], h = P.pose[3 * b + 1], pz = P.pose[3 * b + 2];
     const float c = P.cs[2 * b + 0], s = P.cs[2 * b + 1];
     unsigned n_in = 0;
-    if (e.count > 0) {
-        IvmTileGeom G;
-        ivm_tile_geom(P, px, pz, c, s, r0, r1, c0, c1, G);
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
-        const int row_lo = max(G.row_lo, KNOWN ? e.origin_r : e.rmin);
-        const int row_hi = min(G.row_hi, KNOWN ? e.origin_r + P.SR - 1 : e.rmax);
-        const int col_lo = KNOWN ? e.origin_c : e.cmin, col_hi = KNOWN ? e.origin_c + P.SC - 1 : e.cmax;
-        if (!KNOWN) {
-            // widest possible span of a row (diagonal of the tile in half-cells) -> chunks per row
-            const float diag = sqrtf((float)((r1 - r0) * (r1 - r0) + (c1 - c0) * (c1 - c0))) * (P.res / P.half_res);
-            const int CH = ((int)diag + 8 + 31) / 32;
-            const int nslots = (row_hi - row_lo + 1) * CH;
-            for (int sl = warp; sl < nslots; sl += 2 * nwarps) {
-                uint4 raw[2];
-                bool have[2];
-                uint32_t cell[2];
+    IvmTileGeom G;
+    ivm_tile_geom(P, px, pz, c, s, r0, r1, c0, c1, G);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    int row_lo = max(G.row_lo, KNOWN ? e.origin_r : e.rmin);
+    int row_hi = min(G.row_hi, KNOWN ? e.origin_r + P.SR - 1 : e.rmax);
+    if (e.count <= 0) row_hi = row_lo - 1;
+    if (row_hi - row_lo + 1 > max_rows) row_hi = row_lo + max_rows - 1;  // cannot happen: max_rows bounds the tile diagonal
+    const int nrows = row_hi - row_lo + 1;
+    const int col_lo = KNOWN ? e.origin_c : e.cmin, col_hi = KNOWN ? e.origin_c + P.SC - 1 : e.cmax;
+    __syncthreads();
+    // phase 1: one thread per half-row solves the column span under the rotated tile
+    for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+        int clo, chi;
+        ivm_row_span(G, row_lo + i, clo, chi);
+        clo = max(clo, col_lo); chi = min(chi, col_hi);
+        const int len = chi >= clo ? chi - clo + 1 : 0;
+        s_clo[i] = clo; s_len[i] = len;
+        if (len > 0) atomicMax(&s_maxlen, len);
+    }
+    __syncthreads();
+    if (!KNOWN) {
+        // phase 2: spans are cut into 32-record chunks; warps take chunks round-robin, two at a time
+        const int CH = (s_maxlen + 31) >> 5;
+        const int nslots = nrows * CH;
+        const IvmRecord *env_store = P.store + (size_t)b * P.SR * P.SC;
+        for (int sl = warp; sl < nslots; sl += 2 * nwarps) {
+            uint4 raw[2];
+            bool have[2];
+            uint32_t cell[2];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int slot = sl + u * nwarps;
-                    have[u] = false;
-                    raw[u] = make_uint4(0, 0, 0, 0);
-                    cell[u] = 0;
-                    if (slot < nslots) {
-                        const int rr = row_lo + slot / CH, k = slot - (slot / CH) * CH;
-                        int clo, chi;
-                        ivm_row_span(G, rr, clo, chi);
-                        clo = max(clo, col_lo); chi = min(chi, col_hi);
-                        const int cc = clo + 32 * k + lane;
-                        if (cc <= chi) {
-                            const uint32_t rrel = (uint32_t)(rr - e.origin_r), crel = (uint32_t)(cc - e.origin_c);
-                            cell[u] = rrel * (uint32_t)P.SC + crel;
-                            raw[u] = __ldg(reinterpret_cast<const uint4 *>(P.store + (size_t)b * P.SR * P.SC + cell[u]));
-                            have[u] = true;
-                        }
+            for (int u = 0; u < 2; ++u) {
+                const int slot = sl + u * nwarps;
+                have[u] = false;
+                raw[u] = make_uint4(0, 0, 0, 0);
+                cell[u] = 0;
+                if (slot < nslots) {
+                    const int i = slot / CH, k = slot - i * CH;
+                    const int off = 32 * k + lane;
+                    if (off < s_len[i]) {
+                        const uint32_t rrel = (uint32_t)(row_lo + i - e.origin_r), crel = (uint32_t)(s_clo[i] + off - e.origin_c);
+                        cell[u] = rrel * (uint32_t)P.SC + crel;
+                        raw[u] = __ldg(reinterpret_cast<const uint4 *>(env_store + cell[u]));
+                        have[u] = true;
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-                    raster_record(P, raw[u], have[u], e.reset_stamp, px, h, pz, c, s, r0, r1, c0, c1, tc, cell[u], skey, socc,
-                                  n_in);
             }
-        } else {
-            for (int rr = row_lo + warp; rr <= row_hi; rr += nwarps) {
-                int clo, chi;
-                ivm_row_span(G, rr, clo, chi);
-                clo = max(clo, col_lo); chi = min(chi, col_hi);
-                if (clo > chi) continue;
-                const uint32_t *off = P.koff + (size_t)b * ((size_t)P.SR * P.SC + 1) + (size_t)(rr - e.origin_r) * P.SC;
-                const uint32_t p0 = off[clo - e.origin_c], p1 = off[chi - e.origin_c + 1];
-                const IvmRecord *pts = P.kpts + (size_t)b * P.kcap;
-                for (uint32_t q = p0 + lane; q < p1; q += 32) {
-                    const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(pts + q));
-                    int row, col;
-                    if (!ivm_ego_cell(P, __uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), px, h, pz,
-                                      c, s, row, col))
-                        continue;
-                    if (row < r0 || row >= r1 || col < c0 || col >= c1) continue;
-                    ++n_in;
-                    const int t = (row - r0) * tc + (col - c0);
-                    socc[t] = 1;
-                    // raw.w = (npz index << 8) | label: later points overwrite earlier ones
-                    if (raw.w & 0xFFu) atomicMax(&skey[t], raw.w);
-                }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                raster_record(P, raw[u], have[u], e.reset_stamp, px, h, pz, c, s, r0, r1, c0, c1, tc, cell[u], skey, socc, n_in);
+        }
+    } else {
+        for (int i = warp; i < nrows; i += nwarps) {
+            if (s_len[i] <= 0) continue;
+            const int rr = row_lo + i, clo = s_clo[i], chi = s_clo[i] + s_len[i] - 1;
+            const uint32_t *off = P.koff + (size_t)b * ((size_t)P.SR * P.SC + 1) + (size_t)(rr - e.origin_r) * P.SC;
+            const uint32_t p0 = off[clo - e.origin_c], p1 = off[chi - e.origin_c + 1];
+            const IvmRecord *pts = P.kpts + (size_t)b * P.kcap;
+            for (uint32_t q = p0 + lane; q < p1; q += 32) {
+                const uint4 raw = __ldg(reinterpret_cast<const uint4 *>(pts + q));
+                int row, col;
+                if (!ivm_ego_cell(P, __uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), px, h, pz, c,
+                                  s, row, col))
+                    continue;
+                if (row < r0 || row >= r1 || col < c0 || col >= c1) continue;
+                ++n_in;
+                const int t = (row - r0) * tc + (col - c0);
+                socc[t] = 1;
+                // raw.w = (npz index << 8) | label: later points overwrite earlier ones
+                if (raw.w & 0xFFu) atomicMax(&skey[t], raw.w);
             }
         }
     }
@@ -663,6 +783,7 @@ struct ivm_ctx {
     int hi_water;      // envs [0, hi_water) may hold records
     int first_call;
     int bulk_attr_set;
+    int num_sms;
     int64_t launches;
     // known-mode scratch
     uint32_t *kfill, *ktotals;
@@ -782,6 +903,13 @@ int ivm_create(const ivm_config *cfg, void *workspace_dev, size_t workspace_byte
     if (tc > P.C) tc = P.C;
     P.tile_r = tr; P.tile_c = tc;
     ctx->first_call = 1;
+    ctx->num_sms = 148;
+    {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+            ctx->num_sms = sms;
+        cudaGetLastError();
+    }
     *out = ctx;
     return IVM_OK;
 }
@@ -870,9 +998,12 @@ static int next_step(ivm_ctx *ctx) {
 
 static void launch_raster(ivm_ctx *ctx, const IvmParams &P, cudaStream_t st, bool known) {
     dim3 grid((P.C + P.tile_c - 1) / P.tile_c, (P.R + P.tile_r - 1) / P.tile_r, P.B);
-    const size_t smem = (size_t)P.tile_r * P.tile_c * 5 + 16;
-    if (known) k_raster<true><<<grid, IVM_RASTER_THREADS, smem, st>>>(P);
-    else k_raster<false><<<grid, IVM_RASTER_THREADS, smem, st>>>(P);
+    // half-rows under a rotated tile: its diagonal in half-cells + the conservative margins
+    const float diag = sqrtf((float)(P.tile_r * P.tile_r + P.tile_c * P.tile_c)) * (P.res / P.half_res);
+    const int max_rows = (int)diag + 12;
+    const size_t smem = (size_t)P.tile_r * P.tile_c * 5 + (size_t)max_rows * 8 + 16;
+    if (known) k_raster<true><<<grid, IVM_RASTER_THREADS, smem, st>>>(P, max_rows);
+    else k_raster<false><<<grid, IVM_RASTER_THREADS, smem, st>>>(P, max_rows);
     ctx->launches += 1;
 }
 
@@ -918,7 +1049,10 @@ int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const
             if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(k_ingest_scatter_bulk)");
             ctx->bulk_attr_set = 1;
         }
-        k_ingest_scatter_bulk<<<dim3(P.HW / IVM_BULK_TILE, nenv), IVM_THREADS, smem, st>>>(P, logits, num_classes, labels_out);
+        long long tiles = (long long)num_envs * (P.HW / IVM_BULK_TILE);
+        int ctas = ctx->num_sms * IVM_BULK_CTAS_PER_SM;
+        if (ctas > tiles) ctas = (int)tiles;
+        k_ingest_scatter_bulk<<<ctas, IVM_THREADS, smem, st>>>(P, logits, num_classes, labels_out, nenv);
     } else if (logits) {
         if (vec4) k_ingest_scatter<true, 4><<<grid, IVM_THREADS, 0, st>>>(P, logits, num_classes, labels_out);
         else k_ingest_scatter<true, 1><<<grid, IVM_THREADS, 0, st>>>(P, logits, num_classes, labels_out);
