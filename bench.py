@@ -57,11 +57,15 @@ def parse_args():
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--seed", type=int, default=1002)
+    ap.add_argument("--store", type=int, default=0, help="override the world-store extent (half-cells per side)")
+    ap.add_argument("--roam", type=float, default=8.0, help="radius (m) the synthetic walk stays within")
+    ap.add_argument("--variant", type=int, default=0,
+                    help="0 = fused persistent step kernel (default), 1/2 = four-kernel step (register / bulk-async loads)")
     return ap.parse_args()
 
 
 # ------------------------------------------------------------------------------------------ inputs
-def make_poses(cfg, steps, seed):
+def make_poses(cfg, steps, seed, roam=8.0):
     """Random walk of 0.25 m forward steps / 15 degree turns per env, kept within 8 m
     of its start (a house-sized area).  Every env lives in its own scene, and scene coordinates all lie near
     the origin (as in MP3D), so the envs' world coordinates overlap -- this keeps the reference's de-dup key
@@ -70,7 +74,7 @@ def make_poses(cfg, steps, seed):
     from ivlnce_b200.synthetic import ScenarioConfig, random_walk, reset_masks
 
     sc = ScenarioConfig(num_envs=cfg["envs"], height=cfg["H"], width=cfg["W"], steps=steps, resolution=cfg["res"],
-                        map_meters=cfg["map_m"], num_labels=cfg["classes"], seed=seed, env_spacing=0.0, roam_radius=8.0)
+                        map_meters=cfg["map_m"], num_labels=cfg["classes"], seed=seed, env_spacing=0.0, roam_radius=roam)
     pose, orient = random_walk(sc, np.random.default_rng(seed))
     return pose, orient, reset_masks(sc)
 
@@ -88,13 +92,13 @@ def make_frames(cfg, device, seed):
     return depth, sem
 
 
-def build_module(cfg, device, max_envs):
+def build_module(cfg, device, max_envs, variant=0):
     from ivlnce_b200.mapper import (CameraParameters, MapDimensions, PrecomputedScores,
                                     create_gt_semantics_iterative_mapper, create_iterative_mapper)
 
     cam = CameraParameters(math.pi / 2, (cfg["H"], cfg["W"]), 0.1)
     md = MapDimensions(cfg["map_m"], cfg["map_m"], cfg["res"])
-    kw = dict(store_cells=cfg["store"], max_envs=max_envs, trig="kernel")
+    kw = dict(store_cells=cfg["store"], max_envs=max_envs, trig="kernel", scatter_variant=variant)
     if cfg["pred"]:
         return create_iterative_mapper(device, cam, md, PrecomputedScores(), **kw)
     return create_gt_semantics_iterative_mapper(device, cam, md, **kw)
@@ -202,6 +206,8 @@ def main():
     cfg = dict(WORKLOADS[args.workload])
     if args.envs_per_gpu:
         cfg["envs"] = args.envs_per_gpu
+    if args.store:
+        cfg["store"] = args.store
     B = cfg["envs"]
     K, Wm = args.steps, max(args.warmup, 0)
     config = {"workload": f"{args.workload}: {cfg['desc']}", "envs_per_gpu": B, "depth": [cfg["H"], cfg["W"]],
@@ -214,7 +220,7 @@ def main():
         if rank != 0:
             return 0
         total = Wm + K + 1
-        pose, orient, masks = make_poses(cfg, total, args.seed)
+        pose, orient, masks = make_poses(cfg, total, args.seed, args.roam)
         depth, sem = make_frames(cfg, torch.device("cpu"), args.seed)
         r = cpu_reference_run(cfg, (depth, sem), pose, orient, masks, min(Wm, 3), K, args.cpu_budget_s)
         sample = (f"{r['steps']} timed steps of the {args.workload} workload ({B} envs/step, world cloud growing from a "
@@ -253,13 +259,13 @@ def main():
         torch.cuda.synchronize(dev)
 
     total = 2 * (Wm + K) + 64
-    pose, orient, masks = make_poses(cfg, total, args.seed + 17 * rank)
+    pose, orient, masks = make_poses(cfg, total, args.seed + 17 * rank, args.roam)
     depth, sem = make_frames(cfg, dev, args.seed + 17 * rank)
     pose_d = torch.from_numpy(pose).to(dev)
     orient_d = torch.from_numpy(orient).to(dev)
     masks_d = torch.from_numpy(masks).to(dev)
     names = [f"scene{rank}_{b}" for b in range(B)]
-    mm = build_module(cfg, dev, B)
+    mm = build_module(cfg, dev, B, args.variant)
 
     def step(t):
         return call_module(mm, cfg, names, masks_d[t], pose_d[t], orient_d[t], depth[t % RING], sem[t % RING])
@@ -306,7 +312,26 @@ def main():
     stage_ms, stage_n = mm.stage_times(reset=True)
     mm.set_timing(False)
     _, stats = mm.status()
-    names_k = ["prep", "ingest_scatter", "ingest_resolve", "edge_fixup", "raster"]
+    fused = any(mm.phase_ns())
+    phase_us = None
+    if fused:  # split inside the fused kernel: %globaltimer stamps of the phase boundaries, averaged over 32 steps
+        acc = np.zeros(5)
+        facc = np.zeros(7)
+        bacc = np.zeros(5)
+        for _ in range(32):
+            step(t); t += 1
+            ns = mm.phase_ns()
+            acc += np.diff(np.asarray(ns[:6], dtype=np.float64))
+            tr = mm.fixup_trace_ns()
+            facc += np.diff(np.asarray([ns[2]] + tr[:7], dtype=np.float64))
+            bacc += np.diff(np.asarray([ns[1]] + tr[8:12] + [ns[2]], dtype=np.float64))
+        phase_us = dict(zip(["ingest_scatter", "resolve", "edge_fixup", "raster_release", "raster"], (acc / 32e3).tolist()))
+        phase_us["fixup_split_cta0"] = dict(zip(["enter", "stage1", "bbox_segments", "grid_barrier", "edge_scan+grid_barrier",
+                                                 "stage2", "publish"], (facc / 32e3).tolist()))
+        phase_us["resolve_split_cta0"] = dict(zip(["slot_setup", "filter", "drain", "box_flush", "grid_barrier"], (bacc / 32e3).tolist()))
+        phase_us["edge_entries"] = {"e1": int(stats[4]), "e2": int(stats[5]), "merged_total": int(stats[6]),
+                                    "scan_segments": int(stats[7]) >> 32, "scan_cells": int(stats[7]) & 0xFFFFFFFF}
+    names_k = ["prep", "step_fused" if fused else "ingest_scatter", "ingest_resolve", "edge_fixup", "raster"]
     per_kernel = {n: (stage_ms[i] / max(stage_n[i], 1)) for i, n in enumerate(names_k)}
     dom = max(per_kernel, key=per_kernel.get)
     HW = cfg["H"] * cfg["W"]
@@ -316,6 +341,7 @@ def main():
     bytes_in = HW * 4 + (HW * 4 * cfg["classes"] if cfg["pred"] else HW)
     bytes_frame = bytes_in + 2 * R * R + 16 * (2 * p_local + p_in)
     kernel_bytes = {  # per launch (B env-frames); see DESIGN.md "Kernels"
+        "step_fused": B * bytes_frame,
         "ingest_scatter": B * (bytes_in + (HW if cfg["pred"] else 0)),
         "ingest_resolve": B * (HW * 5 + 16 * 2 * p_local),
         "raster": B * (16 * p_in + 2 * R * R),
@@ -336,10 +362,15 @@ def main():
         pass
     roofline = {"bound": "hbm", "kernel": dom, "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
                 "frac": dom_gbs / peak, "traffic": traffic, "peak_source": peak_src,
-                "kernel_ms": per_kernel, "kernel_alg_bytes_per_launch": kernel_bytes,
+                "kernel_ms": {k: v for k, v in per_kernel.items() if v > 0},
+                "kernel_alg_bytes_per_launch": {k: kernel_bytes[k] for k in per_kernel if per_kernel[k] > 0},
                 "step_alg_bytes_per_env_frame": bytes_frame,
                 "step_achieved_gbs": bytes_frame * value / world / 1e9,
                 "step_frac": bytes_frame * value / world / 1e9 / peak}
+    if phase_us is not None:
+        roofline["phase_us"] = phase_us
+        ing = B * (bytes_in + (HW if cfg["pred"] else 0))
+        roofline["ingest_phase_gbs"] = ing / (phase_us["ingest_scatter"] * 1e-6) / 1e9 if phase_us["ingest_scatter"] > 0 else None
 
     # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
     e2e = None
@@ -427,6 +458,7 @@ def main():
                 "warmup": max(Wm, 3), "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
                 "gpu_launches": int(launches), "roofline": roofline}
+        line["config"]["step"] = ("one fused persistent kernel per step" if fused else "four kernels per step") + f" (variant {args.variant})"
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:

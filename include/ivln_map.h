@@ -52,11 +52,13 @@ typedef struct ivm_config {
     int32_t mode;         /* 0 = iterative (depth ingested every step), 1 = known map */
     int64_t known_capacity; /* known mode: max points per env */
     int32_t tile_rows, tile_cols;   /* ego tile per raster CTA; 0 = choose */
-    int32_t reserved[4];
+    int32_t reserved[4];  /* [0] step variant: 0 = auto (fused persistent kernel when it applies), 1 = four
+                           * kernels with register-staged score loads, 2 = four kernels with the bulk-async ring */
 } ivm_config;
 
 typedef struct ivm_status {
-    uint32_t error_flags; /* 1 = point outside world store, 2 = edge list overflow, 4 = known cloud overflow */
+    uint32_t error_flags; /* 1 = point outside world store, 2 = edge list overflow, 4 = known cloud overflow,
+                           * 8 = grid barrier time-out in the fused kernel */
     uint32_t pad;
     uint64_t stats[8];    /* valid pixels, frame survivors, world records, rasterised records, e1, e2, merged, - */
 } ivm_status;
@@ -114,9 +116,19 @@ int ivm_read_status(ivm_ctx *ctx, ivm_status *host_out, ivm_stream_t stream);
 /* Per-kernel device timing: when enabled, CUDA events bracket each kernel of the next
  * steps; ivm_stage_times returns the accumulated milliseconds per stage since the last
  * reset (synchronises the events).  Stages: 0 prep, 1 ingest-scatter, 2 ingest-resolve,
- * 3 edge fix-up, 4 raster. */
+ * 3 edge fix-up, 4 raster.  When a step runs as the single fused persistent kernel
+ * (config.reserved[0] == 0 and the image tiles evenly), the whole step is booked under
+ * stage 1 and stages 2-4 stay empty; ivm_read_phase_ns gives the split inside it. */
 int ivm_set_timing(ivm_ctx *ctx, int32_t enabled);
 int ivm_stage_times(ivm_ctx *ctx, float *ms_out5, int32_t *launches_out5, int32_t reset);
+
+/* Fused step kernel only: %globaltimer (ns) at the phase boundaries of the LAST step --
+ * [0] start, [1] ingest-scatter done, [2] resolve done, [3] edge fix-up done, [4] raster
+ * released, [5] end (max over CTAs), [6..7] unused; [8..23] milestones inside the edge
+ * fix-up (start, stage-1 classes, stage-1 merges, bbox + segments, edge-line scan, stage-2
+ * classes, end; rest unused).  [0..7] are all zero if the last step took the multi-kernel
+ * path.  `ns_out24` has room for 24 values.  Synchronises `stream`. */
+int ivm_read_phase_ns(ivm_ctx *ctx, uint64_t *ns_out24, ivm_stream_t stream);
 
 /* Number of kernels launched by this context so far. */
 int64_t ivm_kernel_launches(const ivm_ctx *ctx);

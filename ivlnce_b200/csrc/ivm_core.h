@@ -24,8 +24,26 @@
 
 #if defined(__CUDACC__)
 #define IVM_HD __host__ __device__ __forceinline__
+// Out-of-line on the device: rarely executed or called from several places.  The step kernel runs
+// every phase once per launch, so its cost is dominated by first-touch instruction fetches; code
+// that is not executed must not sit in the fetched path, and code used twice must exist once.
+#define IVM_HD_COLD __host__ __device__ __noinline__
 #else
 #define IVM_HD inline
+#define IVM_HD_COLD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define IVM_TRACE(g, k, tid)                                                      \
+    do {                                                                          \
+        if ((tid) == 0) {                                                         \
+            unsigned long long _t;                                                \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(_t));                \
+            (g)->ttrace[k] = _t;                                                  \
+        }                                                                         \
+    } while (0)
+#else
+#define IVM_TRACE(g, k, tid) do { } while (0)
 #endif
 
 // ---------------------------------------------------------------------------
@@ -98,6 +116,7 @@ struct IvmEdge {
 #define IVM_ERR_STORE_OVERFLOW 1u  // a point fell outside an env's world store window
 #define IVM_ERR_EDGE_OVERFLOW 2u   // edge list / hash capacity exceeded
 #define IVM_ERR_KNOWN_OVERFLOW 4u  // known-map cloud larger than capacity / index range
+#define IVM_ERR_GRID_BARRIER 8u    // a grid barrier of the fused step kernel timed out (results invalid)
 
 struct IvmGlobal {
     int32_t loc[4];               // frame (stage-1) bbox over all envs: rmin,rmax,cmin,cmax
@@ -108,9 +127,15 @@ struct IvmGlobal {
     uint32_t err;
     uint32_t any_dirty;
     uint32_t n_seg;
-    uint32_t pad1[3];
+    uint32_t scan_chunks;         // chunks of IVM_SCAN_CHUNK cells per edge-line segment (longest segment)
+    uint32_t pad1[2];
     unsigned long long acc_valid, acc_local;  // per-step accumulators (K1 / K2+F), published and zeroed by F
     unsigned long long stats[IVM_NSTATS];     // published figures of the last step; stats[IN] accumulates in K4
+    // fused step kernel only
+    unsigned long long tstamp[8];             // %globaltimer at the phase boundaries of the last fused step:
+                                              // 0 start, 1 ingest done, 2 resolve done, 3 fix-up done, 4 raster released,
+                                              // 5 max over CTAs of the end time
+    unsigned long long ttrace[16];            // %globaltimer at the milestones inside the fix-up program (device only)
 };
 
 struct IvmParams {
@@ -127,6 +152,9 @@ struct IvmParams {
     IvmEnv *env;                  // [maxB]
     int32_t *rowcount, *colcount; // [maxB][SR], [maxB][SC] live records per store row / col
     IvmGlobal *g;
+    uint32_t *bar;                // grid-barrier arrival counter of the fused step kernel, alone in its own 256-byte
+                                  // block (CTAs spin on it; nothing else may share its L2 slice line), monotone
+                                  // across launches (the host tracks the base)
     IvmEdge *e1, *e2;             // edge lists, capacity ecap each
     uint32_t ecap;
     int32_t *segs;                // [4*maxB][4] edge-line segments to scan: b, is_col, line, pad
@@ -155,6 +183,24 @@ struct IvmParams {
 };
 
 #define IVM_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+
+// Record / candidate loads.  In the fused step kernel these locations are written by other SMs
+// earlier in the SAME launch, so the device versions read through L2 (ld.global.cg) and never
+// from a possibly stale L1 line.
+#if defined(__CUDA_ARCH__)
+IVM_HD IvmRecord ivm_load_record(const IvmRecord *p) {
+    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
+    IvmRecord r;
+    r.x = __uint_as_float(v.x); r.y = __uint_as_float(v.y); r.z = __uint_as_float(v.z); r.meta = v.w;
+    return r;
+}
+IVM_HD unsigned long long ivm_load_cand(const unsigned long long *p) { return __ldcg(p); }
+IVM_HD uint32_t ivm_load_meta(const IvmRecord *p) { return __ldcg(&p->meta); }
+#else
+IVM_HD uint32_t ivm_load_meta(const IvmRecord *p) { return p->meta; }
+IVM_HD IvmRecord ivm_load_record(const IvmRecord *p) { return *p; }
+IVM_HD unsigned long long ivm_load_cand(const unsigned long long *p) { return *p; }
+#endif
 
 IVM_HD bool ivm_live(uint32_t meta, uint32_t reset_stamp) {
     return meta != 0u && (meta >> 8) >= reset_stamp;
@@ -272,21 +318,29 @@ IVM_HD void ivm_box_flush(IvmEnv *e, const IvmBoxAcc &a) {
 // Insert the frame/edge survivor into the world store ("world.concatenate(local)" +
 // second keep_highest for a cell that does not collide): the older record wins ties
 // because world points precede local points in the list (mapper.py:226-230, 299-308).
+// `old` = the cell's current record, `reset_stamp` / origin = the env's (callers that already hold
+// them pass them in, so that the hot loops issue no dependent loads of the env struct).
 template <class A>
-IVM_HD void ivm_merge_into_world(const IvmParams &P, int b, size_t idx, int32_t r, int32_t c, float x, float y, float z,
-                                 uint32_t label, IvmBoxAcc &acc) {
-    const IvmEnv *e = &P.env[b];
-    const IvmRecord old = P.store[idx];
-    const bool live = ivm_live(old.meta, e->reset_stamp);
+IVM_HD void ivm_merge_record(const IvmParams &P, int b, size_t idx, int32_t r, int32_t c, float x, float y, float z,
+                             uint32_t label, const IvmRecord &old, uint32_t reset_stamp, int32_t origin_r, int32_t origin_c,
+                             IvmBoxAcc &acc) {
+    const bool live = ivm_live(old.meta, reset_stamp);
     if (live && !(y > old.y)) return;
     IvmRecord rec;
     rec.x = x; rec.y = y; rec.z = z; rec.meta = (P.step << 8) | (label & 0xFFu);
     P.store[idx] = rec;
     if (!live) {
-        A::add_i(&P.rowcount[(size_t)b * P.SR + (r - e->origin_r)], 1);
-        A::add_i(&P.colcount[(size_t)b * P.SC + (c - e->origin_c)], 1);
+        A::add_i(&P.rowcount[(size_t)b * P.SR + (r - origin_r)], 1);
+        A::add_i(&P.colcount[(size_t)b * P.SC + (c - origin_c)], 1);
         acc.add(r, c);
     }
+}
+template <class A>
+IVM_HD void ivm_merge_into_world(const IvmParams &P, int b, size_t idx, int32_t r, int32_t c, float x, float y, float z,
+                                 uint32_t label, IvmBoxAcc &acc) {
+    const IvmEnv *e = &P.env[b];
+    const IvmRecord old = ivm_load_record(&P.store[idx]);
+    ivm_merge_record<A>(P, b, idx, r, c, x, y, z, label, old, e->reset_stamp, e->origin_r, e->origin_c, acc);
 }
 
 // ---------------------------------------------------------------------------
@@ -346,10 +400,11 @@ IVM_HD void ivm_pose_matrices_t(const float *pose, F elevation, F heading, float
     T[0] = (float)cy; T[1] = (float)(sx * sy); T[2] = (float)(cx * sy); T[3] = pose[0];
     T[4] = 0.0f;      T[5] = (float)cx;        T[6] = (float)(-sx);     T[7] = pose[1];
     T[8] = (float)(-sy); T[9] = (float)(cy * sx); T[10] = (float)(cy * cx); T[11] = pose[2];
-    const F a = -heading;
-    cs[0] = (float)ivm_cos(a); cs[1] = (float)ivm_sin(a);
+    // cos(-a) = cos(a) and sin(-a) = -sin(a) hold exactly for libm / libdevice (odd/even symmetric
+    // implementations), so the reference's cos(-heading), sin(-heading) need no second evaluation
+    cs[0] = (float)cy; cs[1] = (float)(-sy);
 }
-IVM_HD void ivm_pose_matrices(const IvmParams &P, int b, float *T, float *cs) {
+IVM_HD_COLD void ivm_pose_matrices(const IvmParams &P, int b, float *T, float *cs) {
     if (P.orient_f64) {
         const double *o = (const double *)P.orient;
         ivm_pose_matrices_t<double>(P.pose + 3 * b, o[2 * b], o[2 * b + 1], T, cs);
@@ -375,24 +430,34 @@ IVM_HD void ivm_reset_step_globals(IvmGlobal *g) {
 // list (they may collide with other cells); all others are
 // merged into the world store directly.  Returns 1 if the pixel was a
 // non-edge winner (for the LOCAL statistic).
+// does the candidate word of a cell name this pixel (and its height) as the frame winner?
+IVM_HD bool ivm_cand_is_mine(unsigned long long cand, uint32_t pix, float y) {
+    return (uint32_t)(cand & 0xFFFFFFFFull) == 0xFFFFFFFFu - pix && (uint32_t)(cand >> 32) == ivm_orderable(y);
+}
+IVM_HD bool ivm_on_frame_edge(const IvmPoint &p, const int32_t *loc) {
+    return p.r == loc[0] || p.r == loc[1] || p.c == loc[2] || p.c == loc[3];
+}
+// a frame winner on the frame bbox edge waits in the edge list for the fix-up
+template <class A>
+IVM_HD void ivm_push_edge1(const IvmParams &P, int b, uint32_t pix, const IvmPoint &p, uint32_t label, size_t idx) {
+    const uint32_t k = A::add_u(&P.g->n_e1, 1u);
+    if (k >= P.ecap) { A::or_u(&P.g->err, IVM_ERR_EDGE_OVERFLOW); return; }
+    IvmEdge ed;
+    ed.x = p.x; ed.y = p.y; ed.z = p.z; ed.label = label;
+    ed.b = b; ed.r = p.r; ed.c = p.c; ed.slot = 0;
+    ed.xorder = (unsigned long long)b * (unsigned long long)P.HW + pix;  // position in the frame point list
+    ed.addr = idx;
+    P.e1[k] = ed;
+}
 template <class A>
 IVM_HD int ivm_resolve_pixel(const IvmParams &P, int b, uint32_t pix, const IvmPoint &p, uint32_t label,
                              const int32_t *loc, int32_t origin_r, int32_t origin_c, IvmBoxAcc &acc) {
     size_t idx;
     if (!ivm_store_index(P, origin_r, origin_c, b, p.r, p.c, idx)) return 0;  // overflow was flagged by the scatter
-    const unsigned long long cand = P.cand[idx];
-    if ((uint32_t)(cand & 0xFFFFFFFFull) != 0xFFFFFFFFu - pix || (uint32_t)(cand >> 32) != ivm_orderable(p.y)) return 0;
+    if (!ivm_cand_is_mine(ivm_load_cand(&P.cand[idx]), pix, p.y)) return 0;
     P.cand[idx] = 0ull;  // leave the scratch plane clean for the next step
-    const bool edge = p.r == loc[0] || p.r == loc[1] || p.c == loc[2] || p.c == loc[3];
-    if (edge) {
-        const uint32_t k = A::add_u(&P.g->n_e1, 1u);
-        if (k >= P.ecap) { A::or_u(&P.g->err, IVM_ERR_EDGE_OVERFLOW); return 0; }
-        IvmEdge ed;
-        ed.x = p.x; ed.y = p.y; ed.z = p.z; ed.label = label;
-        ed.b = b; ed.r = p.r; ed.c = p.c; ed.slot = 0;
-        ed.xorder = (unsigned long long)b * (unsigned long long)P.HW + pix;  // position in the frame point list
-        ed.addr = idx;
-        P.e1[k] = ed;
+    if (ivm_on_frame_edge(p, loc)) {
+        ivm_push_edge1<A>(P, b, pix, p, label, idx);
         return 0;
     }
     ivm_merge_into_world<A>(P, b, idx, p.r, p.c, p.x, p.y, p.z, label, acc);
@@ -415,33 +480,14 @@ struct IvmFixScratch {
     unsigned long long *key, *xo;  // [cap]
     uint32_t *ord;                 // [cap]
     uint32_t cap;
-    int32_t *ibuf;                 // [8]: 0..3 world bbox, 4 segment count, 5 any-dirty
+    int32_t *ibuf;                 // [8]: 0..3 world bbox, 4 segment count, 5 any-dirty, 6 longest segment
     unsigned long long *lbuf;      // [2]: 0 live-record total
 };
 
-// on return E[i].slot = 0xFFFFFFFF for losers, anything else for winners
+// many entries: open-addressing hash in global memory
 template <class A>
-IVM_HD void ivm_resolve_classes(const IvmParams &P, IvmEdge *E, uint32_t n, int32_t rmin, int32_t cmin, long long Rx,
-                                long long Cx, const IvmFixScratch &S, int tid, int nthreads) {
-    if (n <= S.cap) {
-        // few entries (the usual case: a bbox edge holds a handful of points): all-pairs in block memory
-        for (uint32_t i = tid; i < n; i += nthreads) {
-            S.key[i] = ivm_list_key(E[i].b, E[i].r, E[i].c, rmin, cmin, Rx, Cx);
-            S.ord[i] = ivm_orderable(E[i].y);
-            S.xo[i] = E[i].xorder;
-        }
-        A::sync();
-        for (uint32_t i = tid; i < n; i += nthreads) {
-            const unsigned long long ki = S.key[i], xi = S.xo[i];
-            const uint32_t oi = S.ord[i];
-            bool lose = false;
-            for (uint32_t j = 0; j < n; ++j)
-                if (S.key[j] == ki && (S.ord[j] > oi || (S.ord[j] == oi && S.xo[j] < xi))) { lose = true; break; }
-            E[i].slot = lose ? 0xFFFFFFFFu : 0u;
-        }
-        A::sync();
-        return;
-    }
+IVM_HD_COLD void ivm_resolve_classes_hash(const IvmParams &P, IvmEdge *E, uint32_t n, int32_t rmin, int32_t cmin,
+                                          long long Rx, long long Cx, int tid, int nthreads) {
     for (uint32_t i = tid; i < n; i += nthreads) {
         const unsigned long long k = ivm_list_key(E[i].b, E[i].r, E[i].c, rmin, cmin, Rx, Cx);
         uint32_t s = ivm_mix(k) & P.hmask;
@@ -473,13 +519,40 @@ IVM_HD void ivm_resolve_classes(const IvmParams &P, IvmEdge *E, uint32_t n, int3
     A::sync();
 }
 
+// on return E[i].slot = 0xFFFFFFFF for losers, anything else for winners.  One out-of-line copy
+// serves both de-dup stages (the second call finds the code already fetched).
+template <class A>
+IVM_HD_COLD void ivm_resolve_classes(const IvmParams &P, IvmEdge *E, uint32_t n, int32_t rmin, int32_t cmin, long long Rx,
+                                     long long Cx, const IvmFixScratch &S, int tid, int nthreads) {
+    if (n > S.cap) {
+        ivm_resolve_classes_hash<A>(P, E, n, rmin, cmin, Rx, Cx, tid, nthreads);
+        return;
+    }
+    // few entries (the usual case: a bbox edge holds a handful of points): all-pairs in block memory
+    for (uint32_t i = tid; i < n; i += nthreads) {
+        S.key[i] = ivm_list_key(E[i].b, E[i].r, E[i].c, rmin, cmin, Rx, Cx);
+        S.ord[i] = ivm_orderable(E[i].y);
+        S.xo[i] = E[i].xorder;
+    }
+    A::sync();
+    for (uint32_t i = tid; i < n; i += nthreads) {
+        const unsigned long long ki = S.key[i], xi = S.xo[i];
+        const uint32_t oi = S.ord[i];
+        bool lose = false;
+        for (uint32_t j = 0; j < n; ++j)
+            if (S.key[j] == ki && (S.ord[j] > oi || (S.ord[j] == oi && S.xo[j] < xi))) { lose = true; break; }
+        E[i].slot = lose ? 0xFFFFFFFFu : 0u;
+    }
+    A::sync();
+}
+
 // scan one store cell of an edge line; live records join the stage-2 edge list
 template <class A>
-IVM_HD void ivm_scan_edge_cell(const IvmParams &P, int b, int32_t r, int32_t c, const int32_t *loc) {
+IVM_HD_COLD void ivm_scan_edge_cell(const IvmParams &P, int b, int32_t r, int32_t c, const int32_t *loc) {
     const IvmEnv &e = P.env[b];
     size_t idx;
     if (!ivm_store_index(P, e.origin_r, e.origin_c, b, r, c, idx)) return;
-    const IvmRecord rec = P.store[idx];
+    const IvmRecord rec = ivm_load_record(&P.store[idx]);
     if (!ivm_live(rec.meta, e.reset_stamp)) return;
     const uint32_t k = A::add_u(&P.g->n_e2, 1u);
     if (k >= P.ecap) { A::or_u(&P.g->err, IVM_ERR_EDGE_OVERFLOW); return; }
@@ -498,16 +571,49 @@ IVM_HD void ivm_scan_edge_cell(const IvmParams &P, int b, int32_t r, int32_t c, 
     P.e2[k] = ed;
 }
 
-// F: the edge fix-up of both de-dup stages + bbox bookkeeping, one thread block.
+// exact bbox of the envs that lost records, from the per-row / per-column live counts
 template <class A>
-IVM_HD void ivm_fixup_program(const IvmParams &P, const IvmFixScratch &S, int tid, int nthreads) {
+IVM_HD_COLD void ivm_rebuild_dirty_boxes(const IvmParams &P, int tid, int nthreads) {
+    for (int b = tid; b < P.B; b += nthreads) {
+        IvmEnv *e = &P.env[b];
+        if (e->dirty) { e->rmin = INT32_MAX; e->rmax = INT32_MIN; e->cmin = INT32_MAX; e->cmax = INT32_MIN; }
+    }
+    A::sync();
+    const long long per_env = (long long)P.SR + P.SC;
+    for (long long i = tid; i < per_env * P.B; i += nthreads) {
+        const int b = (int)(i / per_env);
+        IvmEnv *e = &P.env[b];
+        if (!e->dirty) continue;
+        const int j = (int)(i - (long long)b * per_env);
+        if (j < P.SR) {
+            if (P.rowcount[(size_t)b * P.SR + j] > 0) { A::min_i(&e->rmin, e->origin_r + j); A::max_i(&e->rmax, e->origin_r + j); }
+        } else {
+            const int jc = j - P.SR;
+            if (P.colcount[(size_t)b * P.SC + jc] > 0) { A::min_i(&e->cmin, e->origin_c + jc); A::max_i(&e->cmax, e->origin_c + jc); }
+        }
+    }
+    A::sync();
+    for (int b = tid; b < P.B; b += nthreads) P.env[b].dirty = 0;
+}
+
+// F: the edge fix-up of both de-dup stages + bbox bookkeeping, in three parts so that the fused
+// step kernel can spread the middle one (the edge-line scan) over the whole grid:
+//   ivm_fixup_stage1  one thread block: stage-1 classes + merges, world bbox, edge-line segments
+//   ivm_fixup_scan    any number of blocks: live records on the edge lines -> stage-2 edge list
+//   ivm_fixup_stage2  one thread block: stage-2 classes, deletions, bookkeeping, publish
+// State handed from part to part lives in IvmGlobal (glob[], n_seg, scan_chunks) and P.segs.
+#define IVM_SCAN_CHUNK 256   // cells of one segment handled by one block pass
+
+template <class A>
+IVM_HD void ivm_fixup_stage1(const IvmParams &P, const IvmFixScratch &S, int tid, int nthreads) {
     IvmGlobal *g = P.g;
     const uint32_t n1 = g->n_e1 < P.ecap ? g->n_e1 : P.ecap;
     const int32_t loc[4] = {g->loc[0], g->loc[1], g->loc[2], g->loc[3]};
     if (tid == 0) {
         S.ibuf[0] = INT32_MAX; S.ibuf[1] = INT32_MIN; S.ibuf[2] = INT32_MAX; S.ibuf[3] = INT32_MIN;
-        S.ibuf[4] = 0; S.ibuf[5] = 0; S.lbuf[0] = 0ull;
+        S.ibuf[4] = 0; S.ibuf[5] = 0; S.ibuf[6] = 0;
     }
+    IVM_TRACE(g, 0, tid);
     // ---- stage 1: collisions on the frame bbox edge (mapper.py:840-842)
     if (n1 > 0) {
         ivm_resolve_classes<A>(P, P.e1, n1, loc[0], loc[2], (long long)loc[1] - loc[0], (long long)loc[3] - loc[2], S, tid,
@@ -523,6 +629,7 @@ IVM_HD void ivm_fixup_program(const IvmParams &P, const IvmFixScratch &S, int ti
         }
     }
     A::sync();
+    IVM_TRACE(g, 1, tid);
     // ---- stage-2 bbox over all live records of all envs (mapper.py:461-469 on world + frame survivors)
     for (int b = tid; b < P.B; b += nthreads) {
         const IvmEnv &e = P.env[b];
@@ -534,10 +641,9 @@ IVM_HD void ivm_fixup_program(const IvmParams &P, const IvmFixScratch &S, int ti
     A::sync();
     const int32_t grmin = S.ibuf[0], grmax = S.ibuf[1], gcmin = S.ibuf[2], gcmax = S.ibuf[3];
     const bool alive = grmin <= grmax;  // else nothing alive: the reference skips keep_highest on an empty cloud
-    uint32_t n2 = 0;
     if (alive) {
         // ---- which edge lines hold records?  an env has cells on a global edge line only if its own
-        //      bbox touches that line.
+        //      bbox touches that line.  segs[q] = (env, is_col, line, cells to scan)
         for (int b = tid; b < P.B; b += nthreads) {
             const IvmEnv &e = P.env[b];
             if (e.count <= 0) continue;
@@ -547,22 +653,63 @@ IVM_HD void ivm_fixup_program(const IvmParams &P, const IvmFixScratch &S, int ti
             for (int s = 0; s < 4; ++s)
                 if (touch[s]) {
                     const int k = (int)A::add_u((uint32_t *)&S.ibuf[4], 1u);
-                    P.segs[4 * k + 0] = b; P.segs[4 * k + 1] = s >> 1; P.segs[4 * k + 2] = lines[s]; P.segs[4 * k + 3] = 0;
+                    const int len = (s >> 1) ? e.rmax - e.rmin + 1 : e.cmax - e.cmin + 1;
+                    P.segs[4 * k + 0] = b; P.segs[4 * k + 1] = s >> 1; P.segs[4 * k + 2] = lines[s]; P.segs[4 * k + 3] = len;
+                    A::max_i(&S.ibuf[6], len);
                 }
         }
-        A::sync();
-        const int nseg = S.ibuf[4];
-        for (int q = 0; q < nseg; ++q) {
-            const int b = P.segs[4 * q + 0], is_col = P.segs[4 * q + 1], line = P.segs[4 * q + 2];
-            const IvmEnv &e = P.env[b];
-            if (!is_col) {
-                for (int32_t c = e.cmin + tid; c <= e.cmax; c += nthreads) ivm_scan_edge_cell<A>(P, b, line, c, loc);
+    }
+    A::sync();
+    if (tid == 0) {
+        g->glob[0] = grmin; g->glob[1] = grmax; g->glob[2] = gcmin; g->glob[3] = gcmax;
+        g->n_seg = alive ? (uint32_t)S.ibuf[4] : 0u;
+        g->scan_chunks = alive ? (uint32_t)((S.ibuf[6] + IVM_SCAN_CHUNK - 1) / IVM_SCAN_CHUNK) : 0u;
+    }
+    IVM_TRACE(g, 2, tid);
+}
+
+// Block `blk` of `nblk` visits the (segment, chunk) units blk, blk + nblk, ...: one cell per thread
+// and unit, so that on the device the whole scan is a single round of independent loads.
+template <class A>
+IVM_HD void ivm_fixup_scan(const IvmParams &P, int blk, int nblk, int tid, int nthreads) {
+    const IvmGlobal *g = P.g;
+    const int nseg = (int)g->n_seg, nchunks = (int)g->scan_chunks;
+    if (nseg <= 0 || nchunks <= 0) return;
+    const int32_t grmin = g->glob[0], grmax = g->glob[1];
+    const int32_t loc[4] = {g->loc[0], g->loc[1], g->loc[2], g->loc[3]};
+    const long long units = (long long)nseg * nchunks;
+    for (long long u = blk; u < units; u += nblk) {
+        const int q = (int)(u % nseg), j = (int)(u / nseg);
+        const int b = P.segs[4 * q + 0], is_col = P.segs[4 * q + 1], line = P.segs[4 * q + 2], len = P.segs[4 * q + 3];
+        const IvmEnv &e = P.env[b];
+        const int32_t lo = is_col ? e.rmin : e.cmin;
+        for (int t = tid; t < IVM_SCAN_CHUNK; t += nthreads) {
+            const int off = j * IVM_SCAN_CHUNK + t;
+            if (off >= len) break;
+            const int32_t v = lo + off;
+            size_t idx;
+            if (!ivm_store_index(P, e.origin_r, e.origin_c, b, is_col ? v : line, is_col ? line : v, idx)) continue;
+            if (!ivm_live(ivm_load_meta(&P.store[idx]), e.reset_stamp)) continue;
+            if (is_col) {
+                if (v != grmin && v != grmax) ivm_scan_edge_cell<A>(P, b, v, line, loc);  // corners belong to the row scans
             } else {
-                for (int32_t r = e.rmin + tid; r <= e.rmax; r += nthreads)
-                    if (r != grmin && r != grmax) ivm_scan_edge_cell<A>(P, b, r, line, loc);  // corners belong to the row scans
+                ivm_scan_edge_cell<A>(P, b, line, v, loc);
             }
         }
-        A::sync();
+    }
+}
+
+template <class A>
+IVM_HD void ivm_fixup_stage2(const IvmParams &P, const IvmFixScratch &S, int tid, int nthreads) {
+    IvmGlobal *g = P.g;
+    const int32_t grmin = g->glob[0], grmax = g->glob[1], gcmin = g->glob[2], gcmax = g->glob[3];
+    const bool alive = grmin <= grmax;
+    const uint32_t n1 = g->n_e1 < P.ecap ? g->n_e1 : P.ecap;
+    uint32_t n2 = 0;
+    if (tid == 0) { S.ibuf[5] = 0; S.lbuf[0] = 0ull; }
+    A::sync();
+    IVM_TRACE(g, 4, tid);
+    if (alive) {
         // ---- stage 2: collisions on the world bbox edge (mapper.py:844-847)
         n2 = g->n_e2 < P.ecap ? g->n_e2 : P.ecap;
         if (n2 > 1) {
@@ -582,29 +729,9 @@ IVM_HD void ivm_fixup_program(const IvmParams &P, const IvmFixScratch &S, int ti
             }
             A::sync();
             // ---- rebuild the bbox of envs that lost records
-            if (S.ibuf[5]) {
-                for (int b = tid; b < P.B; b += nthreads) {
-                    IvmEnv *e = &P.env[b];
-                    if (e->dirty) { e->rmin = INT32_MAX; e->rmax = INT32_MIN; e->cmin = INT32_MAX; e->cmax = INT32_MIN; }
-                }
-                A::sync();
-                const long long per_env = (long long)P.SR + P.SC;
-                for (long long i = tid; i < per_env * P.B; i += nthreads) {
-                    const int b = (int)(i / per_env);
-                    IvmEnv *e = &P.env[b];
-                    if (!e->dirty) continue;
-                    const int j = (int)(i - (long long)b * per_env);
-                    if (j < P.SR) {
-                        if (P.rowcount[(size_t)b * P.SR + j] > 0) { A::min_i(&e->rmin, e->origin_r + j); A::max_i(&e->rmax, e->origin_r + j); }
-                    } else {
-                        const int jc = j - P.SR;
-                        if (P.colcount[(size_t)b * P.SC + jc] > 0) { A::min_i(&e->cmin, e->origin_c + jc); A::max_i(&e->cmax, e->origin_c + jc); }
-                    }
-                }
-                A::sync();
-                for (int b = tid; b < P.B; b += nthreads) P.env[b].dirty = 0;
-            }
+            if (S.ibuf[5]) ivm_rebuild_dirty_boxes<A>(P, tid, nthreads);
         }
+        IVM_TRACE(g, 5, tid);
         for (int b = tid; b < P.B; b += nthreads) {
             const int32_t c = P.env[b].count;
             if (c > 0) A::add_ull(&S.lbuf[0], (unsigned long long)c);
@@ -624,8 +751,21 @@ IVM_HD void ivm_fixup_program(const IvmParams &P, const IvmFixScratch &S, int ti
         g->stats[IVM_STAT_WORLD] = S.lbuf[0];
         g->stats[IVM_STAT_E1] = n1;
         g->stats[IVM_STAT_E2] = n2;
+        g->stats[7] = ((unsigned long long)g->n_seg << 32) | ((unsigned long long)g->scan_chunks * IVM_SCAN_CHUNK);
         ivm_reset_step_globals(g);
     }
+    IVM_TRACE(g, 6, tid);
+}
+
+// the whole fix-up in one thread block (multi-kernel step, emulator)
+template <class A>
+IVM_HD void ivm_fixup_program(const IvmParams &P, const IvmFixScratch &S, int tid, int nthreads) {
+    ivm_fixup_stage1<A>(P, S, tid, nthreads);
+    A::sync();
+    IVM_TRACE(P.g, 3, tid);
+    ivm_fixup_scan<A>(P, 0, 1, tid, nthreads);
+    A::sync();
+    ivm_fixup_stage2<A>(P, S, tid, nthreads);
 }
 
 // ---------------------------------------------------------------------------
@@ -691,14 +831,15 @@ IVM_HD void ivm_row_span(const IvmTileGeom &G, int32_t rr, int32_t &clo, int32_t
 // (mapper.py:101-114).  Returns true and (row, col) if the record is inside the map.
 IVM_HD bool ivm_ego_cell(const IvmParams &P, float x, float y, float z, float px, float h, float pz, float c, float s,
                          int32_t &row, int32_t &col) {
-    if (!(y > ivm_sub(h, 1.25f) && y < ivm_add(h, 0.75f))) return false;
+    // straight-line on purpose (no early exit): independent records interleave in the raster loop
+    const bool band = y > ivm_sub(h, 1.25f) && y < ivm_add(h, 0.75f);
     const float x1 = ivm_add(x, -px);
     const float z1 = ivm_add(z, -pz);
     const float xe = ivm_add(ivm_mul(c, x1), ivm_mul(s, z1));
     const float ze = ivm_add(ivm_mul(-s, x1), ivm_mul(c, z1));
     const float rf = rintf(ivm_div(ivm_add(ze, P.half_h), P.res));
     const float cf = rintf(ivm_div(ivm_add(xe, P.half_w), P.res));
-    if (!(rf >= 0.0f && rf < (float)P.R && cf >= 0.0f && cf < (float)P.C)) return false;
-    row = (int32_t)rf; col = (int32_t)cf;
-    return true;
+    const bool in = band && rf >= 0.0f && rf < (float)P.R && cf >= 0.0f && cf < (float)P.C;
+    row = in ? (int32_t)rf : 0; col = in ? (int32_t)cf : 0;
+    return in;
 }

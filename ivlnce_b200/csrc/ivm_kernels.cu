@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(IVM_THREADS) k_ingest_resolve(IvmParams P) {
 
 // ------------------------------------------------------------------ K3: fix-up
 #define IVM_FIX_SMALL 512
-__global__ void __launch_bounds__(1024) k_fixup(IvmParams P) {
+__global__ void __launch_bounds__(1024) k_fixup(const __grid_constant__ IvmParams P) {
     __shared__ unsigned long long s_key[IVM_FIX_SMALL], s_xo[IVM_FIX_SMALL], s_l[2];
     __shared__ uint32_t s_ord[IVM_FIX_SMALL];
     __shared__ int32_t s_i[8];
@@ -492,92 +492,114 @@ __global__ void __launch_bounds__(1024) k_fixup(IvmParams P) {
 }
 
 // ------------------------------------------------------------------ K4: raster
-// One CTA = one ego tile of one env (output-stationary).  The store half-rows under the rotated
-// tile are cut into 32-record chunks; warps take chunks round-robin, two at a time, so that
-// every lane has two independent 16-byte loads in flight.
+// One thread group (a whole CTA in the stand-alone kernel, a 128-thread half of the CTA in the
+// fused step kernel) = one ego tile of one env (output-stationary).  The store half-rows under the
+// rotated tile are cut into 32-record chunks; warps take chunks round-robin, IVM_RASTER_MLP at a
+// time, so that every lane has that many independent 16-byte loads in flight.
+#define IVM_RASTER_MLP 4
+
+// named barrier with a compile-time id (a register id would make ptxas reserve all 16 barriers)
+__device__ __forceinline__ void group_bar(int bar_id, int nthr) {
+    switch (bar_id) {
+        case 0: asm volatile("bar.sync 0, %0;" ::"r"(nthr) : "memory"); break;
+        case 1: asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); break;
+        case 2: asm volatile("bar.sync 2, %0;" ::"r"(nthr) : "memory"); break;
+        default: asm volatile("bar.sync 3, %0;" ::"r"(nthr) : "memory"); break;
+    }
+}
+
 __device__ __forceinline__ void raster_record(const IvmParams &P, const uint4 raw, bool have, uint32_t reset_stamp, float px,
                                               float h, float pz, float c, float s, int r0, int r1, int c0, int c1, int tc,
                                               uint32_t cell, uint32_t *skey, uint8_t *socc, unsigned &n_in) {
-    if (!have || !ivm_live(raw.w, reset_stamp)) return;
     int row, col;
-    if (!ivm_ego_cell(P, __uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), px, h, pz, c, s, row, col))
-        return;
-    if (row < r0 || row >= r1 || col < c0 || col >= c1) return;
-    ++n_in;
-    const int t = (row - r0) * tc + (col - c0);
-    socc[t] = 1;  // OccupancyStatus.OCCUPIED
-    const uint32_t label = raw.w & 0xFFu;
-    // last point in list order wins (mapper.py:569-571); list order within an env is (half-row,
-    // half-col) lexicographic; labels 0 are excluded (mapper.py:611)
-    if (label) atomicMax(&skey[t], (cell << 8) | label);
+    bool ok = ivm_ego_cell(P, __uint_as_float(raw.x), __uint_as_float(raw.y), __uint_as_float(raw.z), px, h, pz, c, s, row, col);
+    ok = ok && have && ivm_live(raw.w, reset_stamp) && row >= r0 && row < r1 && col >= c0 && col < c1;
+    if (ok) {
+        ++n_in;
+        const int t = (row - r0) * tc + (col - c0);
+        socc[t] = 1;  // OccupancyStatus.OCCUPIED
+        const uint32_t label = raw.w & 0xFFu;
+        // last point in list order wins (mapper.py:569-571); list order within an env is (half-row,
+        // half-col) lexicographic; labels 0 are excluded (mapper.py:611)
+        if (label) atomicMax(&skey[t], (cell << 8) | label);
+    }
+}
+
+// bytes of shared memory one raster group needs
+static inline size_t raster_smem_bytes(int tile_r, int tile_c, int max_rows) {
+    return (((size_t)tile_r * tile_c * 5 + (size_t)max_rows * 8 + 16) + 15) & ~(size_t)15;
 }
 
 template <bool KNOWN>
-__global__ void __launch_bounds__(IVM_RASTER_THREADS) k_raster(IvmParams P, int max_rows) {
-    extern __shared__ uint32_t skey[];
+__device__ __forceinline__ void raster_tile(const IvmParams &P, int max_rows, int b, int r0, int c0, uint32_t *smem, int tid,
+                                            int nthr, int bar_id, unsigned &n_in) {
     const int tr = P.tile_r, tc = P.tile_c;
+    uint32_t *skey = smem;
     int32_t *s_clo = reinterpret_cast<int32_t *>(skey + tr * tc);   // first store column of each half-row's span
     int32_t *s_len = s_clo + max_rows;                              // span length (0 = nothing to read)
-    uint8_t *socc = reinterpret_cast<uint8_t *>(s_len + max_rows);
-    __shared__ int s_maxlen;
-    const int b = blockIdx.z;
-    const int r0 = blockIdx.y * tr, c0 = blockIdx.x * tc;
+    int32_t *s_maxlen = s_len + max_rows;
+    uint8_t *socc = reinterpret_cast<uint8_t *>(s_maxlen + 4);
     const int r1 = min(r0 + tr, P.R), c1 = min(c0 + tc, P.C);
-    for (int i = threadIdx.x; i < tr * tc; i += blockDim.x) { skey[i] = 0u; socc[i] = 0; }
-    if (threadIdx.x == 0) s_maxlen = 0;
+    group_bar(bar_id, nthr);  // the group's previous tile has been written out
+    for (int i = tid; i < tr * tc; i += nthr) { skey[i] = 0u; socc[i] = 0; }
+    if (tid == 0) *s_maxlen = 0;
     const IvmEnv e = P.env[b];
     const float px = P.pose[3 * b + 0], h = P.pose[3 * b + 1], pz = P.pose[3 * b + 2];
     const float c = P.cs[2 * b + 0], s = P.cs[2 * b + 1];
-    unsigned n_in = 0;
     IvmTileGeom G;
     ivm_tile_geom(P, px, pz, c, s, r0, r1, c0, c1, G);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+    (void)lane;
     int row_lo = max(G.row_lo, KNOWN ? e.origin_r : e.rmin);
     int row_hi = min(G.row_hi, KNOWN ? e.origin_r + P.SR - 1 : e.rmax);
     if (e.count <= 0) row_hi = row_lo - 1;
     if (row_hi - row_lo + 1 > max_rows) row_hi = row_lo + max_rows - 1;  // cannot happen: max_rows bounds the tile diagonal
     const int nrows = row_hi - row_lo + 1;
     const int col_lo = KNOWN ? e.origin_c : e.cmin, col_hi = KNOWN ? e.origin_c + P.SC - 1 : e.cmax;
-    __syncthreads();
+    group_bar(bar_id, nthr);
     // phase 1: one thread per half-row solves the column span under the rotated tile
-    for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+    for (int i = tid; i < nrows; i += nthr) {
         int clo, chi;
         ivm_row_span(G, row_lo + i, clo, chi);
         clo = max(clo, col_lo); chi = min(chi, col_hi);
         const int len = chi >= clo ? chi - clo + 1 : 0;
         s_clo[i] = clo; s_len[i] = len;
-        if (len > 0) atomicMax(&s_maxlen, len);
+        if (len > 0) atomicMax(s_maxlen, len);
     }
-    __syncthreads();
+    group_bar(bar_id, nthr);
     if (!KNOWN) {
-        // phase 2: spans are cut into 32-record chunks; warps take chunks round-robin, two at a time
-        const int CH = (s_maxlen + 31) >> 5;
-        const int nslots = nrows * CH;
+        // phase 2: one half-warp per store half-row (a span under a 16x16 tile holds ~40 records);
+        // its 16 lanes read up to IVM_RASTER_MLP x 16 consecutive records (independent 16-byte
+        // loads, 256 contiguous bytes per half-warp and load) before any of them is processed
         const IvmRecord *env_store = P.store + (size_t)b * P.SR * P.SC;
-        for (int sl = warp; sl < nslots; sl += 2 * nwarps) {
-            uint4 raw[2];
-            bool have[2];
-            uint32_t cell[2];
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const int slot = sl + u * nwarps;
-                have[u] = false;
-                raw[u] = make_uint4(0, 0, 0, 0);
-                cell[u] = 0;
-                if (slot < nslots) {
-                    const int i = slot / CH, k = slot - i * CH;
-                    const int off = 32 * k + lane;
-                    if (off < s_len[i]) {
-                        const uint32_t rrel = (uint32_t)(row_lo + i - e.origin_r), crel = (uint32_t)(s_clo[i] + off - e.origin_c);
-                        cell[u] = rrel * (uint32_t)P.SC + crel;
-                        raw[u] = __ldg(reinterpret_cast<const uint4 *>(env_store + cell[u]));
-                        have[u] = true;
-                    }
-                }
+        const int hw = tid >> 4, nhw = nthr >> 4, l16 = tid & 15;
+        // pull the whole footprint of the tile towards L2 first (one prefetch per 128-byte line)
+        for (int j = tid; j < nrows * 8; j += nthr) {
+            const int i = j >> 3, seg = j & 7;  // a span of <= 64 records covers <= 9 lines; longer spans are only partly prefetched
+            if (seg * 8 < s_len[i]) {
+                const size_t first = (size_t)(row_lo + i - e.origin_r) * P.SC + (size_t)(s_clo[i] - e.origin_c);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(env_store + first + seg * 8));
             }
+        }
+        for (int i = hw; i < nrows; i += nhw) {
+            const int len = s_len[i];
+            const uint32_t rowbase = (uint32_t)(row_lo + i - e.origin_r) * (uint32_t)P.SC + (uint32_t)(s_clo[i] - e.origin_c);
+            for (int k0 = 0; k0 < len; k0 += 16 * IVM_RASTER_MLP) {
+                uint4 raw[IVM_RASTER_MLP];
+                bool have[IVM_RASTER_MLP];
 #pragma unroll
-            for (int u = 0; u < 2; ++u)
-                raster_record(P, raw[u], have[u], e.reset_stamp, px, h, pz, c, s, r0, r1, c0, c1, tc, cell[u], skey, socc, n_in);
+                for (int u = 0; u < IVM_RASTER_MLP; ++u) {
+                    const int off = k0 + 16 * u + l16;
+                    have[u] = off < len;
+                    raw[u] = make_uint4(0, 0, 0, 0);
+                    // L2-only load: in the fused kernel the records were written earlier in the same launch
+                    if (have[u]) raw[u] = __ldcg(reinterpret_cast<const uint4 *>(env_store + rowbase + off));
+                }
+#pragma unroll
+                for (int u = 0; u < IVM_RASTER_MLP; ++u)
+                    raster_record(P, raw[u], have[u], e.reset_stamp, px, h, pz, c, s, r0, r1, c0, c1, tc,
+                                  rowbase + (uint32_t)(k0 + 16 * u + l16), skey, socc, n_in);
+            }
         }
     } else {
         for (int i = warp; i < nrows; i += nwarps) {
@@ -601,14 +623,22 @@ __global__ void __launch_bounds__(IVM_RASTER_THREADS) k_raster(IvmParams P, int 
             }
         }
     }
-    __syncthreads();
+    group_bar(bar_id, nthr);
     const int wr = r1 - r0, wc = c1 - c0;
-    for (int i = threadIdx.x; i < wr * wc; i += blockDim.x) {
+    for (int i = tid; i < wr * wc; i += nthr) {
         const int rr = i / wc, cc = i - rr * wc;
         const size_t o = ((size_t)b * P.R + (size_t)(r0 + rr)) * P.C + (size_t)(c0 + cc);
         P.occ[o] = socc[rr * tc + cc];
         P.sem[o] = (uint8_t)(skey[rr * tc + cc] & 0xFFu);
     }
+}
+
+template <bool KNOWN>
+__global__ void __launch_bounds__(IVM_RASTER_THREADS) k_raster(IvmParams P, int max_rows) {
+    extern __shared__ __align__(16) uint32_t raster_smem[];
+    unsigned n_in = 0;
+    raster_tile<KNOWN>(P, max_rows, blockIdx.z, blockIdx.y * P.tile_r, blockIdx.x * P.tile_c, raster_smem, threadIdx.x,
+                       blockDim.x, 0, n_in);
     const unsigned wn = warp_sum(n_in);
     if (wn && (threadIdx.x & 31) == 0) atomicAdd(&P.g->stats[IVM_STAT_IN], (unsigned long long)wn);
 }
@@ -616,6 +646,439 @@ __global__ void __launch_bounds__(IVM_RASTER_THREADS) k_raster(IvmParams P, int 
 __global__ void k_pose(IvmParams P) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b < P.B) ivm_pose_matrices(P, b, P.T12_buf + 12 * b, P.cs_buf + 2 * b);
+}
+
+// ------------------------------------------------------------------ fused persistent step kernel
+// The whole map update as ONE cooperative launch of co-resident CTAs (2 per SM), phases separated
+// by grid barriers instead of kernel boundaries:
+//   A  ingest-scatter  warp-specialised: warp 8 is the producer (one lane issues cp.async.bulk =
+//                      TMA 1-D copies of the class-score planes into a 6 x 16 KB shared-memory
+//                      ring, full/empty mbarriers), warps 0-7 consume (running argmax from shared
+//                      memory, labels out, unproject, atomicMax into the candidate plane).  No
+//                      block-wide barrier inside the stream.
+//   B  resolve         every CTA revisits its own tiles (depth/labels are L2-resident by now)
+//   C  edge fix-up     CTA 0 only (the others wait at the next barrier)
+//   D  raster          two 128-thread groups per CTA, one ego tile each at a time
+// CTA t owns a contiguous range of 512-pixel tiles in A and B.
+#define IVM_F_THREADS 288      // 8 consumer warps + 1 producer warp
+#define IVM_F_CONSUMERS 256
+#define IVM_F_TILE 512         // pixels per tile (= 256 consumer threads x 2)
+#define IVM_F_SP 8             // planes per ring stage (16 KB)
+#define IVM_F_NSTAGE 6         // ring depth (96 KB per CTA, 192 KB per SM)
+#define IVM_F_CTAS_PER_SM 2
+#define IVM_F_GROUP 128        // raster group
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Grid barrier over the co-resident CTAs of a cooperative launch.  `target` = arrivals expected
+// on the monotone counter.  Returns false on time-out (never observed; guards against a hang).
+__device__ __forceinline__ bool grid_barrier(uint32_t *bar, uint32_t target, int *s_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();  // release: this CTA's writes (made visible to thread 0 by the bar.sync) before the arrival
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+        int ok = 1;
+        uint32_t spins = 0;
+        for (;;) {
+            // RELAXED polling: an acquire load would invalidate this SM's L1 (CCTL.IVALL) on every
+            // iteration and stall the memory pipeline of the CTA that shares the SM and is still working
+            uint32_t v;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if ((int32_t)(v - target) >= 0) break;
+            if (++spins > (1u << 22)) { ok = 0; break; }
+            __nanosleep(spins < 8 ? 64 : 256);
+        }
+        __threadfence();  // acquire, once: later loads of this CTA see the other CTAs' writes
+        *s_flag = ok;
+    }
+    __syncthreads();
+    return *s_flag != 0;
+}
+
+#define IVM_F_BR 8             // tiles per resolve round (= consumer warps)
+struct FusedSlot {             // one tile of a resolve round
+    float T[12];
+    int32_t b, tp0, origin_r, origin_c;
+    uint32_t reset_stamp;
+    float h, hlo, hhi;
+    int32_t box[5];            // bbox + count of the cells this CTA newly occupied in the slot's env
+};
+struct FusedShared {
+    K1Shared k1;
+    FusedSlot slot[IVM_F_BR];
+    unsigned qn;
+    uint64_t full[IVM_F_NSTAGE];
+    uint64_t empty[IVM_F_NSTAGE];
+    int flag;
+};
+
+template <bool PRED>
+__global__ void __launch_bounds__(IVM_F_THREADS, IVM_F_CTAS_PER_SM)
+k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out, int nenv_total,
+             uint32_t bar_base, int max_rows, int raster_group_bytes) {
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ __align__(8) FusedShared sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tpe = P.HW / IVM_F_TILE;                     // tiles per env
+    const long long total = (long long)P.B * tpe;
+    const int t0 = (int)((long long)blockIdx.x * total / gridDim.x);
+    const int t1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
+    IvmGlobal *g = P.g;
+    if (blockIdx.x == 0 && tid == 0) { g->tstamp[0] = global_timer(); g->tstamp[5] = 0ull; }
+
+    // ================================================================ phase A: ingest-scatter
+    if (PRED && tid == 0) {
+        for (int s = 0; s < IVM_F_NSTAGE; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], IVM_F_CONSUMERS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // paused envs (mapper.py:315-318) are wiped by the last CTA
+    if (blockIdx.x == gridDim.x - 1)
+        for (int b = P.B; b < nenv_total; ++b) {
+            IvmEnvPrep q; q.reset = 1; q.origin_r = 0; q.origin_c = 0;
+            ivm_env_publish<IvmAtomics>(P, b, q, tid, blockDim.x);
+        }
+    __syncthreads();
+    if (warp == IVM_F_CONSUMERS / 32) {
+        // ---- producer warp: one lane keeps the ring full
+        if (PRED && lane == 0) {
+            float(*ring)[IVM_F_SP][IVM_F_TILE] = reinterpret_cast<float(*)[IVM_F_SP][IVM_F_TILE]>(dyn);
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            int slot = 0;
+            uint32_t round = 0;  // how many times the ring has wrapped
+            for (int tile = t0; tile < t1; ++tile) {
+                const int eb = tile / tpe, tp0 = (tile - eb * tpe) * IVM_F_TILE;
+                const float *src = logits + (size_t)eb * ncls * P.HW + tp0;
+                for (int p0 = 0; p0 < ncls; p0 += IVM_F_SP) {
+                    const int np = min(IVM_F_SP, ncls - p0);
+                    if (round > 0) mbar_wait(&sh.empty[slot], (round - 1) & 1u);
+                    mbar_expect_tx(&sh.full[slot], (uint32_t)(np * IVM_F_TILE * sizeof(float)));
+                    for (int p = 0; p < np; ++p)
+                        bulk_g2s(&ring[slot][p][0], src + (size_t)(p0 + p) * P.HW, IVM_F_TILE * sizeof(float), &sh.full[slot],
+                                 policy);
+                    if (++slot == IVM_F_NSTAGE) { slot = 0; ++round; }
+                }
+            }
+        }
+    } else {
+        // ---- consumer warps
+        float(*ring)[IVM_F_SP][IVM_F_TILE] = reinterpret_cast<float(*)[IVM_F_SP][IVM_F_TILE]>(dyn);
+        int rmin = INT32_MAX, rmax = INT32_MIN, cmin = INT32_MAX, cmax = INT32_MIN;
+        unsigned nvalid = 0;
+        int cur_env = -1;
+        int slot = 0;
+        uint32_t round = 0;
+        if (tid == 0) { sh.k1.bb[0] = INT32_MAX; sh.k1.bb[1] = INT32_MIN; sh.k1.bb[2] = INT32_MAX; sh.k1.bb[3] = INT32_MIN; sh.k1.valid = 0; }
+        for (int tile = t0; tile < t1; ++tile) {
+            const int b = tile / tpe, tp0 = (tile - b * tpe) * IVM_F_TILE;
+            const int pix0 = tp0 + tid * 2;
+            const size_t base = (size_t)b * P.HW + pix0;
+            const float2 dv = __ldcg(reinterpret_cast<const float2 *>(P.depth + base));  // stays in L2 for phase B
+            if (b != cur_env) {  // uniform over the consumers: a CTA's tile range is contiguous
+                group_bar(1, IVM_F_CONSUMERS);  // the previous env's matrices are no longer read
+                if (tid == 0) {
+                    const IvmEnvPrep q = ivm_env_decide(P, b);
+                    sh.k1.origin_r = q.origin_r; sh.k1.origin_c = q.origin_c; sh.k1.reset = q.reset;
+                }
+                if (P.orient != nullptr) {
+                    if (tid == 32) ivm_pose_matrices(P, b, sh.k1.T, sh.k1.cs);
+                } else if (tid >= 32 && tid < 44) {
+                    sh.k1.T[tid - 32] = P.T12[12 * b + tid - 32];
+                }
+                group_bar(1, IVM_F_CONSUMERS);
+                cur_env = b;
+            }
+            if (tp0 == 0) {  // the CTA that owns an env's first tile publishes the env's new state
+                IvmEnvPrep q;
+                q.reset = sh.k1.reset; q.origin_r = sh.k1.origin_r; q.origin_c = sh.k1.origin_c;
+                ivm_env_publish<IvmAtomics>(P, b, q, tid, IVM_F_CONSUMERS);
+                if (P.orient != nullptr) {
+                    if (tid < 12) P.T12_buf[12 * b + tid] = sh.k1.T[tid];
+                    if (tid < 2) P.cs_buf[2 * b + tid] = sh.k1.cs[tid];
+                }
+            }
+            if (PRED) {
+                // PredictSemantics tail (mapper.py:795-798): running argmax over the planes, first max
+                // wins, NaN counts as maximal (torch.argmax)
+                float best0 = 0.f, best1 = 0.f;
+                int a0 = 0, a1 = 0;
+                for (int p0 = 0; p0 < ncls; p0 += IVM_F_SP) {
+                    mbar_wait(&sh.full[slot], round & 1u);
+                    const int np = min(IVM_F_SP, ncls - p0);
+                    if (np == IVM_F_SP) {
+                        float2 v[IVM_F_SP];
+#pragma unroll
+                        for (int p = 0; p < IVM_F_SP; ++p) v[p] = *reinterpret_cast<const float2 *>(&ring[slot][p][tid * 2]);
+#pragma unroll
+                        for (int p = 0; p < IVM_F_SP; ++p) {
+                            if (p0 + p == 0) { best0 = v[p].x; best1 = v[p].y; }
+                            else { IVM_ARGMAX_STEP(v[p].x, p0 + p, best0, a0); IVM_ARGMAX_STEP(v[p].y, p0 + p, best1, a1); }
+                        }
+                    } else {
+                        for (int p = 0; p < np; ++p) {
+                            const float2 v = *reinterpret_cast<const float2 *>(&ring[slot][p][tid * 2]);
+                            if (p0 + p == 0) { best0 = v.x; best1 = v.y; }
+                            else { IVM_ARGMAX_STEP(v.x, p0 + p, best0, a0); IVM_ARGMAX_STEP(v.y, p0 + p, best1, a1); }
+                        }
+                    }
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sh.empty[slot]);  // this warp is done with the stage
+                    if (++slot == IVM_F_NSTAGE) { slot = 0; ++round; }
+                }
+                uchar2 o;
+                o.x = (uint8_t)a0; o.y = (uint8_t)a1;
+                *reinterpret_cast<uchar2 *>(labels_out + base) = o;
+            }
+            // unproject + scatter this thread's two pixels (the next tiles' planes are already in flight)
+            const float h = P.pose[3 * b + 1];
+            const int v = pix0 / P.W, u0 = pix0 - v * P.W;
+            const float ysv = P.ys[v];
+            const float dd[2] = {dv.x, dv.y};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                IvmPoint p;
+                const int ok = ivm_unproject(dd[j], P.xs[u0 + j], ysv, sh.k1.T, h, P.half_res, p);
+                if (ok == 0) continue;
+                size_t idx;
+                if (ok == 2 || !ivm_store_index(P, sh.k1.origin_r, sh.k1.origin_c, b, p.r, p.c, idx)) {
+                    atomicOr(&g->err, IVM_ERR_STORE_OVERFLOW);
+                    continue;
+                }
+                atomicMax(&P.cand[idx], ivm_cand_key(p.y, (uint32_t)(pix0 + j)));
+                // the resolve phase will read-modify-write this cell's world record: pull it into L2 now
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.store[idx]));
+                rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
+                ++nvalid;
+            }
+        }
+        // frame bbox over ALL envs (mapper.py:465), one flush per CTA
+        const unsigned wv = warp_sum(nvalid);
+        if (wv) {
+            rmin = warp_min(rmin); rmax = warp_max(rmax); cmin = warp_min(cmin); cmax = warp_max(cmax);
+            if (lane == 0) {
+                atomicMin(&sh.k1.bb[0], rmin); atomicMax(&sh.k1.bb[1], rmax); atomicMin(&sh.k1.bb[2], cmin); atomicMax(&sh.k1.bb[3], cmax);
+                atomicAdd(&sh.k1.valid, wv);
+            }
+        }
+        group_bar(1, IVM_F_CONSUMERS);
+        if (tid == 0 && sh.k1.valid) {
+            atomicMin(&g->loc[0], sh.k1.bb[0]); atomicMax(&g->loc[1], sh.k1.bb[1]);
+            atomicMin(&g->loc[2], sh.k1.bb[2]); atomicMax(&g->loc[3], sh.k1.bb[3]);
+            atomicAdd(&g->acc_valid, (unsigned long long)sh.k1.valid);
+        }
+    }
+    if (!grid_barrier(P.bar, bar_base + 1u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
+    if (blockIdx.x == 0 && tid == 0) g->tstamp[1] = global_timer();
+
+    // ================================================================ phase B: resolve
+    // Valid pixels cluster in the image rows around the horizon, so tiles are dealt round-robin
+    // (tile = CTA + j * grid) and the CTA works in rounds of IVM_F_BR tiles: (1) all depth/label
+    // loads of the round are issued together and the filter survivors are compacted into ONE queue
+    // per CTA, (2) the queue is drained by all consumer threads, two entries at a time with the
+    // candidate-word loads and then the world-record loads of both entries in flight together.
+    if (warp < IVM_F_CONSUMERS / 32) {
+        uint32_t *q_pix = reinterpret_cast<uint32_t *>(dyn);                         // (slot << 24) | pixel
+        float *q_d = reinterpret_cast<float *>(dyn + IVM_F_BR * IVM_F_TILE * 4);
+        uint8_t *q_lab = dyn + 2 * IVM_F_BR * IVM_F_TILE * 4;
+        const int32_t loc[4] = {__ldcg(&g->loc[0]), __ldcg(&g->loc[1]), __ldcg(&g->loc[2]), __ldcg(&g->loc[3])};
+        const uint8_t *labels = P.labels;
+        unsigned nlocal = 0;
+        for (int j0 = 0; (long long)blockIdx.x + (long long)j0 * gridDim.x < total; j0 += IVM_F_BR) {
+            // ---- per-slot env data (warp k prepares slot k)
+            {
+                const long long tile = (long long)blockIdx.x + (long long)(j0 + warp) * gridDim.x;
+                FusedSlot &sl = sh.slot[warp];
+                if (tile < total) {
+                    const int b = (int)(tile / tpe);
+                    if (lane < 12) sl.T[lane] = __ldcg(&P.T12[12 * b + lane]);
+                    if (lane == 12) {
+                        const IvmEnv *e = &P.env[b];
+                        sl.b = b; sl.tp0 = (int)(tile - (long long)b * tpe) * IVM_F_TILE;
+                        sl.origin_r = __ldcg(&e->origin_r); sl.origin_c = __ldcg(&e->origin_c);
+                        sl.reset_stamp = __ldcg(&e->reset_stamp);
+                        const float h = P.pose[3 * b + 1];
+                        sl.h = h; sl.hlo = ivm_sub(h, 1.0f); sl.hhi = ivm_add(h, 0.5f);
+                        sl.box[0] = INT32_MAX; sl.box[1] = INT32_MIN; sl.box[2] = INT32_MAX; sl.box[3] = INT32_MIN; sl.box[4] = 0;
+                    }
+                } else if (lane == 12) {
+                    sl.b = -1;
+                }
+                if (tid == 0) sh.qn = 0u;
+            }
+            group_bar(1, IVM_F_CONSUMERS);
+            if (blockIdx.x == 0 && tid == 0 && j0 == 0) g->ttrace[8] = global_timer();
+            // ---- filter pass: this warp's 64-pixel segment of every tile of the round
+            float2 dv[IVM_F_BR];
+            uchar2 lv[IVM_F_BR];
+#pragma unroll
+            for (int k = 0; k < IVM_F_BR; ++k) {
+                dv[k] = make_float2(2.0f, 2.0f);
+                lv[k] = make_uchar2(0, 0);
+                if (sh.slot[k].b >= 0) {
+                    const size_t base = (size_t)sh.slot[k].b * P.HW + sh.slot[k].tp0 + warp * 64 + lane * 2;
+                    dv[k] = __ldcg(reinterpret_cast<const float2 *>(P.depth + base));
+                    lv[k] = __ldcg(reinterpret_cast<const uchar2 *>(labels + base));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < IVM_F_BR; ++k) {
+                const FusedSlot &sl = sh.slot[k];
+                if (sl.b < 0) continue;  // uniform
+                const int pix0 = sl.tp0 + warp * 64 + lane * 2;
+                const int v = pix0 / P.W, u0 = pix0 - v * P.W;
+                const float ysv = P.ys[v];
+                const float dd[2] = {dv[k].x, dv[k].y};
+                const uint8_t ll[2] = {lv[k].x, lv[k].y};
+                bool ok[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    ok[j] = dd[j] > 0.01f && dd[j] < 0.99f;
+                    if (ok[j]) {
+                        const float z = ivm_mul(dd[j], 10.0f);
+                        float a = ivm_mul(sl.T[4], ivm_mul(z, P.xs[u0 + j]));
+                        a = ivm_fma(sl.T[5], ivm_mul(z, ysv), a);
+                        a = ivm_fma(sl.T[6], z, a);
+                        a = ivm_fma(sl.T[7], 1.0f, a);
+                        ok[j] = a > sl.hlo && a < sl.hhi;
+                    }
+                }
+                const unsigned m0 = __ballot_sync(0xffffffffu, ok[0]), m1 = __ballot_sync(0xffffffffu, ok[1]);
+                const int n0 = __popc(m0), n01 = n0 + __popc(m1);
+                if (n01 == 0) continue;
+                unsigned basepos = 0;
+                if (lane == 0) basepos = atomicAdd(&sh.qn, (unsigned)n01);
+                basepos = __shfl_sync(0xffffffffu, basepos, 0);
+                const unsigned below = (1u << lane) - 1u;
+                if (ok[0]) {
+                    const unsigned pos = basepos + __popc(m0 & below);
+                    q_pix[pos] = ((uint32_t)k << 24) | (uint32_t)pix0; q_d[pos] = dd[0]; q_lab[pos] = ll[0];
+                }
+                if (ok[1]) {
+                    const unsigned pos = basepos + n0 + __popc(m1 & below);
+                    q_pix[pos] = ((uint32_t)k << 24) | (uint32_t)(pix0 + 1); q_d[pos] = dd[1]; q_lab[pos] = ll[1];
+                }
+            }
+            group_bar(1, IVM_F_CONSUMERS);
+            if (blockIdx.x == 0 && tid == 0 && j0 == 0) g->ttrace[9] = global_timer();
+            // ---- drain: two entries per thread and iteration
+            const int n = (int)sh.qn;
+            for (int i0 = tid; i0 < n; i0 += 2 * IVM_F_CONSUMERS) {
+                IvmPoint pt[2];
+                size_t idx[2];
+                uint32_t pix[2];
+                int kk[2];
+                bool act[2];
+                unsigned long long cw[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int i = i0 + u * IVM_F_CONSUMERS;
+                    act[u] = i < n;
+                    cw[u] = 0ull; idx[u] = 0; pix[u] = 0; kk[u] = 0;
+                    if (act[u]) {
+                        const uint32_t qp = q_pix[i];
+                        kk[u] = (int)(qp >> 24); pix[u] = qp & 0xFFFFFFu;
+                        const FusedSlot &sl = sh.slot[kk[u]];
+                        const int v = (int)pix[u] / P.W, uu = (int)pix[u] - v * P.W;
+                        act[u] = ivm_unproject(q_d[i], P.xs[uu], P.ys[v], sl.T, sl.h, P.half_res, pt[u]) == 1 &&
+                                 ivm_store_index(P, sl.origin_r, sl.origin_c, sl.b, pt[u].r, pt[u].c, idx[u]);
+                        if (act[u]) cw[u] = ivm_load_cand(&P.cand[idx[u]]);
+                    }
+                }
+                IvmRecord old[2];
+                bool merge[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    merge[u] = false;
+                    old[u].x = old[u].y = old[u].z = 0.f; old[u].meta = 0u;
+                    if (act[u] && ivm_cand_is_mine(cw[u], pix[u], pt[u].y)) {
+                        P.cand[idx[u]] = 0ull;  // leave the scratch plane clean for the next step
+                        if (ivm_on_frame_edge(pt[u], loc)) {
+                            ivm_push_edge1<IvmAtomics>(P, sh.slot[kk[u]].b, pix[u], pt[u], q_lab[i0 + u * IVM_F_CONSUMERS], idx[u]);
+                        } else {
+                            merge[u] = true;
+                            old[u] = ivm_load_record(&P.store[idx[u]]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    if (!merge[u]) continue;
+                    FusedSlot &sl = sh.slot[kk[u]];
+                    IvmBoxAcc acc;
+                    acc.clear();
+                    ivm_merge_record<IvmAtomics>(P, sl.b, idx[u], pt[u].r, pt[u].c, pt[u].x, pt[u].y, pt[u].z,
+                                                 q_lab[i0 + u * IVM_F_CONSUMERS], old[u], sl.reset_stamp, sl.origin_r, sl.origin_c, acc);
+                    ++nlocal;
+                    if (acc.n) {  // a newly occupied cell: fold into the slot's box
+                        atomicMin(&sl.box[0], acc.rmin); atomicMax(&sl.box[1], acc.rmax);
+                        atomicMin(&sl.box[2], acc.cmin); atomicMax(&sl.box[3], acc.cmax);
+                        atomicAdd(&sl.box[4], 1);
+                    }
+                }
+            }
+            group_bar(1, IVM_F_CONSUMERS);
+            if (blockIdx.x == 0 && tid == 0 && j0 == 0) g->ttrace[10] = global_timer();
+            if (tid < IVM_F_BR && sh.slot[tid].b >= 0 && sh.slot[tid].box[4] > 0) {
+                IvmBoxAcc t;
+                const FusedSlot &sl = sh.slot[tid];
+                t.rmin = sl.box[0]; t.rmax = sl.box[1]; t.cmin = sl.box[2]; t.cmax = sl.box[3]; t.n = sl.box[4];
+                ivm_box_flush<IvmAtomics>(&P.env[sl.b], t);
+            }
+            group_bar(1, IVM_F_CONSUMERS);
+            if (blockIdx.x == 0 && tid == 0 && j0 == 0) g->ttrace[11] = global_timer();
+        }
+        const unsigned wl = warp_sum(nlocal);
+        if (wl && lane == 0) atomicAdd(&g->acc_local, (unsigned long long)wl);
+    }
+    if (!grid_barrier(P.bar, bar_base + 2u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
+    if (blockIdx.x == 0 && tid == 0) g->tstamp[2] = global_timer();
+
+    // ================================================================ phase C: edge fix-up
+    // C1 (CTA 0): stage-1 collision classes + merges, world bbox, edge-line segments
+    // C2 (all):   the live records on the edge lines, one cell per thread
+    // C3 (CTA 0): stage-2 classes, deletions, bookkeeping
+    IvmFixScratch S;
+    S.key = reinterpret_cast<unsigned long long *>(dyn);
+    S.xo = S.key + IVM_FIX_SMALL;
+    S.ord = reinterpret_cast<uint32_t *>(S.xo + IVM_FIX_SMALL);
+    S.cap = IVM_FIX_SMALL;
+    S.ibuf = reinterpret_cast<int32_t *>(S.ord + IVM_FIX_SMALL);
+    S.lbuf = reinterpret_cast<unsigned long long *>(S.ibuf + 8);
+    if (blockIdx.x == 0) ivm_fixup_stage1<IvmAtomics>(P, S, tid, blockDim.x);
+    if (!grid_barrier(P.bar, bar_base + 3u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
+    if (blockIdx.x == 0 && tid == 0) g->ttrace[3] = global_timer();
+    ivm_fixup_scan<IvmAtomics>(P, blockIdx.x, gridDim.x, tid, blockDim.x);
+    if (!grid_barrier(P.bar, bar_base + 4u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
+    if (blockIdx.x == 0) {
+        ivm_fixup_stage2<IvmAtomics>(P, S, tid, blockDim.x);
+        if (tid == 0) g->tstamp[3] = global_timer();
+    }
+    if (!grid_barrier(P.bar, bar_base + 5u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
+    if (blockIdx.x == 0 && tid == 0) g->tstamp[4] = global_timer();
+
+    // ================================================================ phase D: raster
+    if (warp < IVM_F_CONSUMERS / 32) {
+        const int group = tid / IVM_F_GROUP, gtid = tid - group * IVM_F_GROUP;
+        uint32_t *gsm = reinterpret_cast<uint32_t *>(dyn + (size_t)group * raster_group_bytes);
+        const int tiles_x = (P.C + P.tile_c - 1) / P.tile_c, tiles_y = (P.R + P.tile_r - 1) / P.tile_r;
+        const int per_env = tiles_x * tiles_y, units = P.B * per_env;
+        unsigned n_in = 0;
+        for (int u = blockIdx.x * 2 + group; u < units; u += 2 * gridDim.x) {
+            const int b = u / per_env, w = u - b * per_env;
+            const int ty = w / tiles_x, tx = w - ty * tiles_x;
+            raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in);
+        }
+        const unsigned wn = warp_sum(n_in);
+        if (wn && lane == 0) atomicAdd(&g->stats[IVM_STAT_IN], (unsigned long long)wn);
+    }
+    if (tid == 0) atomicMax(&g->tstamp[5], global_timer());
 }
 
 // ------------------------------------------------------------------ known-map store build
@@ -784,6 +1247,10 @@ struct ivm_ctx {
     int first_call;
     int bulk_attr_set;
     int num_sms;
+    int coop;             // device supports cooperative launches
+    int fused_grid[2];    // co-resident CTAs of k_step_fused<false/true> (0 = not queried yet)
+    size_t fused_smem[2];
+    uint32_t bar_base;    // value of IvmGlobal.bar_count before the next fused launch
     int64_t launches;
     // known-mode scratch
     uint32_t *kfill, *ktotals;
@@ -825,6 +1292,7 @@ static void carve(const ivm_config *c, void *ws, IvmParams *P, ivm_ctx *ctx, siz
     IvmParams q;
     memset(&q, 0, sizeof(q));
     q.g = cv.take<IvmGlobal>(1);
+    q.bar = cv.take<uint32_t>(64);
     q.env = cv.take<IvmEnv>(B);
     float *xs = cv.take<float>(c->width > 0 ? c->width : 1);
     float *ys = cv.take<float>(c->height > 0 ? c->height : 1);
@@ -908,6 +1376,8 @@ int ivm_create(const ivm_config *cfg, void *workspace_dev, size_t workspace_byte
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
             ctx->num_sms = sms;
+        int coop = 0;
+        if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess) ctx->coop = coop;
         cudaGetLastError();
     }
     *out = ctx;
@@ -996,15 +1466,66 @@ static int next_step(ivm_ctx *ctx) {
     return IVM_OK;
 }
 
+static int raster_max_rows(const IvmParams &P);
 static void launch_raster(ivm_ctx *ctx, const IvmParams &P, cudaStream_t st, bool known) {
     dim3 grid((P.C + P.tile_c - 1) / P.tile_c, (P.R + P.tile_r - 1) / P.tile_r, P.B);
-    // half-rows under a rotated tile: its diagonal in half-cells + the conservative margins
-    const float diag = sqrtf((float)(P.tile_r * P.tile_r + P.tile_c * P.tile_c)) * (P.res / P.half_res);
-    const int max_rows = (int)diag + 12;
-    const size_t smem = (size_t)P.tile_r * P.tile_c * 5 + (size_t)max_rows * 8 + 16;
+    const int max_rows = raster_max_rows(P);
+    const size_t smem = raster_smem_bytes(P.tile_r, P.tile_c, max_rows);
     if (known) k_raster<true><<<grid, IVM_RASTER_THREADS, smem, st>>>(P, max_rows);
     else k_raster<false><<<grid, IVM_RASTER_THREADS, smem, st>>>(P, max_rows);
     ctx->launches += 1;
+}
+
+static int raster_max_rows(const IvmParams &P) {
+    // half-rows under a rotated tile: its diagonal in half-cells + the conservative margins
+    const float diag = sqrtf((float)(P.tile_r * P.tile_r + P.tile_c * P.tile_c)) * (P.res / P.half_res);
+    return (int)diag + 12;
+}
+
+// The fused persistent kernel applies when the image tiles evenly and the inputs are aligned.
+static bool fused_applies(const ivm_ctx *ctx, const IvmParams &P, const float *depth, const uint8_t *labels, const float *logits) {
+    if (!ctx->coop || ctx->cfg.reserved[0] != 0) return false;
+    if (P.HW % IVM_F_TILE != 0 || (P.W & 1) || P.HW > (1 << 24)) return false;
+    if (((uintptr_t)depth & 7) || ((uintptr_t)labels & 1) || (logits && ((uintptr_t)logits & 15))) return false;
+    const size_t rb = 2 * raster_smem_bytes(P.tile_r, P.tile_c, raster_max_rows(P));
+    return rb <= 96 * 1024;
+}
+
+static int launch_fused(ivm_ctx *ctx, IvmParams &P, const float *logits, int ncls, uint8_t *labels_out, int nenv_total,
+                        cudaStream_t st) {
+    const int pred = logits ? 1 : 0;
+    int max_rows = raster_max_rows(P);
+    int group_bytes = (int)raster_smem_bytes(P.tile_r, P.tile_c, max_rows);
+    size_t smem = (size_t)2 * group_bytes;
+    const size_t scratch = (size_t)IVM_F_BR * IVM_F_TILE * 9 + 1024;  // resolve queue (36 KB) > fix-up scratch (10.3 KB)
+    if (smem < scratch) smem = scratch;
+    if (pred) {
+        const size_t ring = (size_t)IVM_F_NSTAGE * IVM_F_SP * IVM_F_TILE * sizeof(float);
+        if (smem < ring) smem = ring;
+    }
+    const void *fn = pred ? (const void *)k_step_fused<true> : (const void *)k_step_fused<false>;
+    if (!ctx->fused_grid[pred] || ctx->fused_smem[pred] != smem) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(k_step_fused)");
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, IVM_F_THREADS, smem);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "occupancy(k_step_fused)");
+        if (per_sm < 1) { snprintf(ctx->err, sizeof(ctx->err), "k_step_fused does not fit on an SM"); return IVM_E_CUDA; }
+        if (per_sm > IVM_F_CTAS_PER_SM) per_sm = IVM_F_CTAS_PER_SM;
+        ctx->fused_grid[pred] = per_sm * ctx->num_sms;
+        ctx->fused_smem[pred] = smem;
+    }
+    long long tiles = (long long)P.B * (P.HW / IVM_F_TILE);
+    int grid = ctx->fused_grid[pred];
+    if (grid > tiles) grid = (int)tiles;
+    uint32_t bar_base = ctx->bar_base;
+    void *args[] = {(void *)&P, (void *)&logits, (void *)&ncls, (void *)&labels_out, (void *)&nenv_total,
+                    (void *)&bar_base, (void *)&max_rows, (void *)&group_bytes};
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(IVM_F_THREADS), args, smem, st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaLaunchCooperativeKernel(k_step_fused)");
+    ctx->bar_base += 5u * (uint32_t)grid;
+    ctx->launches += 1;
+    return IVM_OK;
 }
 
 int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const uint8_t *labels, const float *logits,
@@ -1036,11 +1557,18 @@ int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const
     const int nenv = num_envs > ctx->hi_water ? num_envs : ctx->hi_water;  // envs >= num_envs get wiped
     ctx->hi_water = num_envs;
 
+    if (fused_applies(ctx, P, depth, P.labels, logits)) {
+        T_BEGIN(1);
+        rc = launch_fused(ctx, P, logits, num_classes, labels_out, nenv, st);
+        T_END(1);
+        return rc;
+    }
+
     const bool vec4 = (P.W % 4 == 0) && (((uintptr_t)depth & 15) == 0) && (((uintptr_t)P.labels & 3) == 0) &&
                       (!logits || ((uintptr_t)logits & 15) == 0);
     const int vec = vec4 ? 4 : 1;
     dim3 grid((P.HW + IVM_THREADS * vec - 1) / (IVM_THREADS * vec), nenv);
-    const bool bulk = logits && vec4 && (P.HW % IVM_BULK_TILE == 0) && ctx->cfg.reserved[0] != 1;
+    const bool bulk = logits && vec4 && (P.HW % IVM_BULK_TILE == 0) && ctx->cfg.reserved[0] != 1;  // 1 = register-staged, 2 = bulk
     T_BEGIN(1);
     if (bulk) {
         const size_t smem = (size_t)IVM_BULK_NSTAGE * IVM_BULK_SP * IVM_BULK_TILE * sizeof(float);
@@ -1171,6 +1699,19 @@ int ivm_read_status(ivm_ctx *ctx, ivm_status *host_out, ivm_stream_t stream) {
     host_out->error_flags = g.err;
     host_out->pad = 0;
     for (int i = 0; i < 8; ++i) host_out->stats[i] = g.stats[i];
+    return IVM_OK;
+}
+
+int ivm_read_phase_ns(ivm_ctx *ctx, uint64_t *ns_out24, ivm_stream_t stream) {
+    if (!ctx || !ns_out24) return IVM_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    IvmGlobal g;
+    cudaError_t e = cudaMemcpyAsync(&g, ctx->P.g, sizeof(g), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "read_phase_ns memcpy");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "read_phase_ns sync");
+    for (int i = 0; i < 8; ++i) ns_out24[i] = g.tstamp[i];
+    for (int i = 0; i < 16; ++i) ns_out24[8 + i] = g.ttrace[i];
     return IVM_OK;
 }
 

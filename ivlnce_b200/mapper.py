@@ -265,7 +265,7 @@ class _MapEngine:
         self.store_cells = int(store_cells)
         self.known_capacity = int(known_capacity)
         self.tile = int(tile)
-        self.scatter_variant = int(scatter_variant)  # 0 = auto (bulk-async ingest when it applies), 1 = register-staged
+        self.scatter_variant = int(scatter_variant)  # 0 = auto (fused persistent step kernel when it applies), 1 / 2 = four kernels (register-staged / bulk-async score loads)
         self.ctx = None
         self.workspace = None
         self.max_envs = 0
@@ -570,6 +570,23 @@ class MappingModule(nn.Module):
             raise _lib.MapLibraryError("edge list capacity exceeded")
         if flags & _lib.ERR_KNOWN_OVERFLOW:
             raise _lib.MapLibraryError("known-map cloud outside the store window / over capacity")
+        if flags & _lib.ERR_GRID_BARRIER:
+            raise _lib.MapLibraryError("grid barrier time-out in the fused step kernel (results invalid)")
+
+    def phase_ns(self) -> List[int]:
+        """%globaltimer stamps (ns) of the last fused step: start, ingest done, resolve done, fix-up done,
+        raster released, end.  Synchronises the stream."""
+        out = (ctypes.c_uint64 * 24)()
+        eng = self._engine
+        _lib.check(eng.lib.ivm_read_phase_ns(eng.ctx, out, eng.stream()), eng.ctx, "ivm_read_phase_ns")
+        return [int(v) for v in out][:8]
+
+    def fixup_trace_ns(self) -> List[int]:
+        """%globaltimer stamps (ns) of the milestones inside the last edge fix-up (see ivln_map.h)."""
+        out = (ctypes.c_uint64 * 24)()
+        eng = self._engine
+        _lib.check(eng.lib.ivm_read_phase_ns(eng.ctx, out, eng.stream()), eng.ctx, "ivm_read_phase_ns")
+        return [int(v) for v in out][8:]
 
     def kernel_launches(self) -> int:
         return 0 if self._engine is None else int(self._engine.lib.ivm_kernel_launches(self._engine.ctx))

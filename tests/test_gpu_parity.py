@@ -65,9 +65,33 @@ def test_raster_tile_sizes(tile):
         assert np.array_equal(o, scn["ref_occupancy"][t]) and np.array_equal(s, scn["ref_semantic"][t])
 
 
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("name", [n for n in golden_names() if n != "known_map"])
+def test_cuda_four_kernel_path_matches_reference_golden(name):
+    """The multi-kernel step (taken when the image does not tile evenly, or on request) against the goldens."""
+    scn = load_golden(name)
+    cs, outs, sizes = _run_cuda(scn, scatter_variant=2)
+    for t, (o, s) in enumerate(outs):
+        B = o.shape[0]
+        assert np.array_equal(o, scn["ref_occupancy"][t, :B]), f"occupancy differs at step {t}"
+        assert np.array_equal(s, scn["ref_semantic"][t, :B]), f"semantic differs at step {t}"
+    cs.mm.check_errors()
+    assert sizes == scn["ref_world_sizes"].tolist()
+    assert all(v == 0 for v in cs.mm.phase_ns())  # the fused kernel never ran
+
+
+def test_fused_kernel_is_the_default_path():
+    """64x64 frames tile evenly: the step must run as the single fused persistent kernel."""
+    scn = load_golden("iid_f64")
+    cs, outs, _ = _run_cuda(scn)
+    ns = cs.mm.phase_ns()
+    assert ns[0] > 0 and ns[0] <= ns[1] <= ns[2] <= ns[3] <= ns[4] <= ns[5], ns
+    T = scn["masks"].shape[0]
+    assert cs.mm.kernel_launches() <= T + 1 + 5 * T  # one step kernel per call (+ init, + the world exports of the test)
+
+
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_predicted_ingest_variants(variant):
-    """Both ingest kernels of the predicted-semantics path (bulk-async ring / register-staged loads)."""
+    """Fused persistent kernel / four kernels with register-staged loads / four kernels with the bulk-async ring."""
     scn = load_golden("predicted")
     cs, outs, _ = _run_cuda(scn, scatter_variant=variant)
     for t, (o, s) in enumerate(outs):
@@ -89,7 +113,7 @@ def test_predicted_full_size_against_oracle():
     scn["labels_for_map"] = np.stack([argmax_labels(lg[t]) for t in range(c.steps)])
     orc = OracleMapper(c.height, c.width, c.vfov_radians, c.map_meters, c.map_meters, c.resolution)
     ref_outs, _ = run_mapper(orc.step, scn)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         cs, outs, _ = _run_cuda(scn, scatter_variant=variant)
         for t in range(c.steps):
             assert np.array_equal(outs[t][0], ref_outs[t][0]) and np.array_equal(outs[t][1], ref_outs[t][1]), (variant, t)
