@@ -58,7 +58,7 @@ typedef struct ivm_config {
 
 typedef struct ivm_status {
     uint32_t error_flags; /* 1 = point outside world store, 2 = edge list overflow, 4 = known cloud overflow,
-                           * 8 = grid barrier time-out in the fused kernel */
+                           * 8 = grid barrier time-out in the fused kernel, 16 = frame candidate table full */
     uint32_t pad;
     uint64_t stats[8];    /* valid pixels, frame survivors, world records, rasterised records, e1, e2, merged, - */
 } ivm_status;
@@ -129,6 +129,12 @@ int ivm_stage_times(ivm_ctx *ctx, float *ms_out5, int32_t *launches_out5, int32_
  * classes, end; rest unused).  [0..7] are all zero if the last step took the multi-kernel
  * path.  `ns_out24` has room for 24 values.  Synchronises `stream`. */
 int ivm_read_phase_ns(ivm_ctx *ctx, uint64_t *ns_out24, ivm_stream_t stream);
+
+/* Fused step kernel only: per-CTA timeline of the LAST step, 16 %globaltimer values (ns) per CTA
+ * for the first `num_ctas` CTAs (<= 1024): [0] resolve start, [1] slots ready, [2] filter done,
+ * [3] drain done, [4] boxes flushed, [5] past the grid barrier, [6] ingest done, [7] kernel start,
+ * [8] raster start, [9] end; rest unused.  Synchronises `stream`. */
+int ivm_read_cta_trace(ivm_ctx *ctx, uint64_t *ns_out, int32_t num_ctas, ivm_stream_t stream);
 
 /* Number of kernels launched by this context so far. */
 int64_t ivm_kernel_launches(const ivm_ctx *ctx);

@@ -20,6 +20,7 @@ ERR_STORE_OVERFLOW = 1
 ERR_EDGE_OVERFLOW = 2
 ERR_KNOWN_OVERFLOW = 4
 ERR_GRID_BARRIER = 8
+ERR_CAND_OVERFLOW = 16
 
 
 class IvmConfig(ctypes.Structure):
@@ -76,13 +77,14 @@ def load() -> ctypes.CDLL:
     L.ivm_kernel_launches.argtypes = [_vp]
     L.ivm_rebase_stamps.argtypes = [_vp, _vp]
     L.ivm_read_phase_ns.argtypes = [_vp, ctypes.POINTER(ctypes.c_uint64), _vp]
+    L.ivm_read_cta_trace.argtypes = [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32, _vp]
     L.ivm_copy_state.argtypes = [_vp, _vp, _vp]
     L.ivm_last_cuda_error.restype = ctypes.c_char_p
     L.ivm_last_cuda_error.argtypes = [_vp]
     L.ivm_version.restype = ctypes.c_char_p
     for name in ("ivm_create", "ivm_destroy", "ivm_set_camera", "ivm_step_iterative", "ivm_known_load", "ivm_known_clear",
                  "ivm_step_known", "ivm_export_world", "ivm_read_status", "ivm_set_timing", "ivm_stage_times",
-                 "ivm_rebase_stamps", "ivm_copy_state", "ivm_read_phase_ns"):
+                 "ivm_rebase_stamps", "ivm_copy_state", "ivm_read_phase_ns", "ivm_read_cta_trace"):
         getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L

@@ -84,6 +84,19 @@ struct IvmRecord {
     uint32_t meta;
 };
 
+// One slot of an env's frame candidate table: open addressing, keyed by the half-cell.
+//   tag = stamp << 24 | cell index in the env's store window   (cell < 2^24)
+//   val = stamp << 56 | orderable(height) << 24 | (0xFFFFFF - pixel index)
+// stamp = 1..255 cycles with the step counter, so entries of earlier steps read as free slots and
+// lose every atomicMax: the table is never cleared between steps (the host clears it once per
+// 255 steps, when the stamp wraps).  2 slots per pixel, 16 B each: 2 MB per env at 256x256 --
+// small enough to live in the 126 MB L2, so the frame de-dup never touches HBM.
+struct IvmCand {
+    unsigned long long val;
+    uint32_t tag;
+    uint32_t pad;
+};
+
 struct IvmEnv {                   // 64 bytes
     int32_t origin_r, origin_c;   // absolute half-cell index of store cell (0,0)
     uint32_t reset_stamp;         // records older than this are dead (O(1) reset)
@@ -117,6 +130,7 @@ struct IvmEdge {
 #define IVM_ERR_EDGE_OVERFLOW 2u   // edge list / hash capacity exceeded
 #define IVM_ERR_KNOWN_OVERFLOW 4u  // known-map cloud larger than capacity / index range
 #define IVM_ERR_GRID_BARRIER 8u    // a grid barrier of the fused step kernel timed out (results invalid)
+#define IVM_ERR_CAND_OVERFLOW 16u  // frame candidate table full (cannot happen: it holds 2 slots per pixel)
 
 struct IvmGlobal {
     int32_t loc[4];               // frame (stage-1) bbox over all envs: rmin,rmax,cmin,cmax
@@ -148,13 +162,16 @@ struct IvmParams {
     int32_t tile_r, tile_c;       // ego tile of one raster CTA
     // persistent device memory
     IvmRecord *store;             // [maxB][SR][SC]
-    unsigned long long *cand;     // [maxB][SR][SC] frame de-dup scratch, all zero between steps
+    IvmCand *ctab;                // [maxB][chash] frame candidate table (see IvmCand)
+    uint32_t chash;               // slots per env, a power of two >= 2 * HW
+    uint32_t cstamp;              // per step: 1..255
     IvmEnv *env;                  // [maxB]
     int32_t *rowcount, *colcount; // [maxB][SR], [maxB][SC] live records per store row / col
     IvmGlobal *g;
     uint32_t *bar;                // grid-barrier arrival counter of the fused step kernel, alone in its own 256-byte
                                   // block (CTAs spin on it; nothing else may share its L2 slice line), monotone
                                   // across launches (the host tracks the base)
+    unsigned long long *cta_trace; // [IVM_TRACE_CTAS][IVM_TRACE_SLOTS] %globaltimer stamps per CTA of the fused kernel
     IvmEdge *e1, *e2;             // edge lists, capacity ecap each
     uint32_t ecap;
     int32_t *segs;                // [4*maxB][4] edge-line segments to scan: b, is_col, line, pad
@@ -179,10 +196,14 @@ struct IvmParams {
     const uint8_t *masks;         // [B] 0 = reset this env before ingesting
     const void *orient;           // [B][2] (elevation, heading), f64 or f32; NULL if T12/cs are given
     int32_t orient_f64;
+    int32_t debug;                // profiling experiments only (config.reserved[1]); results are invalid when non-zero:
+                                  // 1 = ingest phase without candidate inserts, 2 = without world-record prefetch
     uint8_t *occ, *sem;           // [B][R][C]
 };
 
 #define IVM_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
+#define IVM_TRACE_CTAS 1024
+#define IVM_TRACE_SLOTS 16
 
 // Record / candidate loads.  In the fused step kernel these locations are written by other SMs
 // earlier in the SAME launch, so the device versions read through L2 (ld.global.cg) and never
@@ -194,12 +215,14 @@ IVM_HD IvmRecord ivm_load_record(const IvmRecord *p) {
     r.x = __uint_as_float(v.x); r.y = __uint_as_float(v.y); r.z = __uint_as_float(v.z); r.meta = v.w;
     return r;
 }
-IVM_HD unsigned long long ivm_load_cand(const unsigned long long *p) { return __ldcg(p); }
+IVM_HD unsigned long long ivm_load_ull(const unsigned long long *p) { return __ldcg(p); }
+IVM_HD uint32_t ivm_load_u32(const uint32_t *p) { return __ldcg(p); }
 IVM_HD uint32_t ivm_load_meta(const IvmRecord *p) { return __ldcg(&p->meta); }
 #else
 IVM_HD uint32_t ivm_load_meta(const IvmRecord *p) { return p->meta; }
 IVM_HD IvmRecord ivm_load_record(const IvmRecord *p) { return *p; }
-IVM_HD unsigned long long ivm_load_cand(const unsigned long long *p) { return *p; }
+IVM_HD unsigned long long ivm_load_ull(const unsigned long long *p) { return *p; }
+IVM_HD uint32_t ivm_load_u32(const uint32_t *p) { return *p; }
 #endif
 
 IVM_HD bool ivm_live(uint32_t meta, uint32_t reset_stamp) {
@@ -221,6 +244,7 @@ struct IvmAtomics {
     static __device__ __forceinline__ void min_ull(unsigned long long *p, unsigned long long v) { atomicMin(p, v); }
     static __device__ __forceinline__ unsigned long long cas_ull(unsigned long long *p, unsigned long long c,
                                                                   unsigned long long v) { return atomicCAS(p, c, v); }
+    static __device__ __forceinline__ uint32_t cas_u(uint32_t *p, uint32_t c, uint32_t v) { return atomicCAS(p, c, v); }
     static __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 #else
@@ -237,6 +261,7 @@ struct IvmAtomics {
     static unsigned long long cas_ull(unsigned long long *p, unsigned long long c, unsigned long long v) {
         unsigned long long o = *p; if (o == c) *p = v; return o;
     }
+    static uint32_t cas_u(uint32_t *p, uint32_t c, uint32_t v) { uint32_t o = *p; if (o == c) *p = v; return o; }
     static void sync() {}
 };
 #endif
@@ -278,9 +303,11 @@ IVM_HD int ivm_unproject(float d, float xs_u, float ys_v, const float *T, float 
 
 // frame de-dup candidate: highest point wins, lowest pixel index on ties
 // (first-index rule of scatter_max; pixels are listed in (v,u) order, mapper.py:32-35).
-IVM_HD unsigned long long ivm_cand_key(float y, uint32_t pix) {
-    return ((unsigned long long)ivm_orderable(y) << 32) | (unsigned long long)(0xFFFFFFFFu - pix);
+IVM_HD unsigned long long ivm_cand_key(const IvmParams &P, float y, uint32_t pix) {
+    return ((unsigned long long)P.cstamp << 56) | ((unsigned long long)ivm_orderable(y) << 24) |
+           (unsigned long long)(0xFFFFFFu - pix);
 }
+IVM_HD uint32_t ivm_cand_hash(uint32_t cell) { return (cell * 0x9E3779B1u) >> 7; }  // neighbours land far apart
 
 IVM_HD bool ivm_store_index(const IvmParams &P, int32_t origin_r, int32_t origin_c, int b, int32_t r, int32_t c,
                             size_t &idx) {
@@ -425,14 +452,43 @@ IVM_HD void ivm_reset_step_globals(IvmGlobal *g) {
 
 // ---------------------------------------------------------------------------
 // K1b per-pixel resolve.  `p` is the pixel's point (already unprojected and
-// valid).  The pixel that owns the candidate slot of its cell is the frame
+// valid).  The pixel whose key sits in the candidate slot of its cell is the frame
 // de-dup winner of that cell.  Winners on the frame bbox edge go to the edge
 // list (they may collide with other cells); all others are
 // merged into the world store directly.  Returns 1 if the pixel was a
 // non-edge winner (for the LOCAL statistic).
-// does the candidate word of a cell name this pixel (and its height) as the frame winner?
-IVM_HD bool ivm_cand_is_mine(unsigned long long cand, uint32_t pix, float y) {
-    return (uint32_t)(cand & 0xFFFFFFFFull) == 0xFFFFFFFFu - pix && (uint32_t)(cand >> 32) == ivm_orderable(y);
+// Offer a point to its cell's slot of env b's candidate table (claiming a free or stale slot on
+// the way).  `cell` = index of the half-cell inside the env's store window.
+template <class A>
+IVM_HD void ivm_cand_insert(const IvmParams &P, int b, uint32_t cell, unsigned long long key) {
+    IvmCand *tab = P.ctab + (size_t)b * P.chash;
+    const uint32_t mask = P.chash - 1u, mine = (P.cstamp << 24) | cell;
+    uint32_t s = ivm_cand_hash(cell) & mask;
+    for (uint32_t probes = 0; probes <= mask; ++probes) {
+        uint32_t t = ivm_load_u32(&tab[s].tag);
+        for (;;) {
+            if (t == mine) { A::max_ull(&tab[s].val, key); return; }
+            if ((t >> 24) == P.cstamp) break;            // taken by another cell in this step: next slot
+            const uint32_t old = A::cas_u(&tab[s].tag, t, mine);  // free or stale: claim it
+            if (old == t) { A::max_ull(&tab[s].val, key); return; }
+            t = old;                                     // somebody else changed it first: look again
+        }
+        s = (s + 1u) & mask;
+    }
+    A::or_u(&P.g->err, IVM_ERR_CAND_OVERFLOW);
+}
+// The winning key of a cell after all inserts of the step (0 if the cell has no slot).
+IVM_HD unsigned long long ivm_cand_lookup(const IvmParams &P, int b, uint32_t cell) {
+    const IvmCand *tab = P.ctab + (size_t)b * P.chash;
+    const uint32_t mask = P.chash - 1u, mine = (P.cstamp << 24) | cell;
+    uint32_t s = ivm_cand_hash(cell) & mask;
+    for (uint32_t probes = 0; probes <= mask; ++probes) {
+        const uint32_t t = ivm_load_u32(&tab[s].tag);
+        if (t == mine) return ivm_load_ull(&tab[s].val);
+        if ((t >> 24) != P.cstamp) return 0ull;
+        s = (s + 1u) & mask;
+    }
+    return 0ull;
 }
 IVM_HD bool ivm_on_frame_edge(const IvmPoint &p, const int32_t *loc) {
     return p.r == loc[0] || p.r == loc[1] || p.c == loc[2] || p.c == loc[3];
@@ -454,8 +510,8 @@ IVM_HD int ivm_resolve_pixel(const IvmParams &P, int b, uint32_t pix, const IvmP
                              const int32_t *loc, int32_t origin_r, int32_t origin_c, IvmBoxAcc &acc) {
     size_t idx;
     if (!ivm_store_index(P, origin_r, origin_c, b, p.r, p.c, idx)) return 0;  // overflow was flagged by the scatter
-    if (!ivm_cand_is_mine(ivm_load_cand(&P.cand[idx]), pix, p.y)) return 0;
-    P.cand[idx] = 0ull;  // leave the scratch plane clean for the next step
+    const uint32_t cell = (uint32_t)(idx - (size_t)b * P.SR * P.SC);
+    if (ivm_cand_lookup(P, b, cell) != ivm_cand_key(P, p.y, pix)) return 0;
     if (ivm_on_frame_edge(p, loc)) {
         ivm_push_edge1<A>(P, b, pix, p, label, idx);
         return 0;

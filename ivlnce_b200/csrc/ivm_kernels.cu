@@ -92,7 +92,7 @@ __device__ __forceinline__ void k1_scatter_pixels(const IvmParams &P, int b, int
                 atomicOr(&P.g->err, IVM_ERR_STORE_OVERFLOW);
                 continue;
             }
-            atomicMax(&P.cand[idx], ivm_cand_key(p.y, (uint32_t)(pix0 + j)));
+            ivm_cand_insert<IvmAtomics>(P, b, (uint32_t)(idx - (size_t)b * P.SR * P.SC), ivm_cand_key(P, p.y, (uint32_t)(pix0 + j)));
             rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
             ++nvalid;
         }
@@ -355,7 +355,7 @@ k_ingest_scatter_bulk(IvmParams P, const float *__restrict__ logits, int ncls, u
                 atomicOr(&P.g->err, IVM_ERR_STORE_OVERFLOW);
                 continue;
             }
-            atomicMax(&P.cand[idx], ivm_cand_key(p.y, (uint32_t)(pix0 + j)));
+            ivm_cand_insert<IvmAtomics>(P, b, (uint32_t)(idx - (size_t)b * P.SR * P.SC), ivm_cand_key(P, p.y, (uint32_t)(pix0 + j)));
             rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
             ++nvalid;
         }
@@ -719,6 +719,16 @@ struct FusedShared {
     int flag;
 };
 
+// per-CTA timeline (profiling): slot k of this CTA <- %globaltimer, taken by thread 0.  `dep` is a
+// value the stamp must wait for (a barrier does not block the timer read by itself).
+#define CTA_STAMP(k, dep)                                                                              \
+    do {                                                                                               \
+        if (tid == 0 && blockIdx.x < IVM_TRACE_CTAS) {                                                 \
+            asm volatile("" ::"r"(dep) : "memory");                                                    \
+            P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + (k)] = global_timer();                  \
+        }                                                                                              \
+    } while (0)
+
 template <bool PRED>
 __global__ void __launch_bounds__(IVM_F_THREADS, IVM_F_CTAS_PER_SM)
 k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out, int nenv_total,
@@ -732,6 +742,7 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
     const int t1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
     IvmGlobal *g = P.g;
     if (blockIdx.x == 0 && tid == 0) { g->tstamp[0] = global_timer(); g->tstamp[5] = 0ull; }
+    CTA_STAMP(7, 0);
 
     // ================================================================ phase A: ingest-scatter
     if (PRED && tid == 0) {
@@ -851,9 +862,10 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
                     atomicOr(&g->err, IVM_ERR_STORE_OVERFLOW);
                     continue;
                 }
-                atomicMax(&P.cand[idx], ivm_cand_key(p.y, (uint32_t)(pix0 + j)));
+                if (!(P.debug & 1))
+                    ivm_cand_insert<IvmAtomics>(P, b, (uint32_t)(idx - (size_t)b * P.SR * P.SC), ivm_cand_key(P, p.y, (uint32_t)(pix0 + j)));
                 // the resolve phase will read-modify-write this cell's world record: pull it into L2 now
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.store[idx]));
+                if (!(P.debug & 2)) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.store[idx]));
                 rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
                 ++nvalid;
             }
@@ -874,8 +886,10 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
             atomicAdd(&g->acc_valid, (unsigned long long)sh.k1.valid);
         }
     }
+    CTA_STAMP(6, 0);
     if (!grid_barrier(P.bar, bar_base + 1u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
     if (blockIdx.x == 0 && tid == 0) g->tstamp[1] = global_timer();
+    CTA_STAMP(0, sh.flag);
 
     // ================================================================ phase B: resolve
     // Valid pixels cluster in the image rows around the horizon, so tiles are dealt round-robin
@@ -913,7 +927,7 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
                 if (tid == 0) sh.qn = 0u;
             }
             group_bar(1, IVM_F_CONSUMERS);
-            if (blockIdx.x == 0 && tid == 0 && j0 == 0) g->ttrace[8] = global_timer();
+            if (j0 == 0) CTA_STAMP(1, *(volatile unsigned *)&sh.qn);
             // ---- filter pass: this warp's 64-pixel segment of every tile of the round
             float2 dv[IVM_F_BR];
             uchar2 lv[IVM_F_BR];
@@ -966,7 +980,7 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
                 }
             }
             group_bar(1, IVM_F_CONSUMERS);
-            if (blockIdx.x == 0 && tid == 0 && j0 == 0) g->ttrace[9] = global_timer();
+            if (j0 == 0) CTA_STAMP(2, *(volatile unsigned *)&sh.qn);
             // ---- drain: two entries per thread and iteration
             const int n = (int)sh.qn;
             for (int i0 = tid; i0 < n; i0 += 2 * IVM_F_CONSUMERS) {
@@ -988,7 +1002,7 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
                         const int v = (int)pix[u] / P.W, uu = (int)pix[u] - v * P.W;
                         act[u] = ivm_unproject(q_d[i], P.xs[uu], P.ys[v], sl.T, sl.h, P.half_res, pt[u]) == 1 &&
                                  ivm_store_index(P, sl.origin_r, sl.origin_c, sl.b, pt[u].r, pt[u].c, idx[u]);
-                        if (act[u]) cw[u] = ivm_load_cand(&P.cand[idx[u]]);
+                        if (act[u]) cw[u] = ivm_cand_lookup(P, sl.b, (uint32_t)(idx[u] - (size_t)sl.b * P.SR * P.SC));
                     }
                 }
                 IvmRecord old[2];
@@ -997,8 +1011,7 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
                 for (int u = 0; u < 2; ++u) {
                     merge[u] = false;
                     old[u].x = old[u].y = old[u].z = 0.f; old[u].meta = 0u;
-                    if (act[u] && ivm_cand_is_mine(cw[u], pix[u], pt[u].y)) {
-                        P.cand[idx[u]] = 0ull;  // leave the scratch plane clean for the next step
+                    if (act[u] && cw[u] == ivm_cand_key(P, pt[u].y, pix[u])) {
                         if (ivm_on_frame_edge(pt[u], loc)) {
                             ivm_push_edge1<IvmAtomics>(P, sh.slot[kk[u]].b, pix[u], pt[u], q_lab[i0 + u * IVM_F_CONSUMERS], idx[u]);
                         } else {
@@ -1024,7 +1037,7 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
                 }
             }
             group_bar(1, IVM_F_CONSUMERS);
-            if (blockIdx.x == 0 && tid == 0 && j0 == 0) g->ttrace[10] = global_timer();
+            if (j0 == 0) CTA_STAMP(3, *(volatile int *)&sh.slot[7].box[4]);
             if (tid < IVM_F_BR && sh.slot[tid].b >= 0 && sh.slot[tid].box[4] > 0) {
                 IvmBoxAcc t;
                 const FusedSlot &sl = sh.slot[tid];
@@ -1032,13 +1045,14 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
                 ivm_box_flush<IvmAtomics>(&P.env[sl.b], t);
             }
             group_bar(1, IVM_F_CONSUMERS);
-            if (blockIdx.x == 0 && tid == 0 && j0 == 0) g->ttrace[11] = global_timer();
+            if (j0 == 0) CTA_STAMP(4, *(volatile unsigned *)&sh.qn);
         }
         const unsigned wl = warp_sum(nlocal);
         if (wl && lane == 0) atomicAdd(&g->acc_local, (unsigned long long)wl);
     }
     if (!grid_barrier(P.bar, bar_base + 2u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
     if (blockIdx.x == 0 && tid == 0) g->tstamp[2] = global_timer();
+    CTA_STAMP(5, sh.flag);
 
     // ================================================================ phase C: edge fix-up
     // C1 (CTA 0): stage-1 collision classes + merges, world bbox, edge-line segments
@@ -1062,6 +1076,7 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
     }
     if (!grid_barrier(P.bar, bar_base + 5u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
     if (blockIdx.x == 0 && tid == 0) g->tstamp[4] = global_timer();
+    CTA_STAMP(8, sh.flag);
 
     // ================================================================ phase D: raster
     if (warp < IVM_F_CONSUMERS / 32) {
@@ -1078,6 +1093,8 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
         const unsigned wn = warp_sum(n_in);
         if (wn && lane == 0) atomicAdd(&g->stats[IVM_STAT_IN], (unsigned long long)wn);
     }
+    __syncthreads();
+    CTA_STAMP(9, 0);
     if (tid == 0) atomicMax(&g->tstamp[5], global_timer());
 }
 
@@ -1283,6 +1300,11 @@ static uint32_t edge_capacity(const ivm_config *c) {
     if (cap > (1ll << 20)) cap = 1ll << 20;
     return (uint32_t)cap;
 }
+static uint32_t cand_slots(const ivm_config *c) {  // 2 slots per pixel, power of two
+    uint32_t h = 1024;
+    while ((long long)h < 2ll * c->height * c->width) h <<= 1;
+    return h;
+}
 static uint32_t hash_size(uint32_t ecap) { uint32_t h = 1024; while (h < 2 * ecap) h <<= 1; return h; }
 
 static void carve(const ivm_config *c, void *ws, IvmParams *P, ivm_ctx *ctx, size_t *total) {
@@ -1293,6 +1315,7 @@ static void carve(const ivm_config *c, void *ws, IvmParams *P, ivm_ctx *ctx, siz
     memset(&q, 0, sizeof(q));
     q.g = cv.take<IvmGlobal>(1);
     q.bar = cv.take<uint32_t>(64);
+    q.cta_trace = cv.take<unsigned long long>((size_t)IVM_TRACE_CTAS * IVM_TRACE_SLOTS);
     q.env = cv.take<IvmEnv>(B);
     float *xs = cv.take<float>(c->width > 0 ? c->width : 1);
     float *ys = cv.take<float>(c->height > 0 ? c->height : 1);
@@ -1314,7 +1337,8 @@ static void carve(const ivm_config *c, void *ws, IvmParams *P, ivm_ctx *ctx, siz
     uint32_t *kfill = nullptr, *ktotals = nullptr;
     if (c->mode == 0) {
         q.store = cv.take<IvmRecord>(B * SR * SC);
-        q.cand = cv.take<unsigned long long>(B * SR * SC);
+        q.chash = cand_slots(c);
+        q.ctab = cv.take<IvmCand>(B * (size_t)q.chash);
     } else {
         q.kcap = c->known_capacity;
         q.kpts = cv.take<IvmRecord>(B * (size_t)c->known_capacity);
@@ -1333,7 +1357,7 @@ static int valid_config(const ivm_config *c) {
     if (c->store_rows < 8 || c->store_cols < 8) return 0;
     if ((long long)c->store_rows * c->store_cols > (1ll << 24)) return 0;  // raster key = cell index << 8 | label
     if (!(c->res > 0.f) || !(c->half_res > 0.f)) return 0;
-    if (c->mode == 0 && (c->height < 1 || c->width < 1)) return 0;
+    if (c->mode == 0 && (c->height < 1 || c->width < 1 || (long long)c->height * c->width > (1ll << 24))) return 0;
     if (c->mode == 1 && (c->known_capacity < 1 || c->known_capacity >= (1ll << 24))) return 0;
     if (c->mode != 0 && c->mode != 1) return 0;
     return 1;
@@ -1370,6 +1394,7 @@ int ivm_create(const ivm_config *cfg, void *workspace_dev, size_t workspace_byte
     if (tr > P.R) tr = P.R;
     if (tc > P.C) tc = P.C;
     P.tile_r = tr; P.tile_c = tc;
+    P.debug = cfg->reserved[1];
     ctx->first_call = 1;
     ctx->num_sms = 148;
     {
@@ -1542,6 +1567,11 @@ int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const
     cudaStream_t st = (cudaStream_t)stream;
     IvmParams P = ctx->P;
     P.B = num_envs; P.step = ctx->step;
+    P.cstamp = (ctx->step - 1u) % 255u + 1u;
+    if (P.cstamp == 1u && ctx->step > 1u) {  // the 8-bit stamp wrapped: forget the last 255 steps' candidates
+        cudaError_t e = cudaMemsetAsync(P.ctab, 0, sizeof(IvmCand) * (size_t)ctx->cfg.max_envs * P.chash, (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "candidate table clear");
+    }
     P.depth = depth; P.labels = labels ? labels : labels_out; P.pose = pose; P.masks = masks;
     P.occ = occ; P.sem = sem;
     if (orientation) { P.orient = orientation; P.orient_f64 = orientation_is_f64; P.T12 = P.T12_buf; P.cs = P.cs_buf; }
@@ -1712,6 +1742,17 @@ int ivm_read_phase_ns(ivm_ctx *ctx, uint64_t *ns_out24, ivm_stream_t stream) {
     if (e != cudaSuccess) return cuda_fail(ctx, e, "read_phase_ns sync");
     for (int i = 0; i < 8; ++i) ns_out24[i] = g.tstamp[i];
     for (int i = 0; i < 16; ++i) ns_out24[8 + i] = g.ttrace[i];
+    return IVM_OK;
+}
+
+int ivm_read_cta_trace(ivm_ctx *ctx, uint64_t *ns_out, int32_t num_ctas, ivm_stream_t stream) {
+    if (!ctx || !ns_out || num_ctas < 1 || num_ctas > IVM_TRACE_CTAS) return IVM_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyAsync(ns_out, ctx->P.cta_trace, sizeof(uint64_t) * IVM_TRACE_SLOTS * (size_t)num_ctas,
+                                    cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "read_cta_trace memcpy");
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "read_cta_trace sync");
     return IVM_OK;
 }
 

@@ -275,7 +275,7 @@ class _MapEngine:
     def _config(self, max_envs: int) -> _lib.IvmConfig:
         md = self.md
         H, W = (self.camera.features_spatial_dimensions if self.camera is not None else (0, 0))
-        reserved = (ctypes.c_int32 * 4)(self.scatter_variant, 0, 0, 0)
+        reserved = (ctypes.c_int32 * 4)(self.scatter_variant, int(os.environ.get("IVM_DEBUG_FLAGS", "0")), 0, 0)
         return _lib.IvmConfig(
             reserved=reserved, max_envs=max_envs, height=int(H), width=int(W), map_rows=md.num_rows, map_cols=md.num_cols,
             res=np.float32(md.resolution_meters), half_res=np.float32(md.resolution_meters / 2),
@@ -570,6 +570,8 @@ class MappingModule(nn.Module):
             raise _lib.MapLibraryError("edge list capacity exceeded")
         if flags & _lib.ERR_KNOWN_OVERFLOW:
             raise _lib.MapLibraryError("known-map cloud outside the store window / over capacity")
+        if flags & _lib.ERR_CAND_OVERFLOW:
+            raise _lib.MapLibraryError("frame candidate table full")
         if flags & _lib.ERR_GRID_BARRIER:
             raise _lib.MapLibraryError("grid barrier time-out in the fused step kernel (results invalid)")
 
@@ -580,6 +582,13 @@ class MappingModule(nn.Module):
         eng = self._engine
         _lib.check(eng.lib.ivm_read_phase_ns(eng.ctx, out, eng.stream()), eng.ctx, "ivm_read_phase_ns")
         return [int(v) for v in out][:8]
+
+    def cta_trace_ns(self, num_ctas: int = 296):
+        """Per-CTA %globaltimer stamps of the last fused step as an int64 array [num_ctas, 16] (see ivln_map.h)."""
+        out = (ctypes.c_uint64 * (16 * num_ctas))()
+        eng = self._engine
+        _lib.check(eng.lib.ivm_read_cta_trace(eng.ctx, out, num_ctas, eng.stream()), eng.ctx, "ivm_read_cta_trace")
+        return np.frombuffer(out, dtype=np.uint64).astype(np.int64).reshape(num_ctas, 16)
 
     def fixup_trace_ns(self) -> List[int]:
         """%globaltimer stamps (ns) of the milestones inside the last edge fix-up (see ivln_map.h)."""

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "../../ivlnce_b200/csrc/ivm_core.h"
@@ -22,7 +23,7 @@ struct Emu {
     int order;  // 0 forward, 1 reverse, 2 strided
     int fix_cap;  // capacity of the fix-up's small-class fast path (0 forces the hash path)
     std::vector<IvmRecord> store;
-    std::vector<unsigned long long> cand;
+    std::vector<IvmCand> cand;
     std::vector<IvmEnv> env;
     std::vector<int32_t> rowcount, colcount, segs;
     IvmGlobal g;
@@ -64,14 +65,18 @@ Emu *emu_create(int H, int W, const float *xs, const float *ys, float res, float
     if (mode == 0) {
         IvmRecord z; z.x = z.y = z.z = 0.f; z.meta = 0;
         m->store.assign(cells, z);
-        m->cand.assign(cells, 0ull);
+        uint32_t ch = 1024;
+        while ((long long)ch < 2ll * H * W) ch <<= 1;
+        IvmCand zc; zc.val = 0ull; zc.tag = 0u; zc.pad = 0u;
+        m->cand.assign((size_t)maxB * ch, zc);
+        P.chash = ch;
     } else {
         IvmRecord z; z.x = z.y = z.z = 0.f; z.meta = 0;
         m->kpts.assign((size_t)maxB * kcap, z);
         m->koff.assign((size_t)maxB * ((size_t)SR * SC + 1), 0u);
         P.kcap = kcap;
     }
-    P.store = m->store.data(); P.cand = m->cand.data(); P.env = m->env.data();
+    P.store = m->store.data(); P.ctab = m->cand.data(); P.env = m->env.data();
     P.rowcount = m->rowcount.data(); P.colcount = m->colcount.data(); P.g = &m->g;
     P.e1 = m->e1.data(); P.e2 = m->e2.data(); P.ecap = ecap; P.segs = m->segs.data();
     P.hkeys = m->hkeys.data(); P.hbest = m->hbest.data(); P.hxord = m->hxord.data(); P.hmask = hs - 1;
@@ -84,6 +89,7 @@ Emu *emu_create(int H, int W, const float *xs, const float *ys, float res, float
 
 void emu_destroy(Emu *m) { delete m; }
 void emu_set_order(Emu *m, int order) { m->order = order; }
+void emu_set_step(Emu *m, unsigned step) { m->step = step; }  // before the first step only (tests the stamp wrap)
 void emu_set_fix_cap(Emu *m, int cap) { m->fix_cap = cap < 1 ? 1 : cap; }
 
 static inline int visit(const Emu *m, int i, int n) {
@@ -170,7 +176,10 @@ int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels,
     if (m->step >= 0xFFFFFFu) return 4;
     m->step += 1;
     IvmParams P = m->P;
-    P.B = B; P.step = m->step; P.depth = depth; P.labels = labels; P.T12 = T12; P.pose = pose; P.cs = cs; P.masks = masks;
+    P.B = B; P.step = m->step;
+    P.cstamp = (m->step - 1u) % 255u + 1u;
+    if (P.cstamp == 1u && m->step > 1u) { IvmCand zc; zc.val = 0ull; zc.tag = 0u; zc.pad = 0u; std::fill(m->cand.begin(), m->cand.end(), zc); }
+    P.depth = depth; P.labels = labels; P.T12 = T12; P.pose = pose; P.cs = cs; P.masks = masks;
     P.occ = occ; P.sem = sem;
     if (orient) {  // the K0 path that derives the matrices from the angles
         P.orient = orient; P.orient_f64 = orient_f64; P.T12 = P.T12_buf; P.cs = P.cs_buf;
@@ -197,7 +206,7 @@ int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels,
         if (ok == 0) continue;
         size_t idx;
         if (ok == 2 || !ivm_store_index(P, prep[b].origin_r, prep[b].origin_c, b, p.r, p.c, idx)) { m->g.err |= IVM_ERR_STORE_OVERFLOW; continue; }
-        IvmAtomics::max_ull(&P.cand[idx], ivm_cand_key(p.y, (uint32_t)pix));
+        ivm_cand_insert<IvmAtomics>(P, b, (uint32_t)(idx - (size_t)b * P.SR * P.SC), ivm_cand_key(P, p.y, (uint32_t)pix));
         IvmAtomics::min_i(&m->g.loc[0], p.r); IvmAtomics::max_i(&m->g.loc[1], p.r);
         IvmAtomics::min_i(&m->g.loc[2], p.c); IvmAtomics::max_i(&m->g.loc[3], p.c);
         m->g.acc_valid++;
@@ -301,9 +310,11 @@ void emu_status(const Emu *m, uint32_t *err, unsigned long long *stats8) {
 }
 
 // invariant check used by tests: the candidate plane must be all zero between steps
-long long emu_cand_nonzero(const Emu *m) {
+// slots of the candidate table that carry the stamp of the last step (= half-cells the last frame touched)
+long long emu_cand_current(const Emu *m) {
     long long n = 0;
-    for (size_t i = 0; i < m->cand.size(); ++i) n += m->cand[i] != 0ull;
+    const uint32_t stamp = (m->step - 1u) % 255u + 1u;
+    for (size_t i = 0; i < m->cand.size(); ++i) n += (m->cand[i].tag >> 24) == stamp && m->cand[i].tag != 0u;
     return n;
 }
 

@@ -44,8 +44,8 @@ def lib():
         L.emu_export_world.restype = ctypes.c_longlong
         L.emu_export_world.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, i64p, f32p, u8p, u64p]
         L.emu_status.argtypes = [ctypes.c_void_p, u32p, u64p]
-        L.emu_cand_nonzero.restype = ctypes.c_longlong
-        L.emu_cand_nonzero.argtypes = [ctypes.c_void_p]
+        L.emu_cand_current.restype = ctypes.c_longlong
+        L.emu_cand_current.argtypes = [ctypes.c_void_p]
         _lib = L
     return _lib
 
@@ -131,8 +131,11 @@ class EmuMapper:
         lib().emu_status(self._h, ctypes.byref(err), _p(stats, ctypes.c_uint64))
         return int(err.value), stats
 
-    def cand_nonzero(self):
-        return int(lib().emu_cand_nonzero(self._h))
+    def set_step(self, step):
+        lib().emu_set_step(self._h, ctypes.c_uint(step))
+
+    def cand_current(self):
+        return int(lib().emu_cand_current(self._h))
 
     def world(self):
         """Live records in the reference's list order (sorted by the reference key)."""

@@ -39,7 +39,22 @@ def test_emulator_matches_golden(name, order):
         assert np.array_equal(b, scn["ref_world_b"])
         assert np.array_equal(xyz.view(np.uint32), scn["ref_world_xyz"].view(np.uint32))  # same bits, same order
         assert np.array_equal(sem, scn["ref_world_sem"])
-        assert emu.cand_nonzero() == 0  # scratch plane left clean
+
+
+@pytest.mark.parametrize("name", ["iid_f64", "scene_overlap", "batch_shrink_grow"])
+def test_candidate_table_stamp_wrap(name):
+    """The frame candidate table is never cleared between steps: entries carry an 8-bit step stamp
+    that wraps every 255 steps.  Start just below the wrap so that it happens in mid-run."""
+    scn = load_golden(name)
+    emu = _emu(scn)
+    emu.set_step(255 * 3 - 4)
+    outs, sizes = run_mapper(emu.step, scn, world_fn=emu.world)
+    for t, (o, s) in enumerate(outs):
+        B = o.shape[0]
+        assert np.array_equal(o, scn["ref_occupancy"][t, :B]) and np.array_equal(s, scn["ref_semantic"][t, :B]), t
+    assert sizes == scn["ref_world_sizes"].tolist()
+    assert emu.cand_current() > 0
+    assert emu.status()[0] == 0
 
 
 @pytest.mark.parametrize("name", ["degenerate", "identical_envs", "scene_f32", "scene_overlap"])

@@ -120,6 +120,28 @@ def test_predicted_full_size_against_oracle():
         cs.mm.check_errors()
 
 
+@pytest.mark.parametrize("variant", [0, 2])
+def test_candidate_table_stamp_wrap(variant):
+    """300 steps of a small scenario: the 8-bit stamp of the frame candidate table wraps (and the
+    table is cleared by the host) at step 256; results must stay bit-exact against the oracle."""
+    from ivlnce_b200.synthetic import ScenarioConfig, make_scenario
+    from oracle.oracle import OracleMapper
+    from scenarios import _wrap
+
+    c = ScenarioConfig(num_envs=2, height=32, width=32, steps=300, resolution=0.1, num_labels=13,
+                       reset_steps={100: [0], 257: [1]}, seed=91, roam_radius=3.0)
+    scn = _wrap(c, make_scenario(c))
+    orc = OracleMapper(c.height, c.width, c.vfov_radians, c.map_meters, c.map_meters, c.resolution)
+    ref_outs, _ = run_mapper(orc.step, scn)
+    from cuda_stepper import CudaStepper
+
+    cs = CudaStepper(scn["cfg"], max_envs=2, scatter_variant=variant)
+    for t in range(c.steps):
+        o, s = cs.step(scn["masks"][t], scn["pose"][t], scn["orientation"][t], depth=scn["depth"][t], labels=scn["labels"][t])
+        assert np.array_equal(o, ref_outs[t][0]) and np.array_equal(s, ref_outs[t][1]), t
+    cs.mm.check_errors()
+
+
 def test_device_trig_f64_matches():
     """sin/cos evaluated by torch on the GPU in float64 round to the same float32 matrices."""
     scn = load_golden("iid_f64")
