@@ -84,18 +84,13 @@ struct IvmRecord {
     uint32_t meta;
 };
 
-// One slot of an env's frame candidate table: open addressing, keyed by the half-cell.
-//   tag = stamp << 24 | cell index in the env's store window   (cell < 2^24)
-//   val = stamp << 56 | orderable(height) << 24 | (0xFFFFFF - pixel index)
-// stamp = 1..255 cycles with the step counter, so entries of earlier steps read as free slots and
-// lose every atomicMax: the table is never cleared between steps (the host clears it once per
-// 255 steps, when the stamp wraps).  2 slots per pixel, 16 B each: 2 MB per env at 256x256 --
-// small enough to live in the 126 MB L2, so the frame de-dup never touches HBM.
-struct IvmCand {
-    unsigned long long val;
-    uint32_t tag;
-    uint32_t pad;
-};
+// Frame candidate plane: one 64-bit word per half-cell of every env's store window,
+//   word = stamp << 56 | orderable(height) << 24 | (0xFFFFFF - pixel index)
+// stamp = 1..255 cycles with the step counter, so words of earlier steps lose every atomicMax of the
+// current step: the plane is never cleaned between steps (the host clears it once per 255 steps,
+// when the stamp wraps).  Offering a point is ONE fire-and-forget 64-bit RED.MAX (no tag to claim,
+// no dependent round trip); a frame touches ~11 k distinct cells per env, so the live part of the
+// plane is a few hundred KB per env and stays in L2 between the scatter and the resolve.
 
 struct IvmEnv {                   // 64 bytes
     int32_t origin_r, origin_c;   // absolute half-cell index of store cell (0,0)
@@ -130,7 +125,6 @@ struct IvmEdge {
 #define IVM_ERR_EDGE_OVERFLOW 2u   // edge list / hash capacity exceeded
 #define IVM_ERR_KNOWN_OVERFLOW 4u  // known-map cloud larger than capacity / index range
 #define IVM_ERR_GRID_BARRIER 8u    // a grid barrier of the fused step kernel timed out (results invalid)
-#define IVM_ERR_CAND_OVERFLOW 16u  // frame candidate table full (cannot happen: it holds 2 slots per pixel)
 
 struct IvmGlobal {
     int32_t loc[4];               // frame (stage-1) bbox over all envs: rmin,rmax,cmin,cmax
@@ -162,8 +156,7 @@ struct IvmParams {
     int32_t tile_r, tile_c;       // ego tile of one raster CTA
     // persistent device memory
     IvmRecord *store;             // [maxB][SR][SC]
-    IvmCand *ctab;                // [maxB][chash] frame candidate table (see IvmCand)
-    uint32_t chash;               // slots per env, a power of two >= 2 * HW
+    unsigned long long *cplane;   // [maxB][SR][SC] frame candidate plane (see above)
     uint32_t cstamp;              // per step: 1..255
     IvmEnv *env;                  // [maxB]
     int32_t *rowcount, *colcount; // [maxB][SR], [maxB][SC] live records per store row / col
@@ -457,38 +450,15 @@ IVM_HD void ivm_reset_step_globals(IvmGlobal *g) {
 // list (they may collide with other cells); all others are
 // merged into the world store directly.  Returns 1 if the pixel was a
 // non-edge winner (for the LOCAL statistic).
-// Offer a point to its cell's slot of env b's candidate table (claiming a free or stale slot on
-// the way).  `cell` = index of the half-cell inside the env's store window.
+// Offer a point to its cell's word of env b's candidate plane.  `cell` = index of the half-cell
+// inside the env's store window.
 template <class A>
 IVM_HD void ivm_cand_insert(const IvmParams &P, int b, uint32_t cell, unsigned long long key) {
-    IvmCand *tab = P.ctab + (size_t)b * P.chash;
-    const uint32_t mask = P.chash - 1u, mine = (P.cstamp << 24) | cell;
-    uint32_t s = ivm_cand_hash(cell) & mask;
-    for (uint32_t probes = 0; probes <= mask; ++probes) {
-        uint32_t t = ivm_load_u32(&tab[s].tag);
-        for (;;) {
-            if (t == mine) { A::max_ull(&tab[s].val, key); return; }
-            if ((t >> 24) == P.cstamp) break;            // taken by another cell in this step: next slot
-            const uint32_t old = A::cas_u(&tab[s].tag, t, mine);  // free or stale: claim it
-            if (old == t) { A::max_ull(&tab[s].val, key); return; }
-            t = old;                                     // somebody else changed it first: look again
-        }
-        s = (s + 1u) & mask;
-    }
-    A::or_u(&P.g->err, IVM_ERR_CAND_OVERFLOW);
+    A::max_ull(&P.cplane[(size_t)b * P.SR * P.SC + cell], key);
 }
-// The winning key of a cell after all inserts of the step (0 if the cell has no slot).
+// The winning key of a cell after all inserts of the step (a stale or zero word if nothing was offered).
 IVM_HD unsigned long long ivm_cand_lookup(const IvmParams &P, int b, uint32_t cell) {
-    const IvmCand *tab = P.ctab + (size_t)b * P.chash;
-    const uint32_t mask = P.chash - 1u, mine = (P.cstamp << 24) | cell;
-    uint32_t s = ivm_cand_hash(cell) & mask;
-    for (uint32_t probes = 0; probes <= mask; ++probes) {
-        const uint32_t t = ivm_load_u32(&tab[s].tag);
-        if (t == mine) return ivm_load_ull(&tab[s].val);
-        if ((t >> 24) != P.cstamp) return 0ull;
-        s = (s + 1u) & mask;
-    }
-    return 0ull;
+    return ivm_load_ull(&P.cplane[(size_t)b * P.SR * P.SC + cell]);
 }
 IVM_HD bool ivm_on_frame_edge(const IvmPoint &p, const int32_t *loc) {
     return p.r == loc[0] || p.r == loc[1] || p.c == loc[2] || p.c == loc[3];

@@ -677,13 +677,16 @@ __device__ __forceinline__ unsigned long long global_timer() {
     return t;
 }
 
-// Grid barrier over the co-resident CTAs of a cooperative launch.  `target` = arrivals expected
-// on the monotone counter.  Returns false on time-out (never observed; guards against a hang).
-__device__ __forceinline__ bool grid_barrier(uint32_t *bar, uint32_t target, int *s_flag) {
-    __syncthreads();
+// Grid barrier over the co-resident CTAs of a cooperative launch, split into ARRIVE and WAIT so
+// that independent work can sit between the two.  `target` = arrivals expected on the monotone
+// counter.  grid_wait returns false on time-out (never observed; guards against a hang).
+// grid_arrive: called by ONE thread after a CTA-level barrier that covers the writes to publish.
+__device__ __forceinline__ void grid_arrive(uint32_t *bar) {
+    __threadfence();  // release: this CTA's writes (made visible to this thread by the bar.sync) before the arrival
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
+}
+__device__ __forceinline__ bool grid_wait(uint32_t *bar, uint32_t target, int *s_flag) {
     if (threadIdx.x == 0) {
-        __threadfence();  // release: this CTA's writes (made visible to thread 0 by the bar.sync) before the arrival
-        asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(bar), "r"(1u) : "memory");
         int ok = 1;
         uint32_t spins = 0;
         for (;;) {
@@ -701,11 +704,18 @@ __device__ __forceinline__ bool grid_barrier(uint32_t *bar, uint32_t target, int
     __syncthreads();
     return *s_flag != 0;
 }
+__device__ __forceinline__ bool grid_barrier(uint32_t *bar, uint32_t target, int *s_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) grid_arrive(bar);
+    return grid_wait(bar, target, s_flag);
+}
 
-#define IVM_F_BR 8             // tiles per resolve round (= consumer warps)
-struct FusedSlot {             // one tile of a resolve round
+#define IVM_F_BR 8             // tiles per round (= consumer warps)
+#define IVM_F_DRAIN 4          // queue entries per thread and drain iteration
+struct FusedSlot {             // one tile of a round
     float T[12];
-    int32_t b, tp0, origin_r, origin_c;
+    float cs[2];
+    int32_t b, tp0, origin_r, origin_c, reset;
     uint32_t reset_stamp;
     float h, hlo, hhi;
     int32_t box[5];            // bbox + count of the cells this CTA newly occupied in the slot's env
@@ -729,6 +739,8 @@ struct FusedShared {
         }                                                                                              \
     } while (0)
 
+// Tiles are dealt round-robin (tile = CTA + j * grid): valid pixels cluster in the image rows around
+// the horizon, so contiguous ranges would give a few CTAs all the scatter / resolve work.
 template <bool PRED>
 __global__ void __launch_bounds__(IVM_F_THREADS, IVM_F_CTAS_PER_SM)
 k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out, int nenv_total,
@@ -738,13 +750,17 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tpe = P.HW / IVM_F_TILE;                     // tiles per env
     const long long total = (long long)P.B * tpe;
-    const int t0 = (int)((long long)blockIdx.x * total / gridDim.x);
-    const int t1 = (int)((long long)(blockIdx.x + 1) * total / gridDim.x);
     IvmGlobal *g = P.g;
     if (blockIdx.x == 0 && tid == 0) { g->tstamp[0] = global_timer(); g->tstamp[5] = 0ull; }
     CTA_STAMP(7, 0);
 
-    // ================================================================ phase A: ingest-scatter
+    // ================================================================ phase A: ingest
+    //   A0 (consumers)  depth -> unproject -> ONE 64-bit RED.MAX per valid pixel into the candidate plane,
+    //                   8 tiles per round so that every thread has 8 depth loads in flight; then the CTA
+    //                   ARRIVES at grid barrier 1 without waiting
+    //   A1 (PRED)       class-score stream: the producer lane keeps a 6 x 16 KB shared-memory ring full with
+    //                   cp.async.bulk (TMA 1-D) copies of the planes from the first cycle of the kernel;
+    //                   the consumers run the argmax from shared memory and write the labels
     if (PRED && tid == 0) {
         for (int s = 0; s < IVM_F_NSTAGE; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], IVM_F_CONSUMERS / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -764,8 +780,8 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
             asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
             int slot = 0;
             uint32_t round = 0;  // how many times the ring has wrapped
-            for (int tile = t0; tile < t1; ++tile) {
-                const int eb = tile / tpe, tp0 = (tile - eb * tpe) * IVM_F_TILE;
+            for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int eb = (int)(tile / tpe), tp0 = (int)(tile - (long long)eb * tpe) * IVM_F_TILE;
                 const float *src = logits + (size_t)eb * ncls * P.HW + tp0;
                 for (int p0 = 0; p0 < ncls; p0 += IVM_F_SP) {
                     const int np = min(IVM_F_SP, ncls - p0);
@@ -779,45 +795,106 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
             }
         }
     } else {
-        // ---- consumer warps
-        float(*ring)[IVM_F_SP][IVM_F_TILE] = reinterpret_cast<float(*)[IVM_F_SP][IVM_F_TILE]>(dyn);
+        // ---- consumer warps, A0: depth scatter
         int rmin = INT32_MAX, rmax = INT32_MIN, cmin = INT32_MAX, cmax = INT32_MIN;
         unsigned nvalid = 0;
-        int cur_env = -1;
-        int slot = 0;
-        uint32_t round = 0;
         if (tid == 0) { sh.k1.bb[0] = INT32_MAX; sh.k1.bb[1] = INT32_MIN; sh.k1.bb[2] = INT32_MAX; sh.k1.bb[3] = INT32_MIN; sh.k1.valid = 0; }
-        for (int tile = t0; tile < t1; ++tile) {
-            const int b = tile / tpe, tp0 = (tile - b * tpe) * IVM_F_TILE;
-            const int pix0 = tp0 + tid * 2;
-            const size_t base = (size_t)b * P.HW + pix0;
-            const float2 dv = __ldcg(reinterpret_cast<const float2 *>(P.depth + base));  // stays in L2 for phase B
-            if (b != cur_env) {  // uniform over the consumers: a CTA's tile range is contiguous
-                group_bar(1, IVM_F_CONSUMERS);  // the previous env's matrices are no longer read
-                if (tid == 0) {
-                    const IvmEnvPrep q = ivm_env_decide(P, b);
-                    sh.k1.origin_r = q.origin_r; sh.k1.origin_c = q.origin_c; sh.k1.reset = q.reset;
+        for (int j0 = 0; (long long)blockIdx.x + (long long)j0 * gridDim.x < total; j0 += IVM_F_BR) {
+            if (j0) group_bar(1, IVM_F_CONSUMERS);  // the previous round's slots are no longer read
+            {   // warp k prepares slot k: env decision (reset / store origin, mapper.py:310-326) + pose matrices
+                const long long tile = (long long)blockIdx.x + (long long)(j0 + warp) * gridDim.x;
+                FusedSlot &sl = sh.slot[warp];
+                if (tile < total) {
+                    const int b = (int)(tile / tpe);
+                    if (lane == 0) {
+                        const IvmEnvPrep q = ivm_env_decide(P, b);
+                        sl.b = b; sl.tp0 = (int)(tile - (long long)b * tpe) * IVM_F_TILE;
+                        sl.origin_r = q.origin_r; sl.origin_c = q.origin_c; sl.reset = q.reset;
+                        sl.h = P.pose[3 * b + 1];
+                    }
+                    if (P.orient != nullptr) {
+                        if (lane == 1) ivm_pose_matrices(P, b, sl.T, sl.cs);
+                    } else if (lane >= 2 && lane < 14) {
+                        sl.T[lane - 2] = P.T12[12 * b + lane - 2];
+                    }
+                } else if (lane == 0) {
+                    sl.b = -1;
                 }
-                if (P.orient != nullptr) {
-                    if (tid == 32) ivm_pose_matrices(P, b, sh.k1.T, sh.k1.cs);
-                } else if (tid >= 32 && tid < 44) {
-                    sh.k1.T[tid - 32] = P.T12[12 * b + tid - 32];
-                }
-                group_bar(1, IVM_F_CONSUMERS);
-                cur_env = b;
             }
-            if (tp0 == 0) {  // the CTA that owns an env's first tile publishes the env's new state
+            // this round's depth loads go out before the barrier
+            float2 dv[IVM_F_BR];
+#pragma unroll
+            for (int k = 0; k < IVM_F_BR; ++k) {
+                const long long tile = (long long)blockIdx.x + (long long)(j0 + k) * gridDim.x;
+                dv[k] = make_float2(2.0f, 2.0f);
+                if (tile < total) dv[k] = __ldcg(reinterpret_cast<const float2 *>(P.depth + (size_t)tile * IVM_F_TILE + tid * 2));  // stays in L2 for phase B
+            }
+            group_bar(1, IVM_F_CONSUMERS);
+            // the CTA that owns an env's first tile publishes the env's new state (read after barrier 1 only)
+            for (int k = 0; k < IVM_F_BR; ++k) {
+                const FusedSlot &sl = sh.slot[k];
+                if (sl.b < 0 || sl.tp0 != 0) continue;  // uniform
                 IvmEnvPrep q;
-                q.reset = sh.k1.reset; q.origin_r = sh.k1.origin_r; q.origin_c = sh.k1.origin_c;
-                ivm_env_publish<IvmAtomics>(P, b, q, tid, IVM_F_CONSUMERS);
+                q.reset = sl.reset; q.origin_r = sl.origin_r; q.origin_c = sl.origin_c;
+                ivm_env_publish<IvmAtomics>(P, sl.b, q, tid, IVM_F_CONSUMERS);
                 if (P.orient != nullptr) {
-                    if (tid < 12) P.T12_buf[12 * b + tid] = sh.k1.T[tid];
-                    if (tid < 2) P.cs_buf[2 * b + tid] = sh.k1.cs[tid];
+                    if (tid < 12) P.T12_buf[12 * sl.b + tid] = sl.T[tid];
+                    if (tid < 2) P.cs_buf[2 * sl.b + tid] = sl.cs[tid];
                 }
             }
-            if (PRED) {
-                // PredictSemantics tail (mapper.py:795-798): running argmax over the planes, first max
-                // wins, NaN counts as maximal (torch.argmax)
+#pragma unroll
+            for (int k = 0; k < IVM_F_BR; ++k) {
+                const FusedSlot &sl = sh.slot[k];
+                if (sl.b < 0) continue;  // uniform
+                const int pix0 = sl.tp0 + tid * 2;
+                const int v = pix0 / P.W, u0 = pix0 - v * P.W;
+                const float ysv = P.ys[v];
+                const float dd[2] = {dv[k].x, dv[k].y};
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    IvmPoint p;
+                    const int ok = ivm_unproject(dd[j], P.xs[u0 + j], ysv, sl.T, sl.h, P.half_res, p);
+                    if (ok == 0) continue;
+                    size_t idx;
+                    if (ok == 2 || !ivm_store_index(P, sl.origin_r, sl.origin_c, sl.b, p.r, p.c, idx)) {
+                        atomicOr(&g->err, IVM_ERR_STORE_OVERFLOW);
+                        continue;
+                    }
+                    if (!(P.debug & 1))
+                        ivm_cand_insert<IvmAtomics>(P, sl.b, (uint32_t)(idx - (size_t)sl.b * P.SR * P.SC), ivm_cand_key(P, p.y, (uint32_t)(pix0 + j)));
+                    // the resolve phase will read-modify-write this cell's world record: pull it into L2 now
+                    if (!(P.debug & 2)) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.store[idx]));
+                    rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
+                    ++nvalid;
+                }
+            }
+        }
+        // frame bbox over ALL envs (mapper.py:465), one flush per CTA
+        const unsigned wv = warp_sum(nvalid);
+        if (wv) {
+            rmin = warp_min(rmin); rmax = warp_max(rmax); cmin = warp_min(cmin); cmax = warp_max(cmax);
+            if (lane == 0) {
+                atomicMin(&sh.k1.bb[0], rmin); atomicMax(&sh.k1.bb[1], rmax); atomicMin(&sh.k1.bb[2], cmin); atomicMax(&sh.k1.bb[3], cmax);
+                atomicAdd(&sh.k1.valid, wv);
+            }
+        }
+        group_bar(1, IVM_F_CONSUMERS);  // every consumer's REDs and the env publication are issued
+        if (tid == 0) {
+            if (sh.k1.valid) {
+                atomicMin(&g->loc[0], sh.k1.bb[0]); atomicMax(&g->loc[1], sh.k1.bb[1]);
+                atomicMin(&g->loc[2], sh.k1.bb[2]); atomicMax(&g->loc[3], sh.k1.bb[3]);
+                atomicAdd(&g->acc_valid, (unsigned long long)sh.k1.valid);
+            }
+            grid_arrive(P.bar);  // barrier 1: arrival only; the wait comes after the score stream
+        }
+        CTA_STAMP(10, 0);
+        // ---- consumer warps, A1: PredictSemantics tail (mapper.py:795-798): running argmax over the
+        //      planes, first max wins, NaN counts as maximal (torch.argmax)
+        if (PRED) {
+            float(*ring)[IVM_F_SP][IVM_F_TILE] = reinterpret_cast<float(*)[IVM_F_SP][IVM_F_TILE]>(dyn);
+            int slot = 0;
+            uint32_t round = 0;
+            for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
                 float best0 = 0.f, best1 = 0.f;
                 int a0 = 0, a1 = 0;
                 for (int p0 = 0; p0 < ncls; p0 += IVM_F_SP) {
@@ -845,58 +922,22 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
                 }
                 uchar2 o;
                 o.x = (uint8_t)a0; o.y = (uint8_t)a1;
-                *reinterpret_cast<uchar2 *>(labels_out + base) = o;
+                *reinterpret_cast<uchar2 *>(labels_out + (size_t)tile * IVM_F_TILE + tid * 2) = o;
             }
-            // unproject + scatter this thread's two pixels (the next tiles' planes are already in flight)
-            const float h = P.pose[3 * b + 1];
-            const int v = pix0 / P.W, u0 = pix0 - v * P.W;
-            const float ysv = P.ys[v];
-            const float dd[2] = {dv.x, dv.y};
-#pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                IvmPoint p;
-                const int ok = ivm_unproject(dd[j], P.xs[u0 + j], ysv, sh.k1.T, h, P.half_res, p);
-                if (ok == 0) continue;
-                size_t idx;
-                if (ok == 2 || !ivm_store_index(P, sh.k1.origin_r, sh.k1.origin_c, b, p.r, p.c, idx)) {
-                    atomicOr(&g->err, IVM_ERR_STORE_OVERFLOW);
-                    continue;
-                }
-                if (!(P.debug & 1))
-                    ivm_cand_insert<IvmAtomics>(P, b, (uint32_t)(idx - (size_t)b * P.SR * P.SC), ivm_cand_key(P, p.y, (uint32_t)(pix0 + j)));
-                // the resolve phase will read-modify-write this cell's world record: pull it into L2 now
-                if (!(P.debug & 2)) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.store[idx]));
-                rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
-                ++nvalid;
-            }
-        }
-        // frame bbox over ALL envs (mapper.py:465), one flush per CTA
-        const unsigned wv = warp_sum(nvalid);
-        if (wv) {
-            rmin = warp_min(rmin); rmax = warp_max(rmax); cmin = warp_min(cmin); cmax = warp_max(cmax);
-            if (lane == 0) {
-                atomicMin(&sh.k1.bb[0], rmin); atomicMax(&sh.k1.bb[1], rmax); atomicMin(&sh.k1.bb[2], cmin); atomicMax(&sh.k1.bb[3], cmax);
-                atomicAdd(&sh.k1.valid, wv);
-            }
-        }
-        group_bar(1, IVM_F_CONSUMERS);
-        if (tid == 0 && sh.k1.valid) {
-            atomicMin(&g->loc[0], sh.k1.bb[0]); atomicMax(&g->loc[1], sh.k1.bb[1]);
-            atomicMin(&g->loc[2], sh.k1.bb[2]); atomicMax(&g->loc[3], sh.k1.bb[3]);
-            atomicAdd(&g->acc_valid, (unsigned long long)sh.k1.valid);
         }
     }
     CTA_STAMP(6, 0);
-    if (!grid_barrier(P.bar, bar_base + 1u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
+    __syncthreads();  // the ring is drained: its memory becomes the resolve queue
+    if (!grid_wait(P.bar, bar_base + 1u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
     if (blockIdx.x == 0 && tid == 0) g->tstamp[1] = global_timer();
     CTA_STAMP(0, sh.flag);
 
     // ================================================================ phase B: resolve
-    // Valid pixels cluster in the image rows around the horizon, so tiles are dealt round-robin
-    // (tile = CTA + j * grid) and the CTA works in rounds of IVM_F_BR tiles: (1) all depth/label
-    // loads of the round are issued together and the filter survivors are compacted into ONE queue
-    // per CTA, (2) the queue is drained by all consumer threads, two entries at a time with the
-    // candidate-word loads and then the world-record loads of both entries in flight together.
+    // Rounds of IVM_F_BR tiles: (1) all depth/label loads of the round are issued together and the
+    // filter survivors are compacted into ONE queue per CTA (only ~1 pixel in 4 survives, clustered in
+    // a few image rows), (2) the queue is drained by all consumer threads, IVM_F_DRAIN entries at a
+    // time: the candidate word AND the world record of every entry are loaded together (the record
+    // speculatively), so a round costs one L2 round trip however many entries it holds.
     if (warp < IVM_F_CONSUMERS / 32) {
         uint32_t *q_pix = reinterpret_cast<uint32_t *>(dyn);                         // (slot << 24) | pixel
         float *q_d = reinterpret_cast<float *>(dyn + IVM_F_BR * IVM_F_TILE * 4);
@@ -905,22 +946,37 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
         const uint8_t *labels = P.labels;
         unsigned nlocal = 0;
         for (int j0 = 0; (long long)blockIdx.x + (long long)j0 * gridDim.x < total; j0 += IVM_F_BR) {
-            // ---- per-slot env data (warp k prepares slot k)
+            // ---- this round's pixel loads first (they do not depend on the slots)
+            float2 dv[IVM_F_BR];
+            uchar2 lv[IVM_F_BR];
+#pragma unroll
+            for (int k = 0; k < IVM_F_BR; ++k) {
+                const long long tile = (long long)blockIdx.x + (long long)(j0 + k) * gridDim.x;
+                dv[k] = make_float2(2.0f, 2.0f);
+                lv[k] = make_uchar2(0, 0);
+                if (tile < total) {
+                    const size_t base = (size_t)tile * IVM_F_TILE + tid * 2;
+                    dv[k] = __ldcg(reinterpret_cast<const float2 *>(P.depth + base));
+                    lv[k] = __ldcg(reinterpret_cast<const uchar2 *>(labels + base));
+                }
+            }
+            // ---- per-slot env data (warp k prepares slot k; every field is loaded by its own lane)
             {
                 const long long tile = (long long)blockIdx.x + (long long)(j0 + warp) * gridDim.x;
                 FusedSlot &sl = sh.slot[warp];
                 if (tile < total) {
                     const int b = (int)(tile / tpe);
+                    const IvmEnv *e = &P.env[b];
                     if (lane < 12) sl.T[lane] = __ldcg(&P.T12[12 * b + lane]);
-                    if (lane == 12) {
-                        const IvmEnv *e = &P.env[b];
-                        sl.b = b; sl.tp0 = (int)(tile - (long long)b * tpe) * IVM_F_TILE;
-                        sl.origin_r = __ldcg(&e->origin_r); sl.origin_c = __ldcg(&e->origin_c);
-                        sl.reset_stamp = __ldcg(&e->reset_stamp);
+                    if (lane == 12) { sl.b = b; sl.tp0 = (int)(tile - (long long)b * tpe) * IVM_F_TILE; }
+                    if (lane == 13) sl.origin_r = __ldcg(&e->origin_r);
+                    if (lane == 14) sl.origin_c = __ldcg(&e->origin_c);
+                    if (lane == 15) sl.reset_stamp = __ldcg(&e->reset_stamp);
+                    if (lane == 16) {
                         const float h = P.pose[3 * b + 1];
                         sl.h = h; sl.hlo = ivm_sub(h, 1.0f); sl.hhi = ivm_add(h, 0.5f);
-                        sl.box[0] = INT32_MAX; sl.box[1] = INT32_MIN; sl.box[2] = INT32_MAX; sl.box[3] = INT32_MIN; sl.box[4] = 0;
                     }
+                    if (lane == 17) { sl.box[0] = INT32_MAX; sl.box[1] = INT32_MIN; sl.box[2] = INT32_MAX; sl.box[3] = INT32_MIN; sl.box[4] = 0; }
                 } else if (lane == 12) {
                     sl.b = -1;
                 }
@@ -928,24 +984,12 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
             }
             group_bar(1, IVM_F_CONSUMERS);
             if (j0 == 0) CTA_STAMP(1, *(volatile unsigned *)&sh.qn);
-            // ---- filter pass: this warp's 64-pixel segment of every tile of the round
-            float2 dv[IVM_F_BR];
-            uchar2 lv[IVM_F_BR];
-#pragma unroll
-            for (int k = 0; k < IVM_F_BR; ++k) {
-                dv[k] = make_float2(2.0f, 2.0f);
-                lv[k] = make_uchar2(0, 0);
-                if (sh.slot[k].b >= 0) {
-                    const size_t base = (size_t)sh.slot[k].b * P.HW + sh.slot[k].tp0 + warp * 64 + lane * 2;
-                    dv[k] = __ldcg(reinterpret_cast<const float2 *>(P.depth + base));
-                    lv[k] = __ldcg(reinterpret_cast<const uchar2 *>(labels + base));
-                }
-            }
+            // ---- filter pass: this thread's two pixels of every tile of the round
 #pragma unroll
             for (int k = 0; k < IVM_F_BR; ++k) {
                 const FusedSlot &sl = sh.slot[k];
                 if (sl.b < 0) continue;  // uniform
-                const int pix0 = sl.tp0 + warp * 64 + lane * 2;
+                const int pix0 = sl.tp0 + tid * 2;
                 const int v = pix0 / P.W, u0 = pix0 - v * P.W;
                 const float ysv = P.ys[v];
                 const float dd[2] = {dv[k].x, dv[k].y};
@@ -981,20 +1025,22 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
             }
             group_bar(1, IVM_F_CONSUMERS);
             if (j0 == 0) CTA_STAMP(2, *(volatile unsigned *)&sh.qn);
-            // ---- drain: two entries per thread and iteration
+            // ---- drain
             const int n = (int)sh.qn;
-            for (int i0 = tid; i0 < n; i0 += 2 * IVM_F_CONSUMERS) {
-                IvmPoint pt[2];
-                size_t idx[2];
-                uint32_t pix[2];
-                int kk[2];
-                bool act[2];
-                unsigned long long cw[2];
+            for (int i0 = tid; i0 < n; i0 += IVM_F_DRAIN * IVM_F_CONSUMERS) {
+                IvmPoint pt[IVM_F_DRAIN];
+                size_t idx[IVM_F_DRAIN];
+                uint32_t pix[IVM_F_DRAIN];
+                int kk[IVM_F_DRAIN];
+                bool act[IVM_F_DRAIN];
+                unsigned long long cw[IVM_F_DRAIN];
+                IvmRecord old[IVM_F_DRAIN];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
+                for (int u = 0; u < IVM_F_DRAIN; ++u) {
                     const int i = i0 + u * IVM_F_CONSUMERS;
                     act[u] = i < n;
                     cw[u] = 0ull; idx[u] = 0; pix[u] = 0; kk[u] = 0;
+                    old[u].x = old[u].y = old[u].z = 0.f; old[u].meta = 0u;
                     if (act[u]) {
                         const uint32_t qp = q_pix[i];
                         kk[u] = (int)(qp >> 24); pix[u] = qp & 0xFFFFFFu;
@@ -1002,32 +1048,25 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
                         const int v = (int)pix[u] / P.W, uu = (int)pix[u] - v * P.W;
                         act[u] = ivm_unproject(q_d[i], P.xs[uu], P.ys[v], sl.T, sl.h, P.half_res, pt[u]) == 1 &&
                                  ivm_store_index(P, sl.origin_r, sl.origin_c, sl.b, pt[u].r, pt[u].c, idx[u]);
-                        if (act[u]) cw[u] = ivm_cand_lookup(P, sl.b, (uint32_t)(idx[u] - (size_t)sl.b * P.SR * P.SC));
-                    }
-                }
-                IvmRecord old[2];
-                bool merge[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    merge[u] = false;
-                    old[u].x = old[u].y = old[u].z = 0.f; old[u].meta = 0u;
-                    if (act[u] && cw[u] == ivm_cand_key(P, pt[u].y, pix[u])) {
-                        if (ivm_on_frame_edge(pt[u], loc)) {
-                            ivm_push_edge1<IvmAtomics>(P, sh.slot[kk[u]].b, pix[u], pt[u], q_lab[i0 + u * IVM_F_CONSUMERS], idx[u]);
-                        } else {
-                            merge[u] = true;
+                        if (act[u]) {
+                            cw[u] = ivm_cand_lookup(P, sl.b, (uint32_t)(idx[u] - (size_t)sl.b * P.SR * P.SC));
                             old[u] = ivm_load_record(&P.store[idx[u]]);
                         }
                     }
                 }
 #pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    if (!merge[u]) continue;
+                for (int u = 0; u < IVM_F_DRAIN; ++u) {
+                    if (!act[u] || cw[u] != ivm_cand_key(P, pt[u].y, pix[u])) continue;
                     FusedSlot &sl = sh.slot[kk[u]];
+                    const uint32_t label = q_lab[i0 + u * IVM_F_CONSUMERS];
+                    if (ivm_on_frame_edge(pt[u], loc)) {
+                        ivm_push_edge1<IvmAtomics>(P, sl.b, pix[u], pt[u], label, idx[u]);
+                        continue;
+                    }
                     IvmBoxAcc acc;
                     acc.clear();
-                    ivm_merge_record<IvmAtomics>(P, sl.b, idx[u], pt[u].r, pt[u].c, pt[u].x, pt[u].y, pt[u].z,
-                                                 q_lab[i0 + u * IVM_F_CONSUMERS], old[u], sl.reset_stamp, sl.origin_r, sl.origin_c, acc);
+                    ivm_merge_record<IvmAtomics>(P, sl.b, idx[u], pt[u].r, pt[u].c, pt[u].x, pt[u].y, pt[u].z, label, old[u],
+                                                 sl.reset_stamp, sl.origin_r, sl.origin_c, acc);
                     ++nlocal;
                     if (acc.n) {  // a newly occupied cell: fold into the slot's box
                         atomicMin(&sl.box[0], acc.rmin); atomicMax(&sl.box[1], acc.rmax);
@@ -1300,11 +1339,6 @@ static uint32_t edge_capacity(const ivm_config *c) {
     if (cap > (1ll << 20)) cap = 1ll << 20;
     return (uint32_t)cap;
 }
-static uint32_t cand_slots(const ivm_config *c) {  // 2 slots per pixel, power of two
-    uint32_t h = 1024;
-    while ((long long)h < 2ll * c->height * c->width) h <<= 1;
-    return h;
-}
 static uint32_t hash_size(uint32_t ecap) { uint32_t h = 1024; while (h < 2 * ecap) h <<= 1; return h; }
 
 static void carve(const ivm_config *c, void *ws, IvmParams *P, ivm_ctx *ctx, size_t *total) {
@@ -1337,8 +1371,7 @@ static void carve(const ivm_config *c, void *ws, IvmParams *P, ivm_ctx *ctx, siz
     uint32_t *kfill = nullptr, *ktotals = nullptr;
     if (c->mode == 0) {
         q.store = cv.take<IvmRecord>(B * SR * SC);
-        q.chash = cand_slots(c);
-        q.ctab = cv.take<IvmCand>(B * (size_t)q.chash);
+        q.cplane = cv.take<unsigned long long>(B * SR * SC);
     } else {
         q.kcap = c->known_capacity;
         q.kpts = cv.take<IvmRecord>(B * (size_t)c->known_capacity);
@@ -1569,8 +1602,9 @@ int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const
     P.B = num_envs; P.step = ctx->step;
     P.cstamp = (ctx->step - 1u) % 255u + 1u;
     if (P.cstamp == 1u && ctx->step > 1u) {  // the 8-bit stamp wrapped: forget the last 255 steps' candidates
-        cudaError_t e = cudaMemsetAsync(P.ctab, 0, sizeof(IvmCand) * (size_t)ctx->cfg.max_envs * P.chash, (cudaStream_t)stream);
-        if (e != cudaSuccess) return cuda_fail(ctx, e, "candidate table clear");
+        cudaError_t e = cudaMemsetAsync(P.cplane, 0, sizeof(unsigned long long) * (size_t)ctx->cfg.max_envs * P.SR * P.SC,
+                                        (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "candidate plane clear");
     }
     P.depth = depth; P.labels = labels ? labels : labels_out; P.pose = pose; P.masks = masks;
     P.occ = occ; P.sem = sem;

@@ -23,7 +23,7 @@ struct Emu {
     int order;  // 0 forward, 1 reverse, 2 strided
     int fix_cap;  // capacity of the fix-up's small-class fast path (0 forces the hash path)
     std::vector<IvmRecord> store;
-    std::vector<IvmCand> cand;
+    std::vector<unsigned long long> cand;
     std::vector<IvmEnv> env;
     std::vector<int32_t> rowcount, colcount, segs;
     IvmGlobal g;
@@ -65,18 +65,14 @@ Emu *emu_create(int H, int W, const float *xs, const float *ys, float res, float
     if (mode == 0) {
         IvmRecord z; z.x = z.y = z.z = 0.f; z.meta = 0;
         m->store.assign(cells, z);
-        uint32_t ch = 1024;
-        while ((long long)ch < 2ll * H * W) ch <<= 1;
-        IvmCand zc; zc.val = 0ull; zc.tag = 0u; zc.pad = 0u;
-        m->cand.assign((size_t)maxB * ch, zc);
-        P.chash = ch;
+        m->cand.assign(cells, 0ull);
     } else {
         IvmRecord z; z.x = z.y = z.z = 0.f; z.meta = 0;
         m->kpts.assign((size_t)maxB * kcap, z);
         m->koff.assign((size_t)maxB * ((size_t)SR * SC + 1), 0u);
         P.kcap = kcap;
     }
-    P.store = m->store.data(); P.ctab = m->cand.data(); P.env = m->env.data();
+    P.store = m->store.data(); P.cplane = m->cand.data(); P.env = m->env.data();
     P.rowcount = m->rowcount.data(); P.colcount = m->colcount.data(); P.g = &m->g;
     P.e1 = m->e1.data(); P.e2 = m->e2.data(); P.ecap = ecap; P.segs = m->segs.data();
     P.hkeys = m->hkeys.data(); P.hbest = m->hbest.data(); P.hxord = m->hxord.data(); P.hmask = hs - 1;
@@ -178,7 +174,7 @@ int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels,
     IvmParams P = m->P;
     P.B = B; P.step = m->step;
     P.cstamp = (m->step - 1u) % 255u + 1u;
-    if (P.cstamp == 1u && m->step > 1u) { IvmCand zc; zc.val = 0ull; zc.tag = 0u; zc.pad = 0u; std::fill(m->cand.begin(), m->cand.end(), zc); }
+    if (P.cstamp == 1u && m->step > 1u) std::fill(m->cand.begin(), m->cand.end(), 0ull);
     P.depth = depth; P.labels = labels; P.T12 = T12; P.pose = pose; P.cs = cs; P.masks = masks;
     P.occ = occ; P.sem = sem;
     if (orient) {  // the K0 path that derives the matrices from the angles
@@ -309,12 +305,11 @@ void emu_status(const Emu *m, uint32_t *err, unsigned long long *stats8) {
     for (int i = 0; i < IVM_NSTATS; ++i) stats8[i] = m->g.stats[i];
 }
 
-// invariant check used by tests: the candidate plane must be all zero between steps
-// slots of the candidate table that carry the stamp of the last step (= half-cells the last frame touched)
+// words of the candidate plane that carry the stamp of the last step (= half-cells the last frame touched)
 long long emu_cand_current(const Emu *m) {
     long long n = 0;
     const uint32_t stamp = (m->step - 1u) % 255u + 1u;
-    for (size_t i = 0; i < m->cand.size(); ++i) n += (m->cand[i].tag >> 24) == stamp && m->cand[i].tag != 0u;
+    for (size_t i = 0; i < m->cand.size(); ++i) n += (uint32_t)(m->cand[i] >> 56) == stamp;
     return n;
 }
 

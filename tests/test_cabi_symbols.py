@@ -35,8 +35,8 @@ def test_workspace_size_and_argument_checks():
     cfg = _lib.IvmConfig(max_envs=16, height=256, width=256, map_rows=128, map_cols=128, res=0.05, half_res=0.025,
                          half_h=3.2, half_w=3.2, store_rows=2048, store_cols=2048, mode=0, known_capacity=0)
     n = L.ivm_workspace_bytes(ctypes.byref(cfg))
-    # 16-byte record per half-cell + a 2 MiB frame candidate table (2 x 16-byte slots per pixel) per env
-    assert 16 * (2048 * 2048 * 16 + 2 * 256 * 256 * 16) < n < 16 * 2048 * 2048 * 17
+    # 16-byte record + 8-byte frame candidate word per half-cell, plus small bookkeeping
+    assert 24 * 2048 * 2048 * 16 < n < 25 * 2048 * 2048 * 16
     bad = _lib.IvmConfig(max_envs=0)
     assert L.ivm_workspace_bytes(ctypes.byref(bad)) == 0
     ctx = ctypes.c_void_p()
