@@ -192,6 +192,7 @@ struct IvmParams {
     int32_t debug;                // profiling experiments only (config.reserved[1]); results are invalid when non-zero:
                                   // 1 = ingest phase without candidate inserts, 2 = without world-record prefetch
     uint8_t *occ, *sem;           // [B][R][C]
+    uint32_t *tile_dirty;         // [maxB][ego tiles]: == step if the tile holds a record the edge fix-up may still change
 };
 
 #define IVM_EMPTY_KEY 0xFFFFFFFFFFFFFFFFull
@@ -201,19 +202,41 @@ struct IvmParams {
 // Record / candidate loads.  In the fused step kernel these locations are written by other SMs
 // earlier in the SAME launch, so the device versions read through L2 (ld.global.cg) and never
 // from a possibly stale L1 line.
+// The world store and the candidate plane are touched sparsely but in (nearly) the same places step after
+// step, while hundreds of MB of class scores stream through L2 in between: their accesses carry an
+// L2 evict_last policy (the score stream is evict_first), so that the working set of a few MB per env
+// stays L2-resident across steps instead of being re-fetched from HBM at loaded latency.
+#if defined(__CUDACC__)
+__device__ __forceinline__ unsigned long long ivm_policy_keep() {
+    unsigned long long p;
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+#endif
 #if defined(__CUDA_ARCH__)
 IVM_HD IvmRecord ivm_load_record(const IvmRecord *p) {
-    const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(p));
+    uint4 v;
+    asm volatile("ld.global.cg.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(ivm_policy_keep()));
     IvmRecord r;
     r.x = __uint_as_float(v.x); r.y = __uint_as_float(v.y); r.z = __uint_as_float(v.z); r.meta = v.w;
     return r;
 }
-IVM_HD unsigned long long ivm_load_ull(const unsigned long long *p) { return __ldcg(p); }
+IVM_HD void ivm_store_record(IvmRecord *p, const IvmRecord &r) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(__float_as_uint(r.x)),
+                 "r"(__float_as_uint(r.y)), "r"(__float_as_uint(r.z)), "r"(r.meta), "l"(ivm_policy_keep()) : "memory");
+}
+IVM_HD unsigned long long ivm_load_ull(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.global.cg.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(ivm_policy_keep()));
+    return v;
+}
 IVM_HD uint32_t ivm_load_u32(const uint32_t *p) { return __ldcg(p); }
 IVM_HD uint32_t ivm_load_meta(const IvmRecord *p) { return __ldcg(&p->meta); }
 #else
 IVM_HD uint32_t ivm_load_meta(const IvmRecord *p) { return p->meta; }
 IVM_HD IvmRecord ivm_load_record(const IvmRecord *p) { return *p; }
+IVM_HD void ivm_store_record(IvmRecord *p, const IvmRecord &r) { *p = r; }
 IVM_HD unsigned long long ivm_load_ull(const unsigned long long *p) { return *p; }
 IVM_HD uint32_t ivm_load_u32(const uint32_t *p) { return *p; }
 #endif
@@ -269,22 +292,30 @@ struct IvmPoint {
     int32_t r, c;  // absolute half-row (from z) and half-col (from x)
 };
 
-// returns 0 = filtered out, 1 = valid point, 2 = valid but its cell index is not representable
-// (non-finite / absurd coordinates; the caller flags IVM_ERR_STORE_OVERFLOW)
-IVM_HD int ivm_unproject(float d, float xs_u, float ys_v, const float *T, float h, float half_res, IvmPoint &p) {
-    if (!(d > 0.01f && d < 0.99f)) return 0;
-    const float z = ivm_mul(d, 10.0f);
-    const float xc = ivm_mul(z, xs_u);
-    const float yc = ivm_mul(z, ys_v);
+// world coordinates of one depth pixel (shared by every caller, so that a point recomputed in a later
+// phase is bit-identical to the one offered to the candidate plane)
+IVM_HD void ivm_world_xyz(float d, float xs_u, float ys_v, const float *T, float &x, float &y, float &z) {
+    const float zc = ivm_mul(d, 10.0f);
+    const float xc = ivm_mul(zc, xs_u);
+    const float yc = ivm_mul(zc, ys_v);
     float w[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         float acc = ivm_mul(T[4 * r + 0], xc);
         acc = ivm_fma(T[4 * r + 1], yc, acc);
-        acc = ivm_fma(T[4 * r + 2], z, acc);
+        acc = ivm_fma(T[4 * r + 2], zc, acc);
         acc = ivm_fma(T[4 * r + 3], 1.0f, acc);
         w[r] = acc;
     }
+    x = w[0]; y = w[1]; z = w[2];
+}
+
+// returns 0 = filtered out, 1 = valid point, 2 = valid but its cell index is not representable
+// (non-finite / absurd coordinates; the caller flags IVM_ERR_STORE_OVERFLOW)
+IVM_HD int ivm_unproject(float d, float xs_u, float ys_v, const float *T, float h, float half_res, IvmPoint &p) {
+    if (!(d > 0.01f && d < 0.99f)) return 0;
+    float w[3];
+    ivm_world_xyz(d, xs_u, ys_v, T, w[0], w[1], w[2]);
     if (!(w[1] > ivm_sub(h, 1.0f) && w[1] < ivm_add(h, 0.5f))) return 0;
     const float rf = rintf(ivm_div(w[2], half_res));
     const float cf = rintf(ivm_div(w[0], half_res));
@@ -348,7 +379,7 @@ IVM_HD void ivm_merge_record(const IvmParams &P, int b, size_t idx, int32_t r, i
     if (live && !(y > old.y)) return;
     IvmRecord rec;
     rec.x = x; rec.y = y; rec.z = z; rec.meta = (P.step << 8) | (label & 0xFFu);
-    P.store[idx] = rec;
+    ivm_store_record(&P.store[idx], rec);
     if (!live) {
         A::add_i(&P.rowcount[(size_t)b * P.SR + (r - origin_r)], 1);
         A::add_i(&P.colcount[(size_t)b * P.SC + (c - origin_c)], 1);
@@ -373,19 +404,24 @@ struct IvmEnvPrep {
     int32_t reset;
     int32_t origin_r, origin_c;
 };
-IVM_HD IvmEnvPrep ivm_env_decide(const IvmParams &P, int b) {  // b < P.B
-    const IvmEnv *e = &P.env[b];
+// the decision from already loaded values (callers that batch the loads)
+IVM_HD IvmEnvPrep ivm_env_decide_vals(const IvmParams &P, uint32_t mask, int32_t count, int32_t e_origin_r, int32_t e_origin_c,
+                                      float pose_x, float pose_z) {
     IvmEnvPrep q;
-    q.reset = (P.masks[b] == 0) || (e->count <= 0);
+    q.reset = (mask == 0u) || (count <= 0);
     if (q.reset) {
-        const float pr = rintf(ivm_div(P.pose[3 * b + 2], P.half_res));
-        const float pc = rintf(ivm_div(P.pose[3 * b + 0], P.half_res));
+        const float pr = rintf(ivm_div(pose_z, P.half_res));
+        const float pc = rintf(ivm_div(pose_x, P.half_res));
         q.origin_r = (fabsf(pr) < 1.0e9f ? (int32_t)pr : 0) - P.SR / 2;
         q.origin_c = (fabsf(pc) < 1.0e9f ? (int32_t)pc : 0) - P.SC / 2;
     } else {
-        q.origin_r = e->origin_r; q.origin_c = e->origin_c;
+        q.origin_r = e_origin_r; q.origin_c = e_origin_c;
     }
     return q;
+}
+IVM_HD IvmEnvPrep ivm_env_decide(const IvmParams &P, int b) {  // b < P.B
+    const IvmEnv *e = &P.env[b];
+    return ivm_env_decide_vals(P, P.masks[b], e->count, e->origin_r, e->origin_c, P.pose[3 * b + 0], P.pose[3 * b + 2]);
 }
 // called by all `nthreads` threads of the publishing CTA; for b >= P.B the env is simply wiped
 template <class A>
@@ -725,6 +761,66 @@ IVM_HD void ivm_fixup_scan(const IvmParams &P, int blk, int nblk, int tid, int n
     }
 }
 
+// The same scan by ONE thread block.  The segment headers (and what is needed of their envs) are staged in
+// block memory first; then every thread loads the metas of IVM_SCAN_MLP cells together (independent loads)
+// before any live cell is appended, so the whole scan costs a few memory round trips.
+#define IVM_SCAN_MLP 16
+#define IVM_SCAN_HDR 8   // ints per staged segment: b, is_col, line, len, lo, origin_r, origin_c, reset_stamp
+template <class A>
+IVM_HD void ivm_fixup_scan_block(const IvmParams &P, const IvmFixScratch &S, int tid, int nthreads) {
+    const IvmGlobal *g = P.g;
+    const int nseg = (int)g->n_seg, nchunks = (int)g->scan_chunks;
+    if (nseg <= 0 || nchunks <= 0) return;  // block-uniform
+    if ((size_t)nseg * IVM_SCAN_HDR * sizeof(int32_t) > (size_t)S.cap * sizeof(unsigned long long) ||
+        (long long)nchunks * IVM_SCAN_CHUNK * nseg > (1ll << 30)) {
+        ivm_fixup_scan<A>(P, 0, 1, tid, nthreads);  // more segments than the scratch holds
+        return;
+    }
+    int32_t *hdr = reinterpret_cast<int32_t *>(S.key);  // free between the two class resolutions
+    for (int q = tid; q < nseg; q += nthreads) {
+        const int b = P.segs[4 * q + 0], is_col = P.segs[4 * q + 1];
+        const IvmEnv &e = P.env[b];
+        hdr[IVM_SCAN_HDR * q + 0] = b; hdr[IVM_SCAN_HDR * q + 1] = is_col;
+        hdr[IVM_SCAN_HDR * q + 2] = P.segs[4 * q + 2]; hdr[IVM_SCAN_HDR * q + 3] = P.segs[4 * q + 3];
+        hdr[IVM_SCAN_HDR * q + 4] = is_col ? e.rmin : e.cmin;
+        hdr[IVM_SCAN_HDR * q + 5] = e.origin_r; hdr[IVM_SCAN_HDR * q + 6] = e.origin_c;
+        hdr[IVM_SCAN_HDR * q + 7] = (int32_t)e.reset_stamp;
+    }
+    A::sync();
+    const int32_t grmin = g->glob[0], grmax = g->glob[1];
+    const int32_t loc[4] = {g->loc[0], g->loc[1], g->loc[2], g->loc[3]};
+    const int span = nchunks * IVM_SCAN_CHUNK;  // padded cells per segment
+    const int total = span * nseg;
+    for (int base = 0; base < total; base += nthreads * IVM_SCAN_MLP) {
+        uint32_t meta[IVM_SCAN_MLP];
+#pragma unroll
+        for (int j = 0; j < IVM_SCAN_MLP; ++j) {
+            meta[j] = 0u;
+            const int i = base + j * nthreads + tid;
+            if (i >= total) continue;
+            const int q = i / span, off = i - q * span;
+            const int32_t *h = hdr + IVM_SCAN_HDR * q;
+            if (off >= h[3]) continue;
+            const int32_t v = h[4] + off;
+            if (h[1] && (v == grmin || v == grmax)) continue;  // corners belong to the row scans
+            size_t idx;
+            if (!ivm_store_index(P, h[5], h[6], h[0], h[1] ? v : h[2], h[1] ? h[2] : v, idx)) continue;
+            meta[j] = ivm_load_meta(&P.store[idx]);
+        }
+#pragma unroll
+        for (int j = 0; j < IVM_SCAN_MLP; ++j) {
+            if (meta[j] == 0u) continue;
+            const int i = base + j * nthreads + tid;
+            const int q = i / span, off = i - q * span;
+            const int32_t *h = hdr + IVM_SCAN_HDR * q;
+            if (!ivm_live(meta[j], (uint32_t)h[7])) continue;
+            const int32_t v = h[4] + off;
+            ivm_scan_edge_cell<A>(P, h[0], h[1] ? v : h[2], h[1] ? h[2] : v, loc);
+        }
+    }
+    A::sync();  // the staged headers are dead: the scratch goes back to the class resolution
+}
+
 template <class A>
 IVM_HD void ivm_fixup_stage2(const IvmParams &P, const IvmFixScratch &S, int tid, int nthreads) {
     IvmGlobal *g = P.g;
@@ -789,7 +885,7 @@ IVM_HD void ivm_fixup_program(const IvmParams &P, const IvmFixScratch &S, int ti
     ivm_fixup_stage1<A>(P, S, tid, nthreads);
     A::sync();
     IVM_TRACE(P.g, 3, tid);
-    ivm_fixup_scan<A>(P, 0, 1, tid, nthreads);
+    ivm_fixup_scan_block<A>(P, S, tid, nthreads);
     A::sync();
     ivm_fixup_stage2<A>(P, S, tid, nthreads);
 }
@@ -868,4 +964,12 @@ IVM_HD bool ivm_ego_cell(const IvmParams &P, float x, float y, float z, float px
     const bool in = band && rf >= 0.0f && rf < (float)P.R && cf >= 0.0f && cf < (float)P.C;
     row = in ? (int32_t)rf : 0; col = in ? (int32_t)cf : 0;
     return in;
+}
+
+// The ego tile a world record falls into (if any) still depends on the edge fix-up: stamp it.
+IVM_HD void ivm_mark_tile(const IvmParams &P, int b, float x, float y, float z, float px, float h, float pz, float c, float s) {
+    int32_t row, col;
+    if (!ivm_ego_cell(P, x, y, z, px, h, pz, c, s, row, col)) return;
+    const int tiles_x = (P.C + P.tile_c - 1) / P.tile_c, tiles_y = (P.R + P.tile_r - 1) / P.tile_r;
+    P.tile_dirty[(size_t)b * (tiles_x * tiles_y) + (row / P.tile_r) * tiles_x + col / P.tile_c] = P.step;
 }

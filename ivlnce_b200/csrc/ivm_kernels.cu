@@ -530,9 +530,12 @@ static inline size_t raster_smem_bytes(int tile_r, int tile_c, int max_rows) {
     return (((size_t)tile_r * tile_c * 5 + (size_t)max_rows * 8 + 16) + 15) & ~(size_t)15;
 }
 
+// safe_only: the tile is rastered only if nothing under it can still be changed by the edge fix-up, i.e. no
+// frame-edge winner is pending in it (tile_dirty stamp) and its store footprint stays strictly inside the
+// env's bounding box (stage-2 collisions live on the bbox edge lines).  Returns false if the tile was skipped.
 template <bool KNOWN>
-__device__ __forceinline__ void raster_tile(const IvmParams &P, int max_rows, int b, int r0, int c0, uint32_t *smem, int tid,
-                                            int nthr, int bar_id, unsigned &n_in) {
+__device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, int b, int r0, int c0, uint32_t *smem, int tid,
+                                            int nthr, int bar_id, unsigned &n_in, bool safe_only = false) {
     const int tr = P.tile_r, tc = P.tile_c;
     uint32_t *skey = smem;
     int32_t *s_clo = reinterpret_cast<int32_t *>(skey + tr * tc);   // first store column of each half-row's span
@@ -542,7 +545,7 @@ __device__ __forceinline__ void raster_tile(const IvmParams &P, int max_rows, in
     const int r1 = min(r0 + tr, P.R), c1 = min(c0 + tc, P.C);
     group_bar(bar_id, nthr);  // the group's previous tile has been written out
     for (int i = tid; i < tr * tc; i += nthr) { skey[i] = 0u; socc[i] = 0; }
-    if (tid == 0) *s_maxlen = 0;
+    if (tid == 0) { s_maxlen[0] = 0; s_maxlen[1] = 0; }
     const IvmEnv e = P.env[b];
     const float px = P.pose[3 * b + 0], h = P.pose[3 * b + 1], pz = P.pose[3 * b + 2];
     const float c = P.cs[2 * b + 0], s = P.cs[2 * b + 1];
@@ -565,8 +568,16 @@ __device__ __forceinline__ void raster_tile(const IvmParams &P, int max_rows, in
         const int len = chi >= clo ? chi - clo + 1 : 0;
         s_clo[i] = clo; s_len[i] = len;
         if (len > 0) atomicMax(s_maxlen, len);
+        if (!KNOWN && safe_only && len > 0 &&
+            (row_lo + i <= e.rmin || row_lo + i >= e.rmax || clo <= e.cmin || chi >= e.cmax))
+            s_maxlen[1] = 1;
+    }
+    if (!KNOWN && safe_only && tid == 0) {
+        const int tiles_x = (P.C + P.tile_c - 1) / P.tile_c, tiles_y = (P.R + P.tile_r - 1) / P.tile_r;
+        if (__ldcg(&P.tile_dirty[(size_t)b * (tiles_x * tiles_y) + (r0 / P.tile_r) * tiles_x + c0 / P.tile_c]) == P.step) s_maxlen[1] = 1;
     }
     group_bar(bar_id, nthr);
+    if (!KNOWN && safe_only && s_maxlen[1]) return false;  // uniform
     if (!KNOWN) {
         // phase 2: one half-warp per store half-row (a span under a 16x16 tile holds ~40 records);
         // its 16 lanes read up to IVM_RASTER_MLP x 16 consecutive records (independent 16-byte
@@ -578,7 +589,7 @@ __device__ __forceinline__ void raster_tile(const IvmParams &P, int max_rows, in
             const int i = j >> 3, seg = j & 7;  // a span of <= 64 records covers <= 9 lines; longer spans are only partly prefetched
             if (seg * 8 < s_len[i]) {
                 const size_t first = (size_t)(row_lo + i - e.origin_r) * P.SC + (size_t)(s_clo[i] - e.origin_c);
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(env_store + first + seg * 8));
+                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(env_store + first + seg * 8));
             }
         }
         for (int i = hw; i < nrows; i += nhw) {
@@ -593,7 +604,10 @@ __device__ __forceinline__ void raster_tile(const IvmParams &P, int max_rows, in
                     have[u] = off < len;
                     raw[u] = make_uint4(0, 0, 0, 0);
                     // L2-only load: in the fused kernel the records were written earlier in the same launch
-                    if (have[u]) raw[u] = __ldcg(reinterpret_cast<const uint4 *>(env_store + rowbase + off));
+                    if (have[u]) {
+                        const IvmRecord q = ivm_load_record(env_store + rowbase + off);
+                        raw[u] = make_uint4(__float_as_uint(q.x), __float_as_uint(q.y), __float_as_uint(q.z), q.meta);
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < IVM_RASTER_MLP; ++u)
@@ -631,6 +645,7 @@ __device__ __forceinline__ void raster_tile(const IvmParams &P, int max_rows, in
         P.occ[o] = socc[rr * tc + cc];
         P.sem[o] = (uint8_t)(skey[rr * tc + cc] & 0xFFu);
     }
+    return true;
 }
 
 template <bool KNOWN>
@@ -1137,6 +1152,692 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
     if (tid == 0) atomicMax(&g->tstamp[5], global_timer());
 }
 
+// ------------------------------------------------------------------ overlapped persistent step kernel
+// Same phases as k_step_fused, but the class-score stream no longer sits BETWEEN the depth scatter
+// and the resolve: it runs beside them on its own warps, so that the only thing left on the critical
+// path after the last score plane has arrived is the merge of the last tile's winners.
+//   warps 0..NG/32-1  geometry:  G1 depth -> unproject -> RED.MAX into the candidate plane, valid pixels
+//                                   queued per tile in shared memory -> grid barrier 1 ->
+//                                G3 per tile: candidate word + world record + depth loads of the queued
+//                                   pixels go out, THEN the tile's labels are awaited (mbarrier), winners
+//                                   merge into the world store -> grid barrier 2
+//   warps 4..7 (PRED) argmax:    running argmax over the staged planes (4 pixels per thread, LDS.128),
+//                                labels to shared memory (for G3) and to labels_out
+//   warp 8 (PRED)     producer:  one lane keeps a 5 x 16 KB ring full with cp.async.bulk (TMA 1-D)
+// GT labels (PRED = false): there is no stream; warps 0..7 are all geometry warps.
+// Then edge fix-up and raster exactly as in k_step_fused.
+#define IVM_O_THREADS 288
+#define IVM_O_TILE 512         // pixels per tile
+#define IVM_O_SP 8             // planes per ring stage (16 KB)
+#define IVM_O_NSTAGE 3         // ring depth: 48 KB per CTA; <= 64 KB per SM in flight keeps HBM saturated (measured) without
+                               // building multi-microsecond queues in front of the geometry warps' loads and atomics
+#define IVM_O_SLOTS_PRED 8     // tiles whose queue / labels a CTA holds at a time
+#define IVM_O_SLOTS_GT 16
+#define IVM_O_LOADB 8          // tiles whose depth loads are issued together
+#define IVM_O_CTAS_PER_SM 2
+#define IVM_O_TILE_CTR 40      // word of the barrier block (its second 128-byte line) that hands out raster tiles
+
+struct OvlSlot {               // one tile of a chunk
+    float T[12];
+    float cs[2];
+    int32_t b, tp0, origin_r, origin_c, reset;
+    uint32_t reset_stamp;
+    float h, hlo, hhi;         // camera height and the strict height band (mapper.py:416-424)
+    uint32_t qn;               // queued (valid) pixels of the tile
+    int32_t box[5];            // bbox + count of the cells this CTA newly occupied in the slot's env
+};
+template <int NSLOT>
+struct OvlShared {
+    OvlSlot slot[NSLOT];
+    int32_t bb[4];
+    unsigned valid;
+    int flag;
+    uint64_t full[IVM_O_NSTAGE], empty[IVM_O_NSTAGE];
+    uint64_t lab_full[NSLOT], lab_empty[NSLOT];
+    int32_t next[2];           // raster: the group's next ego tile (dynamic distribution)
+    int32_t gflag[2];
+    int32_t pend[2][32];       // raster: tiles of the group that wait for the edge fix-up
+};
+
+static inline size_t ovl_stream_bytes(bool pred) {
+    const size_t nslot = pred ? IVM_O_SLOTS_PRED : IVM_O_SLOTS_GT;
+    return (pred ? (size_t)IVM_O_NSTAGE * IVM_O_SP * IVM_O_TILE * sizeof(float) : 0) + nslot * IVM_O_TILE * (4 + 2 + (pred ? 1 : 0));
+}
+
+template <int PX>
+struct OvlDepth { float v[PX]; };
+template <int PX>
+__device__ __forceinline__ OvlDepth<PX> ovl_load_depth(const float *p) {
+    OvlDepth<PX> r;
+    if (PX == 4) {
+        const float4 q = __ldcg(reinterpret_cast<const float4 *>(p));
+        r.v[0] = q.x; r.v[1 % PX] = q.y; r.v[2 % PX] = q.z; r.v[3 % PX] = q.w;
+    } else {
+        const float2 q = __ldcg(reinterpret_cast<const float2 *>(p));
+        r.v[0] = q.x; r.v[1 % PX] = q.y;
+    }
+    return r;
+}
+
+// The PX pixels of one geometry thread in one tile: unproject, (SCATTER) offer to the candidate plane +
+// prefetch the world record + fold the frame bbox, (enqueue) append the valid ones to the tile's queue as
+// (store row << 16 | store col, pixel in tile).
+template <int PX, bool SCATTER>
+__device__ __forceinline__ void ovl_tile_pixels(const IvmParams &P, OvlSlot &sl, const OvlDepth<PX> &dd, int gt, int lane,
+                                                bool enqueue, uint32_t *qc, uint16_t *qp, int &rmin, int &rmax, int &cmin,
+                                                int &cmax, unsigned &nvalid) {
+    const int tp = gt * PX, pix0 = sl.tp0 + tp;
+    const int v = pix0 / P.W, u0 = pix0 - v * P.W;
+    const float ysv = P.ys[v];
+    bool okv[PX];
+    uint32_t cell[PX];
+#pragma unroll
+    for (int j = 0; j < PX; ++j) {
+        okv[j] = false; cell[j] = 0u;
+        IvmPoint p;
+        const int ok = ivm_unproject(dd.v[j], P.xs[u0 + j], ysv, sl.T, sl.h, P.half_res, p);
+        if (ok == 0) continue;
+        const int32_t rr = p.r - sl.origin_r, cc = p.c - sl.origin_c;
+        if (ok == 2 || rr < 0 || rr >= P.SR || cc < 0 || cc >= P.SC) {
+            if (SCATTER) atomicOr(&P.g->err, IVM_ERR_STORE_OVERFLOW);
+            continue;
+        }
+        okv[j] = true; cell[j] = ((uint32_t)rr << 16) | (uint32_t)cc;
+        if (SCATTER) {
+            const uint32_t ci = (uint32_t)rr * (uint32_t)P.SC + (uint32_t)cc;
+            if (!(P.debug & 1)) ivm_cand_insert<IvmAtomics>(P, sl.b, ci, ivm_cand_key(P, p.y, (uint32_t)(pix0 + j)));
+            // the resolve will read-modify-write this cell's world record: pull it into L2 now
+            if (!(P.debug & 2)) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.store[(size_t)sl.b * P.SR * P.SC + ci]));
+            rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
+            ++nvalid;
+        }
+    }
+    if (enqueue) {  // block-uniform
+        unsigned m[PX];
+        int n = 0;
+#pragma unroll
+        for (int j = 0; j < PX; ++j) { m[j] = __ballot_sync(0xffffffffu, okv[j]); n += __popc(m[j]); }
+        if (n) {  // warp-uniform
+            unsigned pos = 0;
+            if (lane == 0) pos = atomicAdd(&sl.qn, (unsigned)n);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+            for (int j = 0; j < PX; ++j) {
+                if (okv[j]) {
+                    const unsigned o = pos + __popc(m[j] & below);
+                    qc[o] = cell[j]; qp[o] = (uint16_t)(tp + j);
+                }
+                pos += __popc(m[j]);
+            }
+        }
+    }
+}
+
+// wait of a thread GROUP (named barrier 1, nthr threads, leader = thread 0) on the grid barrier
+__device__ __forceinline__ bool grid_wait_group(uint32_t *bar, uint32_t target, int *s_flag, int nthr) {
+    if (threadIdx.x == 0) {
+        int ok = 1;
+        uint32_t spins = 0;
+        for (;;) {
+            uint32_t v;
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+            if ((int32_t)(v - target) >= 0) break;
+            if (++spins > (1u << 22)) { ok = 0; break; }
+            __nanosleep(spins < 8 ? 32 : 128);
+        }
+        __threadfence();
+        *s_flag = ok;
+    }
+    group_bar(1, nthr);
+    return *s_flag != 0;
+}
+
+#define OVL_STAMP(k, who)                                                                              \
+    do {                                                                                               \
+        if (tid == (who) && blockIdx.x < IVM_TRACE_CTAS)                                               \
+            P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + (k)] = global_timer();                  \
+    } while (0)
+
+template <bool PRED>
+__global__ void __launch_bounds__(IVM_O_THREADS, IVM_O_CTAS_PER_SM)
+k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out,
+               int nenv_total, uint32_t bar_base, int max_rows, int raster_group_bytes) {
+    constexpr int NG1 = 256;                               // G1 (depth scatter): warps 0..7 in both modes
+    constexpr int PX1 = IVM_O_TILE / NG1;                  // pixels per thread and tile in G1
+    constexpr int NG = PRED ? 128 : 256;                   // G3 (resolve) threads: warps 0..3 beside the argmax warps, or 0..7
+    constexpr int NGW = NG / 32;
+    constexpr int PX = IVM_O_TILE / NG;                    // refill pass of G3 (more tiles than slots)
+    constexpr int NSLOT = PRED ? IVM_O_SLOTS_PRED : IVM_O_SLOTS_GT;
+    constexpr int NCW = 4;                                 // argmax warps (PRED)
+    constexpr int DRAIN = IVM_O_TILE / NG;                 // queue entries per G3 thread and tile
+    constexpr size_t RING_BYTES = PRED ? (size_t)IVM_O_NSTAGE * IVM_O_SP * IVM_O_TILE * sizeof(float) : 0;
+    extern __shared__ __align__(128) unsigned char dyn[];
+    __shared__ __align__(8) OvlShared<NSLOT> sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tpe = P.HW / IVM_O_TILE;                     // tiles per env
+    const int total = P.B * tpe;                           // < 2^31 (checked by the host)
+    // tiles are dealt round-robin: tile = CTA + j * grid (valid pixels cluster in a few image rows)
+    const int grid_n = (int)gridDim.x, cta = (int)blockIdx.x;
+    const int my_tiles = (total - cta + grid_n - 1) / grid_n;
+    const bool keep_queue = my_tiles <= NSLOT;             // the queue built by G1 is still there in G3
+    uint32_t *qcell = reinterpret_cast<uint32_t *>(dyn + RING_BYTES);
+    uint16_t *qpix = reinterpret_cast<uint16_t *>(dyn + RING_BYTES + (size_t)NSLOT * IVM_O_TILE * 4);
+    uint8_t *slab = dyn + RING_BYTES + (size_t)NSLOT * IVM_O_TILE * 6;
+    IvmGlobal *g = P.g;
+    const bool geo = warp < NGW;
+    const int nstage = ((P.debug >> 8) & 15) ? min((P.debug >> 8) & 15, IVM_O_NSTAGE) : IVM_O_NSTAGE;  // experiment: shallower ring
+
+    // the first batch of depth loads goes out before anything else (ahead of the score stream's first 80 KB)
+    OvlDepth<PX1> dv[IVM_O_LOADB];
+    if (tid < NG1) {
+#pragma unroll
+        for (int k = 0; k < IVM_O_LOADB; ++k) {
+#pragma unroll
+            for (int j = 0; j < PX1; ++j) dv[k].v[j] = 2.0f;
+            if (k < my_tiles) dv[k] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + k * grid_n) * IVM_O_TILE + tid * PX1);
+        }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        g->tstamp[0] = global_timer(); g->tstamp[5] = 0ull;
+        P.bar[IVM_O_TILE_CTR] = 2u * (gridDim.x - (gridDim.x > 1 ? 1u : 0u));  // raster tiles handed out statically
+    }
+    OVL_STAMP(7, 0);
+    if (tid == 0) {
+        if (PRED) {
+            for (int s = 0; s < IVM_O_NSTAGE; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], NCW); }
+            for (int s = 0; s < NSLOT; ++s) { mbar_init(&sh.lab_full[s], NCW); mbar_init(&sh.lab_empty[s], NGW); }
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        sh.bb[0] = INT32_MAX; sh.bb[1] = INT32_MIN; sh.bb[2] = INT32_MAX; sh.bb[3] = INT32_MIN; sh.valid = 0;
+    }
+    // paused envs (mapper.py:315-318) are wiped by the last CTA
+    if (blockIdx.x == gridDim.x - 1)
+        for (int b = P.B; b < nenv_total; ++b) {
+            IvmEnvPrep q; q.reset = 1; q.origin_r = 0; q.origin_c = 0;
+            ivm_env_publish<IvmAtomics>(P, b, q, tid, blockDim.x);
+        }
+    __syncthreads();
+
+    if (tid < NG1) {
+        // ============================================================ G1: depth scatter (warps 0..7)
+        int rmin = INT32_MAX, rmax = INT32_MIN, cmin = INT32_MAX, cmax = INT32_MIN;
+        unsigned nvalid = 0;
+        for (int c0 = 0; c0 < my_tiles; c0 += NSLOT) {
+            const int cn = min(NSLOT, my_tiles - c0);
+            if (c0) {
+                group_bar(1, NG1);  // the previous chunk's slots are no longer read
+#pragma unroll
+                for (int k = 0; k < IVM_O_LOADB; ++k)
+                    if (k < cn) dv[k] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + (c0 + k) * grid_n) * IVM_O_TILE + tid * PX1);
+            }
+            {   // slot prep, 4 slots per warp at a time (8 lanes each): env decision (reset / store origin,
+                // mapper.py:310-326) by lane 0 of the octet, pose matrices by lane 1; every load of a lane is
+                // issued before the first one is used
+                const int role = lane & 7, k = warp + (lane >> 3) * (NG1 / 32);
+                if (k < cn) {
+                    OvlSlot &sl = sh.slot[k];
+                    const int tile = cta + (c0 + k) * grid_n;
+                    const int b = tile / tpe;
+                    if (role == 0) {
+                        const IvmEnv *e = &P.env[b];
+                        const uint32_t m = P.masks[b];
+                        const int32_t cnt = e->count, eor = e->origin_r, eoc = e->origin_c;
+                        const uint32_t ers = e->reset_stamp;
+                        const float px = P.pose[3 * b + 0], h = P.pose[3 * b + 1], pz = P.pose[3 * b + 2];
+                        const IvmEnvPrep q = ivm_env_decide_vals(P, m, cnt, eor, eoc, px, pz);
+                        sl.b = b; sl.tp0 = (tile - b * tpe) * IVM_O_TILE;
+                        sl.origin_r = q.origin_r; sl.origin_c = q.origin_c; sl.reset = q.reset;
+                        sl.reset_stamp = q.reset ? P.step : ers;
+                        sl.h = h; sl.hlo = ivm_sub(h, 1.0f); sl.hhi = ivm_add(h, 0.5f);
+                        sl.qn = 0u;
+                        sl.box[0] = INT32_MAX; sl.box[1] = INT32_MIN; sl.box[2] = INT32_MAX; sl.box[3] = INT32_MIN; sl.box[4] = 0;
+                    } else if (role == 1) {
+                        if (P.orient != nullptr) ivm_pose_matrices(P, b, sl.T, sl.cs);
+                        else
+                            for (int i = 0; i < 12; ++i) sl.T[i] = P.T12[12 * b + i];
+                    }
+                }
+            }
+            group_bar(1, NG1);
+            if (c0 == 0) OVL_STAMP(1, 0);
+            // the CTA that owns an env's first tile publishes the env's new state (read after barrier 1 only)
+            for (int k = 0; k < cn; ++k) {
+                const OvlSlot &sl = sh.slot[k];
+                if (sl.tp0 != 0) continue;  // uniform
+                IvmEnvPrep q;
+                q.reset = sl.reset; q.origin_r = sl.origin_r; q.origin_c = sl.origin_c;
+                ivm_env_publish<IvmAtomics>(P, sl.b, q, tid, NG1);
+                if (P.orient != nullptr) {
+                    if (tid < 12) P.T12_buf[12 * sl.b + tid] = sl.T[tid];
+                    if (tid < 2) P.cs_buf[2 * sl.b + tid] = sl.cs[tid];
+                }
+            }
+            for (int s0 = 0; s0 < cn; s0 += IVM_O_LOADB) {
+                if (s0) {
+#pragma unroll
+                    for (int k = 0; k < IVM_O_LOADB; ++k)
+                        if (s0 + k < cn) dv[k] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + (c0 + s0 + k) * grid_n) * IVM_O_TILE + tid * PX1);
+                }
+                // pass A: every pixel of the batch -- world point, filters, half-cell; the candidate word and the
+                // world record of the valid ones are PREFETCHED into L2, and the pixel is queued for G3
+                float yk[IVM_O_LOADB][PX1];
+                uint32_t cik[IVM_O_LOADB][PX1];     // cell index in the env's store window, ~0 = nothing to offer
+#pragma unroll
+                for (int k = 0; k < IVM_O_LOADB; ++k) {
+#pragma unroll
+                    for (int j = 0; j < PX1; ++j) { yk[k][j] = 0.f; cik[k][j] = 0xFFFFFFFFu; }
+                    if (s0 + k >= cn) continue;  // uniform
+                    OvlSlot &sl = sh.slot[s0 + k];
+                    const int tp = tid * PX1, pix0 = sl.tp0 + tp;
+                    const int v = pix0 / P.W, u0 = pix0 - v * P.W;
+                    const float ysv = P.ys[v];
+                    float x[PX1], z[PX1];
+                    bool ok[PX1];
+                    bool any = false;
+#pragma unroll
+                    for (int j = 0; j < PX1; ++j) {
+                        const float d = dv[k].v[j];
+                        ivm_world_xyz(d, P.xs[u0 + j], ysv, sl.T, x[j], yk[k][j], z[j]);
+                        ok[j] = d > 0.01f && d < 0.99f && yk[k][j] > sl.hlo && yk[k][j] < sl.hhi;
+                        any = any || ok[j];
+                    }
+                    uint32_t cell[PX1];
+#pragma unroll
+                    for (int j = 0; j < PX1; ++j) cell[j] = 0u;
+                    if (__any_sync(0xffffffffu, any)) {
+                        const size_t ebase = (size_t)sl.b * P.SR * P.SC;
+#pragma unroll
+                        for (int j = 0; j < PX1; ++j) {
+                            const float rf = rintf(ivm_div(z[j], P.half_res));
+                            const float cf = rintf(ivm_div(x[j], P.half_res));
+                            const bool rep = fabsf(rf) < 1.0e9f && fabsf(cf) < 1.0e9f;
+                            const int32_t r = rep ? (int32_t)rf : 0, c = rep ? (int32_t)cf : 0;
+                            const int32_t rr = r - sl.origin_r, cc = c - sl.origin_c;
+                            const bool inside = rep && rr >= 0 && rr < P.SR && cc >= 0 && cc < P.SC;
+                            if (ok[j] && !inside) { atomicOr(&g->err, IVM_ERR_STORE_OVERFLOW); ok[j] = false; }
+                            if (ok[j]) {
+                                const uint32_t ci = (uint32_t)rr * (uint32_t)P.SC + (uint32_t)cc;
+                                cik[k][j] = ci; cell[j] = ((uint32_t)rr << 16) | (uint32_t)cc;
+                                if (P.debug & 8) {
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.cplane[ebase + ci]));
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.store[ebase + ci]));
+                                } else {
+                                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(&P.cplane[ebase + ci]));
+                                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(&P.store[ebase + ci]));
+                                }
+                                rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
+                                ++nvalid;
+                            }
+                        }
+                        if (keep_queue) {
+                            unsigned m[PX1];
+                            int n = 0;
+#pragma unroll
+                            for (int j = 0; j < PX1; ++j) { m[j] = __ballot_sync(0xffffffffu, ok[j]); n += __popc(m[j]); }
+                            if (n) {  // warp-uniform
+                                unsigned pos = 0;
+                                if (lane == 0) pos = atomicAdd(&sl.qn, (unsigned)n);
+                                pos = __shfl_sync(0xffffffffu, pos, 0);
+                                const unsigned below = (1u << lane) - 1u;
+                                uint32_t *qc = qcell + (s0 + k) * IVM_O_TILE;
+                                uint16_t *qp = qpix + (s0 + k) * IVM_O_TILE;
+#pragma unroll
+                                for (int j = 0; j < PX1; ++j) {
+                                    if (ok[j]) {
+                                        const unsigned o = pos + __popc(m[j] & below);
+                                        qc[o] = cell[j]; qp[o] = (uint16_t)(tp + j);
+                                    }
+                                    pos += __popc(m[j]);
+                                }
+                            }
+                        }
+                    }
+                }
+                // pass B: ONE 64-bit RED.MAX per valid pixel into the candidate plane (its line is in L2 or on its way)
+#pragma unroll
+                for (int k = 0; k < IVM_O_LOADB; ++k) {
+                    if (s0 + k >= cn) continue;  // uniform
+                    const OvlSlot &sl = sh.slot[s0 + k];
+                    const int pix0 = sl.tp0 + tid * PX1;
+#pragma unroll
+                    for (int j = 0; j < PX1; ++j)
+                        if (cik[k][j] != 0xFFFFFFFFu) {
+                            unsigned long long *w = &P.cplane[(size_t)sl.b * P.SR * P.SC + cik[k][j]];
+                            const unsigned long long key = ivm_cand_key(P, yk[k][j], (uint32_t)(pix0 + j));
+                            if (P.debug & 8) atomicMax(w, key);
+                            else asm volatile("red.relaxed.gpu.global.max.u64.L2::cache_hint [%0], %1, %2;" ::"l"(w), "l"(key), "l"(ivm_policy_keep()) : "memory");
+                        }
+                }
+            }
+        }
+        OVL_STAMP(2, 0);
+        // frame bbox over ALL envs (mapper.py:465), one flush per CTA
+        const unsigned wv = warp_sum(nvalid);
+        if (wv) {
+            rmin = warp_min(rmin); rmax = warp_max(rmax); cmin = warp_min(cmin); cmax = warp_max(cmax);
+            if (lane == 0) {
+                atomicMin(&sh.bb[0], rmin); atomicMax(&sh.bb[1], rmax); atomicMin(&sh.bb[2], cmin); atomicMax(&sh.bb[3], cmax);
+                atomicAdd(&sh.valid, wv);
+            }
+        }
+        // every G1 thread's REDs, queue entries and the env publication are issued; the argmax warps only arrive
+        // (bar.arrive orders their earlier writes like bar.sync does) and go straight to the score stream
+        if (PRED && warp >= NGW) asm volatile("bar.arrive 1, %0;" ::"r"(NG1) : "memory");
+        else group_bar(1, NG1);
+        if (tid == 0) {
+            if (sh.valid) {
+                atomicMin(&g->loc[0], sh.bb[0]); atomicMax(&g->loc[1], sh.bb[1]);
+                atomicMin(&g->loc[2], sh.bb[2]); atomicMax(&g->loc[3], sh.bb[3]);
+                atomicAdd(&g->acc_valid, (unsigned long long)sh.valid);
+            }
+            grid_arrive(P.bar);  // barrier 1
+        }
+    }
+    if (geo) {
+        OVL_STAMP(10, 0);
+        if (!grid_wait_group(P.bar, bar_base + 1u * gridDim.x, &sh.flag, NG) && tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER);
+        if (blockIdx.x == 0 && tid == 0) g->tstamp[1] = global_timer();
+        OVL_STAMP(0, 0);
+
+        // ============================================================ G3: resolve
+        const int32_t loc[4] = {__ldcg(&g->loc[0]), __ldcg(&g->loc[1]), __ldcg(&g->loc[2]), __ldcg(&g->loc[3])};
+        unsigned nlocal = 0;
+        int chunk = 0;
+        for (int c0 = 0; c0 < my_tiles; c0 += NSLOT, ++chunk) {
+            const int cn = min(NSLOT, my_tiles - c0);
+            if (!keep_queue) {
+                // more tiles than slots: rebuild this chunk's slots (from the published env state) and queues
+                group_bar(1, NG);
+                {
+                    const int role = lane & 7, k = warp + (lane >> 3) * NGW;
+                    if (k < cn) {
+                        OvlSlot &sl = sh.slot[k];
+                        const int tile = cta + (c0 + k) * grid_n;
+                        const int b = tile / tpe;
+                        const IvmEnv *e = &P.env[b];
+                        if (role == 0) {
+                            sl.b = b; sl.tp0 = (tile - b * tpe) * IVM_O_TILE;
+                            sl.origin_r = __ldcg(&e->origin_r); sl.origin_c = __ldcg(&e->origin_c);
+                            sl.reset_stamp = __ldcg(&e->reset_stamp);
+                            sl.h = P.pose[3 * b + 1];
+                            sl.qn = 0u;
+                            sl.box[0] = INT32_MAX; sl.box[1] = INT32_MIN; sl.box[2] = INT32_MAX; sl.box[3] = INT32_MIN; sl.box[4] = 0;
+                        } else if (role == 1) {
+                            for (int i = 0; i < 12; ++i) sl.T[i] = __ldcg(&P.T12[12 * b + i]);
+                        }
+                    }
+                }
+                group_bar(1, NG);
+                int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
+                unsigned nv = 0;
+                for (int s0 = 0; s0 < cn; s0 += IVM_O_LOADB) {
+                    OvlDepth<PX> dr[IVM_O_LOADB];
+#pragma unroll
+                    for (int k = 0; k < IVM_O_LOADB; ++k) {
+#pragma unroll
+                        for (int j = 0; j < PX; ++j) dr[k].v[j] = 2.0f;
+                        if (s0 + k < cn) dr[k] = ovl_load_depth<PX>(P.depth + (size_t)(cta + (c0 + s0 + k) * grid_n) * IVM_O_TILE + tid * PX);
+                    }
+#pragma unroll
+                    for (int k = 0; k < IVM_O_LOADB; ++k) {
+                        if (s0 + k >= cn) continue;
+                        ovl_tile_pixels<PX, false>(P, sh.slot[s0 + k], dr[k], tid, lane, true, qcell + (s0 + k) * IVM_O_TILE,
+                                                   qpix + (s0 + k) * IVM_O_TILE, r0, r1, r2, r3, nv);
+                    }
+                }
+                group_bar(1, NG);
+            }
+            for (int k = 0; k < cn; ++k) {
+                OvlSlot &sl = sh.slot[k];
+                const int n = (int)sl.qn;  // <= IVM_O_TILE = DRAIN * NG: one pass
+                const size_t ebase = (size_t)sl.b * P.SR * P.SC;
+                const size_t pbase = (size_t)sl.b * P.HW + sl.tp0;
+                bool act[DRAIN];
+                uint32_t ce[DRAIN], px[DRAIN], ci[DRAIN];
+                float d[DRAIN];
+                unsigned long long cw[DRAIN];
+                IvmRecord old[DRAIN];
+                uint32_t lab[DRAIN];
+                // all loads of the tile's queue entries first: pixel depth, candidate word, world record (speculative)
+#pragma unroll
+                for (int u = 0; u < DRAIN; ++u) {
+                    const int i = tid + u * NG;
+                    act[u] = i < n;
+                    ce[u] = 0u; px[u] = 0u; ci[u] = 0u; d[u] = 2.0f; cw[u] = 0ull; lab[u] = 0u;
+                    old[u].x = old[u].y = old[u].z = 0.f; old[u].meta = 0u;
+                    if (act[u]) {
+                        ce[u] = qcell[k * IVM_O_TILE + i]; px[u] = qpix[k * IVM_O_TILE + i];
+                        ci[u] = (ce[u] >> 16) * (uint32_t)P.SC + (ce[u] & 0xFFFFu);
+                        d[u] = __ldcg(P.depth + pbase + px[u]);
+                        cw[u] = ivm_load_ull(&P.cplane[ebase + ci[u]]);
+                        old[u] = ivm_load_record(&P.store[ebase + ci[u]]);
+                        if (!PRED) lab[u] = __ldcg(P.labels + pbase + px[u]);
+                    }
+                }
+                if (PRED) mbar_wait(&sh.lab_full[k], (uint32_t)(chunk & 1));  // the tile's labels are in shared memory
+#pragma unroll
+                for (int u = 0; u < DRAIN; ++u) {
+                    if (!act[u]) continue;
+                    const uint32_t pix = (uint32_t)sl.tp0 + px[u];
+                    const int v = (int)pix / P.W, uu = (int)pix - v * P.W;
+                    IvmPoint pt;
+                    ivm_world_xyz(d[u], P.xs[uu], P.ys[v], sl.T, pt.x, pt.y, pt.z);
+                    if (cw[u] != ivm_cand_key(P, pt.y, pix)) continue;  // another pixel owns the cell
+                    pt.r = sl.origin_r + (int32_t)(ce[u] >> 16); pt.c = sl.origin_c + (int32_t)(ce[u] & 0xFFFFu);
+                    const uint32_t label = PRED ? (uint32_t)slab[k * IVM_O_TILE + px[u]] : lab[u];
+                    if (ivm_on_frame_edge(pt, loc)) {
+                        ivm_push_edge1<IvmAtomics>(P, sl.b, pix, pt, label, ebase + ci[u]);
+                        // the fix-up decides this cell later: the ego tiles of the pending point and of the record it
+                        // may replace are rastered after the fix-up
+                        const float epx = P.pose[3 * sl.b + 0], epz = P.pose[3 * sl.b + 2];
+                        const float ec = __ldcg(&P.cs[2 * sl.b + 0]), es = __ldcg(&P.cs[2 * sl.b + 1]);
+                        ivm_mark_tile(P, sl.b, pt.x, pt.y, pt.z, epx, sl.h, epz, ec, es);
+                        if (ivm_live(old[u].meta, sl.reset_stamp)) ivm_mark_tile(P, sl.b, old[u].x, old[u].y, old[u].z, epx, sl.h, epz, ec, es);
+                        continue;
+                    }
+                    IvmBoxAcc acc;
+                    acc.clear();
+                    ivm_merge_record<IvmAtomics>(P, sl.b, ebase + ci[u], pt.r, pt.c, pt.x, pt.y, pt.z, label, old[u], sl.reset_stamp,
+                                                 sl.origin_r, sl.origin_c, acc);
+                    ++nlocal;
+                    if (acc.n) {  // a newly occupied cell: fold into the slot's box
+                        atomicMin(&sl.box[0], acc.rmin); atomicMax(&sl.box[1], acc.rmax);
+                        atomicMin(&sl.box[2], acc.cmin); atomicMax(&sl.box[3], acc.cmax);
+                        atomicAdd(&sl.box[4], 1);
+                    }
+                }
+                if (PRED) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sh.lab_empty[k]);  // this warp no longer reads the slot's labels
+                }
+            }
+            group_bar(1, NG);
+            if (tid < cn && sh.slot[tid].box[4] > 0) {
+                IvmBoxAcc t;
+                const OvlSlot &sl = sh.slot[tid];
+                t.rmin = sl.box[0]; t.rmax = sl.box[1]; t.cmin = sl.box[2]; t.cmax = sl.box[3]; t.n = sl.box[4];
+                ivm_box_flush<IvmAtomics>(&P.env[sl.b], t);
+            }
+        }
+        const unsigned wl = warp_sum(nlocal);
+        if (wl && lane == 0) atomicAdd(&g->acc_local, (unsigned long long)wl);
+        OVL_STAMP(3, 0);
+        group_bar(1, NG);
+        if (tid == 0) grid_arrive(P.bar);  // barrier 2
+    } else if (PRED && warp < NGW + NCW) {
+        // ============================================================ argmax warps: PredictSemantics tail
+        // (mapper.py:795-798): running argmax over the planes, first max wins, NaN counts as maximal (torch.argmax)
+        float(*ring)[IVM_O_SP][IVM_O_TILE] = reinterpret_cast<float(*)[IVM_O_SP][IVM_O_TILE]>(dyn);
+        const int ct = tid - NG;  // 0..127, 4 pixels each
+        int slot = 0;
+        uint32_t round = 0;
+        for (int j = 0; j < my_tiles; ++j) {
+            const int tile = cta + j * grid_n;
+            const int ls = j % NSLOT, chunk = j / NSLOT;
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+            int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+            for (int p0 = 0; p0 < ncls; p0 += IVM_O_SP) {
+                mbar_wait(&sh.full[slot], round & 1u);
+                const int np = min(IVM_O_SP, ncls - p0);
+                if (np == IVM_O_SP) {
+                    float4 v[IVM_O_SP];
+#pragma unroll
+                    for (int p = 0; p < IVM_O_SP; ++p) v[p] = *reinterpret_cast<const float4 *>(&ring[slot][p][ct * 4]);
+#pragma unroll
+                    for (int p = 0; p < IVM_O_SP; ++p) {
+                        if (p0 + p == 0) { b0 = v[p].x; b1 = v[p].y; b2 = v[p].z; b3 = v[p].w; }
+                        else {
+                            IVM_ARGMAX_STEP(v[p].x, p0 + p, b0, a0); IVM_ARGMAX_STEP(v[p].y, p0 + p, b1, a1);
+                            IVM_ARGMAX_STEP(v[p].z, p0 + p, b2, a2); IVM_ARGMAX_STEP(v[p].w, p0 + p, b3, a3);
+                        }
+                    }
+                } else {
+                    for (int p = 0; p < np; ++p) {
+                        const float4 v = *reinterpret_cast<const float4 *>(&ring[slot][p][ct * 4]);
+                        if (p0 + p == 0) { b0 = v.x; b1 = v.y; b2 = v.z; b3 = v.w; }
+                        else {
+                            IVM_ARGMAX_STEP(v.x, p0 + p, b0, a0); IVM_ARGMAX_STEP(v.y, p0 + p, b1, a1);
+                            IVM_ARGMAX_STEP(v.z, p0 + p, b2, a2); IVM_ARGMAX_STEP(v.w, p0 + p, b3, a3);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.empty[slot]);  // this warp is done with the stage
+                if (++slot == nstage) { slot = 0; ++round; }
+            }
+            if (chunk > 0) mbar_wait(&sh.lab_empty[ls], (uint32_t)((chunk - 1) & 1));  // G3 is done with the slot's previous labels
+            uchar4 o;
+            o.x = (uint8_t)a0; o.y = (uint8_t)a1; o.z = (uint8_t)a2; o.w = (uint8_t)a3;
+            *reinterpret_cast<uchar4 *>(slab + ls * IVM_O_TILE + ct * 4) = o;
+            *reinterpret_cast<uchar4 *>(labels_out + (size_t)tile * IVM_O_TILE + ct * 4) = o;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh.lab_full[ls]);
+        }
+        OVL_STAMP(6, NG);
+    } else if (PRED && warp == NGW + NCW) {
+        // ============================================================ producer warp: one lane keeps the ring full
+        if (lane == 0) {
+            float(*ring)[IVM_O_SP][IVM_O_TILE] = reinterpret_cast<float(*)[IVM_O_SP][IVM_O_TILE]>(dyn);
+            uint64_t policy;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+            int slot = 0;
+            uint32_t round = 0;  // how many times the ring has wrapped
+            for (int tile = cta; tile < total; tile += grid_n) {
+                const int eb = tile / tpe, tp0 = (tile - eb * tpe) * IVM_O_TILE;
+                const float *src = logits + (size_t)eb * ncls * P.HW + tp0;
+                for (int p0 = 0; p0 < ncls; p0 += IVM_O_SP) {
+                    const int np = min(IVM_O_SP, ncls - p0);
+                    if (round > 0) mbar_wait(&sh.empty[slot], (round - 1) & 1u);
+                    mbar_expect_tx(&sh.full[slot], (uint32_t)(np * IVM_O_TILE * sizeof(float)));
+                    for (int p = 0; p < np; ++p)
+                        bulk_g2s(&ring[slot][p][0], src + (size_t)(p0 + p) * P.HW, IVM_O_TILE * sizeof(float), &sh.full[slot],
+                                 policy);
+                    if (++slot == nstage) { slot = 0; ++round; }
+                }
+            }
+        }
+    }
+    __syncthreads();  // ring and queues are drained: their memory becomes fix-up scratch / raster tiles
+    if (!grid_wait(P.bar, bar_base + 2u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
+    if (blockIdx.x == 0 && tid == 0) g->tstamp[2] = global_timer();
+    OVL_STAMP(5, 0);
+
+    // ================================================================ edge fix-up beside the raster
+    // CTA 0 runs the whole fix-up program (stage-1 classes + merges, edge-line scan, stage-2 classes) on its
+    // own -- no grid barrier inside -- while every other CTA already rasters the ego tiles the fix-up cannot
+    // touch; then CTA 0 releases everybody with ONE add worth the three remaining arrivals, and the few
+    // tiles that had to wait are rastered by the groups that hold them.  Tiles are handed out dynamically
+    // (one static tile per group, then an atomic counter): their cost varies with the records under them.
+    const int first = grid_n > 1 ? 1 : 0;                 // CTAs [first, grid) start rastering at once
+    const int tiles_x = (P.C + P.tile_c - 1) / P.tile_c, tiles_y = (P.R + P.tile_r - 1) / P.tile_r;
+    const int per_env = tiles_x * tiles_y, units = P.B * per_env;
+    const int group = tid / IVM_F_GROUP, gtid = tid - group * IVM_F_GROUP;
+    uint32_t *gsm = reinterpret_cast<uint32_t *>(dyn + (size_t)group * raster_group_bytes);
+    const uint32_t release_target = bar_base + 5u * gridDim.x;
+    if (cta == 0) {
+        IvmFixScratch S;
+        S.key = reinterpret_cast<unsigned long long *>(dyn);
+        S.xo = S.key + IVM_FIX_SMALL;
+        S.ord = reinterpret_cast<uint32_t *>(S.xo + IVM_FIX_SMALL);
+        S.cap = IVM_FIX_SMALL;
+        S.ibuf = reinterpret_cast<int32_t *>(S.ord + IVM_FIX_SMALL);
+        S.lbuf = reinterpret_cast<unsigned long long *>(S.ibuf + 8);
+        ivm_fixup_program<IvmAtomics>(P, S, tid, blockDim.x);
+        __syncthreads();
+        if (tid == 0) {
+            g->tstamp[3] = global_timer();
+            __threadfence();
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(P.bar), "r"(3u * gridDim.x) : "memory");
+            g->tstamp[4] = global_timer();
+        }
+        __syncthreads();
+    }
+    if (warp < 2 * IVM_F_GROUP / 32) {
+        // group-level wait for the release (leader polls, named barrier of the group)
+        auto wait_release = [&]() {
+            if (gtid == 0) {
+                int ok = 1;
+                uint32_t spins = 0;
+                for (;;) {
+                    uint32_t v;
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(P.bar) : "memory");
+                    if ((int32_t)(v - release_target) >= 0) break;
+                    if (++spins > (1u << 22)) { ok = 0; break; }
+                    __nanosleep(spins < 8 ? 32 : 128);
+                }
+                __threadfence();
+                if (!ok) atomicOr(&g->err, IVM_ERR_GRID_BARRIER);
+            }
+            group_bar(2 + group, IVM_F_GROUP);
+        };
+        unsigned n_in = 0;
+        bool released = cta == 0;                         // CTA 0 has just run the fix-up itself
+        int npend = 0;
+        int u = (cta - first) * 2 + group;
+        if (cta == 0 && first == 1) {                     // CTA 0 joins late: no static tile
+            if (gtid == 0) sh.next[group] = (int32_t)atomicAdd(&P.bar[IVM_O_TILE_CTR], 1u);
+            group_bar(2 + group, IVM_F_GROUP);
+            u = sh.next[group];
+        }
+        while (u < units) {
+            int32_t unext = 0;
+            if (gtid == 0) unext = (int32_t)atomicAdd(&P.bar[IVM_O_TILE_CTR], 1u);  // consumed after this tile
+            const int b = u / per_env, w = u - b * per_env;
+            const int ty = w / tiles_x, tx = w - ty * tiles_x;
+            if (released) {
+                raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in);
+            } else if (!raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in, true)) {
+                if (npend < 32) {
+                    if (gtid == 0) sh.pend[group][npend] = u;
+                    ++npend;
+                } else {                                  // no room to remember it: wait here
+                    wait_release();
+                    released = true;
+                    raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in);
+                }
+            }
+            if (gtid == 0) sh.next[group] = unext;
+            group_bar(2 + group, IVM_F_GROUP);
+            u = sh.next[group];
+        }
+        if (tid == 0) OVL_STAMP(11, 0);
+        if (!released && npend > 0) wait_release();  // nothing pending: this group is done, whatever the fix-up still does
+        if (tid == 0) OVL_STAMP(8, 0);
+        for (int i = 0; i < npend; ++i) {
+            const int up = sh.pend[group][i];
+            const int b = up / per_env, w = up - b * per_env;
+            const int ty = w / tiles_x, tx = w - ty * tiles_x;
+            raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in);
+        }
+        const unsigned wn = warp_sum(n_in);
+        if (wn && lane == 0) atomicAdd(&g->stats[IVM_STAT_IN], (unsigned long long)wn);
+    }
+    __syncthreads();
+    OVL_STAMP(9, 0);
+    if (tid == 0) atomicMax(&g->tstamp[5], global_timer());
+}
+
 // ------------------------------------------------------------------ known-map store build
 __global__ void k_known_reset_env(IvmParams P, int b, long long n, int origin_r, int origin_c) {
     IvmEnv *e = &P.env[b];
@@ -1306,6 +2007,8 @@ struct ivm_ctx {
     int coop;             // device supports cooperative launches
     int fused_grid[2];    // co-resident CTAs of k_step_fused<false/true> (0 = not queried yet)
     size_t fused_smem[2];
+    int ovl_grid[2];      // same for k_step_overlap<false/true>
+    size_t ovl_smem[2];
     uint32_t bar_base;    // value of IvmGlobal.bar_count before the next fused launch
     int64_t launches;
     // known-mode scratch
@@ -1341,6 +2044,14 @@ static uint32_t edge_capacity(const ivm_config *c) {
 }
 static uint32_t hash_size(uint32_t ecap) { uint32_t h = 1024; while (h < 2 * ecap) h <<= 1; return h; }
 
+static void tile_dims(const ivm_config *c, int *tr_out, int *tc_out) {
+    int tr = c->tile_rows, tc = c->tile_cols;
+    if (tr <= 0 || tc <= 0) { tr = 16; tc = 16; }
+    if (tr > c->map_rows) tr = c->map_rows;
+    if (tc > c->map_cols) tc = c->map_cols;
+    *tr_out = tr; *tc_out = tc;
+}
+
 static void carve(const ivm_config *c, void *ws, IvmParams *P, ivm_ctx *ctx, size_t *total) {
     Carver cv{(char *)ws, 0};
     const size_t B = c->max_envs, SR = c->store_rows, SC = c->store_cols;
@@ -1359,6 +2070,11 @@ static void carve(const ivm_config *c, void *ws, IvmParams *P, ivm_ctx *ctx, siz
     q.rowcount = cv.take<int32_t>(B * SR);
     q.colcount = cv.take<int32_t>(B * SC);
     q.segs = cv.take<int32_t>(16 * B);
+    {
+        int tr = c->tile_rows, tc = c->tile_cols;
+        tile_dims(c, &tr, &tc);
+        q.tile_dirty = cv.take<uint32_t>(B * (size_t)((c->map_rows + tr - 1) / tr) * (size_t)((c->map_cols + tc - 1) / tc));
+    }
     q.e1 = cv.take<IvmEdge>(ecap);
     q.e2 = cv.take<IvmEdge>(ecap);
     q.ecap = ecap;
@@ -1422,10 +2138,8 @@ int ivm_create(const ivm_config *cfg, void *workspace_dev, size_t workspace_byte
     P.R = cfg->map_rows; P.C = cfg->map_cols;
     P.res = cfg->res; P.half_res = cfg->half_res; P.half_h = cfg->half_h; P.half_w = cfg->half_w;
     P.SR = cfg->store_rows; P.SC = cfg->store_cols; P.maxB = cfg->max_envs;
-    int tr = cfg->tile_rows, tc = cfg->tile_cols;
-    if (tr <= 0 || tc <= 0) { tr = 16; tc = 16; }
-    if (tr > P.R) tr = P.R;
-    if (tc > P.C) tc = P.C;
+    int tr = 0, tc = 0;
+    tile_dims(cfg, &tr, &tc);
     P.tile_r = tr; P.tile_c = tc;
     P.debug = cfg->reserved[1];
     ctx->first_call = 1;
@@ -1542,7 +2256,7 @@ static int raster_max_rows(const IvmParams &P) {
 
 // The fused persistent kernel applies when the image tiles evenly and the inputs are aligned.
 static bool fused_applies(const ivm_ctx *ctx, const IvmParams &P, const float *depth, const uint8_t *labels, const float *logits) {
-    if (!ctx->coop || ctx->cfg.reserved[0] != 0) return false;
+    if (!ctx->coop || (ctx->cfg.reserved[0] != 0 && ctx->cfg.reserved[0] != 3)) return false;
     if (P.HW % IVM_F_TILE != 0 || (P.W & 1) || P.HW > (1 << 24)) return false;
     if (((uintptr_t)depth & 7) || ((uintptr_t)labels & 1) || (logits && ((uintptr_t)logits & 15))) return false;
     const size_t rb = 2 * raster_smem_bytes(P.tile_r, P.tile_c, raster_max_rows(P));
@@ -1586,6 +2300,51 @@ static int launch_fused(ivm_ctx *ctx, IvmParams &P, const float *logits, int ncl
     return IVM_OK;
 }
 
+// The overlapped kernel additionally needs 4-pixel groups inside one image row, 16-byte aligned depth and
+// store coordinates that fit 16 bits each.
+static bool overlap_applies(const ivm_ctx *ctx, const IvmParams &P, const float *depth, const uint8_t *labels, const float *logits,
+                            const uint8_t *labels_out) {
+    if (!fused_applies(ctx, P, depth, labels, logits)) return false;
+    if ((P.W & 3) || ((uintptr_t)depth & 15) || P.SR > 65535 || P.SC > 65535) return false;
+    if ((long long)P.B * (P.HW / IVM_O_TILE) > (1ll << 30)) return false;
+    if (logits && ((uintptr_t)labels_out & 3)) return false;
+    return true;
+}
+
+static int launch_overlap(ivm_ctx *ctx, IvmParams &P, const float *logits, int ncls, uint8_t *labels_out, int nenv_total,
+                          cudaStream_t st) {
+    const int pred = logits ? 1 : 0;
+    int max_rows = raster_max_rows(P);
+    int group_bytes = (int)raster_smem_bytes(P.tile_r, P.tile_c, max_rows);
+    size_t smem = (size_t)2 * group_bytes;
+    const size_t scratch = (size_t)IVM_FIX_SMALL * 20 + 1024;  // fix-up scratch
+    if (smem < scratch) smem = scratch;
+    if (smem < ovl_stream_bytes(pred != 0)) smem = ovl_stream_bytes(pred != 0);
+    const void *fn = pred ? (const void *)k_step_overlap<true> : (const void *)k_step_overlap<false>;
+    if (!ctx->ovl_grid[pred] || ctx->ovl_smem[pred] != smem) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(k_step_overlap)");
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, IVM_O_THREADS, smem);
+        if (e != cudaSuccess) return cuda_fail(ctx, e, "occupancy(k_step_overlap)");
+        if (per_sm < 1) { snprintf(ctx->err, sizeof(ctx->err), "k_step_overlap does not fit on an SM"); return IVM_E_CUDA; }
+        if (per_sm > IVM_O_CTAS_PER_SM) per_sm = IVM_O_CTAS_PER_SM;
+        ctx->ovl_grid[pred] = per_sm * ctx->num_sms;
+        ctx->ovl_smem[pred] = smem;
+    }
+    long long tiles = (long long)P.B * (P.HW / IVM_O_TILE);
+    int grid = ctx->ovl_grid[pred];
+    if (grid > tiles) grid = (int)tiles;
+    uint32_t bar_base = ctx->bar_base;
+    void *args[] = {(void *)&P, (void *)&logits, (void *)&ncls, (void *)&labels_out, (void *)&nenv_total,
+                    (void *)&bar_base, (void *)&max_rows, (void *)&group_bytes};
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(IVM_O_THREADS), args, smem, st);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaLaunchCooperativeKernel(k_step_overlap)");
+    ctx->bar_base += 5u * (uint32_t)grid;
+    ctx->launches += 1;
+    return IVM_OK;
+}
+
 int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const uint8_t *labels, const float *logits,
                        int32_t num_classes, uint8_t *labels_out, const float *T12, const float *pose, const float *cs,
                        const void *orientation, int32_t orientation_is_f64, const uint8_t *masks, uint8_t *occ,
@@ -1621,6 +2380,12 @@ int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const
     const int nenv = num_envs > ctx->hi_water ? num_envs : ctx->hi_water;  // envs >= num_envs get wiped
     ctx->hi_water = num_envs;
 
+    if (ctx->cfg.reserved[0] == 0 && overlap_applies(ctx, P, depth, P.labels, logits, labels_out)) {
+        T_BEGIN(1);
+        rc = launch_overlap(ctx, P, logits, num_classes, labels_out, nenv, st);
+        T_END(1);
+        return rc;
+    }
     if (fused_applies(ctx, P, depth, P.labels, logits)) {
         T_BEGIN(1);
         rc = launch_fused(ctx, P, logits, num_classes, labels_out, nenv, st);
