@@ -761,19 +761,19 @@ IVM_HD void ivm_fixup_scan(const IvmParams &P, int blk, int nblk, int tid, int n
     }
 }
 
-// The same scan by ONE thread block.  The segment headers (and what is needed of their envs) are staged in
+// The same scan by one thread block (or a few: block `blk` of `nblk`).  The segment headers (and what is needed of their envs) are staged in
 // block memory first; then every thread loads the metas of IVM_SCAN_MLP cells together (independent loads)
 // before any live cell is appended, so the whole scan costs a few memory round trips.
 #define IVM_SCAN_MLP 16
 #define IVM_SCAN_HDR 8   // ints per staged segment: b, is_col, line, len, lo, origin_r, origin_c, reset_stamp
 template <class A>
-IVM_HD void ivm_fixup_scan_block(const IvmParams &P, const IvmFixScratch &S, int tid, int nthreads) {
+IVM_HD void ivm_fixup_scan_block(const IvmParams &P, const IvmFixScratch &S, int blk, int nblk, int tid, int nthreads) {
     const IvmGlobal *g = P.g;
     const int nseg = (int)g->n_seg, nchunks = (int)g->scan_chunks;
     if (nseg <= 0 || nchunks <= 0) return;  // block-uniform
     if ((size_t)nseg * IVM_SCAN_HDR * sizeof(int32_t) > (size_t)S.cap * sizeof(unsigned long long) ||
         (long long)nchunks * IVM_SCAN_CHUNK * nseg > (1ll << 30)) {
-        ivm_fixup_scan<A>(P, 0, 1, tid, nthreads);  // more segments than the scratch holds
+        ivm_fixup_scan<A>(P, blk, nblk, tid, nthreads);  // more segments than the scratch holds
         return;
     }
     int32_t *hdr = reinterpret_cast<int32_t *>(S.key);  // free between the two class resolutions
@@ -791,12 +791,13 @@ IVM_HD void ivm_fixup_scan_block(const IvmParams &P, const IvmFixScratch &S, int
     const int32_t loc[4] = {g->loc[0], g->loc[1], g->loc[2], g->loc[3]};
     const int span = nchunks * IVM_SCAN_CHUNK;  // padded cells per segment
     const int total = span * nseg;
-    for (int base = 0; base < total; base += nthreads * IVM_SCAN_MLP) {
+    const int gthreads = nthreads * nblk, gtid = blk * nthreads + tid;  // `nblk` blocks share the cells
+    for (int base = 0; base < total; base += gthreads * IVM_SCAN_MLP) {
         uint32_t meta[IVM_SCAN_MLP];
 #pragma unroll
         for (int j = 0; j < IVM_SCAN_MLP; ++j) {
             meta[j] = 0u;
-            const int i = base + j * nthreads + tid;
+            const int i = base + j * gthreads + gtid;
             if (i >= total) continue;
             const int q = i / span, off = i - q * span;
             const int32_t *h = hdr + IVM_SCAN_HDR * q;
@@ -810,7 +811,7 @@ IVM_HD void ivm_fixup_scan_block(const IvmParams &P, const IvmFixScratch &S, int
 #pragma unroll
         for (int j = 0; j < IVM_SCAN_MLP; ++j) {
             if (meta[j] == 0u) continue;
-            const int i = base + j * nthreads + tid;
+            const int i = base + j * gthreads + gtid;
             const int q = i / span, off = i - q * span;
             const int32_t *h = hdr + IVM_SCAN_HDR * q;
             if (!ivm_live(meta[j], (uint32_t)h[7])) continue;
@@ -885,7 +886,7 @@ IVM_HD void ivm_fixup_program(const IvmParams &P, const IvmFixScratch &S, int ti
     ivm_fixup_stage1<A>(P, S, tid, nthreads);
     A::sync();
     IVM_TRACE(P.g, 3, tid);
-    ivm_fixup_scan_block<A>(P, S, tid, nthreads);
+    ivm_fixup_scan_block<A>(P, S, 0, 1, tid, nthreads);
     A::sync();
     ivm_fixup_stage2<A>(P, S, tid, nthreads);
 }

@@ -525,17 +525,29 @@ __device__ __forceinline__ void raster_record(const IvmParams &P, const uint4 ra
     }
 }
 
-// bytes of shared memory one raster group needs
-static inline size_t raster_smem_bytes(int tile_r, int tile_c, int max_rows) {
+// bytes of shared memory one raster group needs: keys + occupancy of the tile, the span table, and (stage_cap > 0)
+// a staging area of stage_cap records + the per-row offsets into it
+static inline size_t raster_fixed_bytes(int tile_r, int tile_c, int max_rows) {
+    return (((size_t)tile_r * tile_c * 5 + (size_t)max_rows * 8 + 16) + 15) & ~(size_t)15;
+}
+static inline size_t raster_smem_bytes(int tile_r, int tile_c, int max_rows, int stage_cap = 0) {
+    size_t n = raster_fixed_bytes(tile_r, tile_c, max_rows);
+    if (stage_cap > 0) n += (((size_t)(max_rows + 1) * 4 + 15) & ~(size_t)15) + (size_t)stage_cap * 16;
+    return n;
+}
+__device__ __forceinline__ size_t raster_fixed_bytes_dev(int tile_r, int tile_c, int max_rows) {
     return (((size_t)tile_r * tile_c * 5 + (size_t)max_rows * 8 + 16) + 15) & ~(size_t)15;
 }
 
 // safe_only: the tile is rastered only if nothing under it can still be changed by the edge fix-up, i.e. no
 // frame-edge winner is pending in it (tile_dirty stamp) and its store footprint stays strictly inside the
 // env's bounding box (stage-2 collisions live on the bbox edge lines).  Returns false if the tile was skipped.
+// stage_cap > 0: the records under the tile are first copied into shared memory with cp.async (every copy of the
+// tile in flight at once, no registers held), so that a tile costs ONE memory round trip instead of one per
+// batch of rows; tiles with more records than stage_cap take the direct path.
 template <bool KNOWN>
 __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, int b, int r0, int c0, uint32_t *smem, int tid,
-                                            int nthr, int bar_id, unsigned &n_in, bool safe_only = false) {
+                                            int nthr, int bar_id, unsigned &n_in, bool safe_only = false, int stage_cap = 0) {
     const int tr = P.tile_r, tc = P.tile_c;
     uint32_t *skey = smem;
     int32_t *s_clo = reinterpret_cast<int32_t *>(skey + tr * tc);   // first store column of each half-row's span
@@ -578,7 +590,63 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
     }
     group_bar(bar_id, nthr);
     if (!KNOWN && safe_only && s_maxlen[1]) return false;  // uniform
-    if (!KNOWN) {
+    bool staged = false;
+    if (!KNOWN && stage_cap > 0) {
+        int32_t *s_off = reinterpret_cast<int32_t *>(reinterpret_cast<unsigned char *>(smem) + raster_fixed_bytes_dev(tr, tc, max_rows));
+        uint4 *stage = reinterpret_cast<uint4 *>(s_off + ((max_rows + 1 + 3) & ~3));
+        if (warp == 0) {  // exclusive prefix of the span lengths
+            int carry = 0;
+            for (int i0 = 0; i0 < nrows; i0 += 32) {
+                const int i = i0 + lane;
+                const int len = i < nrows ? s_len[i] : 0;
+                int x = len;
+                for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+                if (i < nrows) s_off[i] = carry + x - len;
+                carry += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (lane == 0) s_maxlen[2] = carry;
+        }
+        group_bar(bar_id, nthr);
+        const int total = s_maxlen[2];
+        if (total <= stage_cap) {
+            staged = true;
+            const IvmRecord *env_store = P.store + (size_t)b * P.SR * P.SC;
+            const int hw = tid >> 4, nhw = nthr >> 4, l16 = tid & 15;
+            const unsigned long long pol = ivm_policy_keep();
+            for (int i = hw; i < nrows; i += nhw) {
+                const int len = s_len[i];
+                const IvmRecord *src = env_store + (size_t)(row_lo + i - e.origin_r) * P.SC + (size_t)(s_clo[i] - e.origin_c);
+                uint4 *dst = stage + s_off[i];
+                for (int k = l16; k < len; k += 16)
+                    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(smem_u32(dst + k)), "l"(src + k), "l"(pol) : "memory");
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            group_bar(bar_id, nthr);
+            // every record of the tile is in shared memory: one half-warp per half-row, as in the direct path
+            for (int i = hw; i < nrows; i += nhw) {
+                const int len = s_len[i];
+                const uint32_t rowbase = (uint32_t)(row_lo + i - e.origin_r) * (uint32_t)P.SC + (uint32_t)(s_clo[i] - e.origin_c);
+                const uint4 *srow = stage + s_off[i];
+                for (int k0 = 0; k0 < len; k0 += 16 * IVM_RASTER_MLP) {
+                    uint4 raw[IVM_RASTER_MLP];
+                    bool have[IVM_RASTER_MLP];
+#pragma unroll
+                    for (int u = 0; u < IVM_RASTER_MLP; ++u) {
+                        const int off = k0 + 16 * u + l16;
+                        have[u] = off < len;
+                        raw[u] = have[u] ? srow[off] : make_uint4(0, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < IVM_RASTER_MLP; ++u)
+                        raster_record(P, raw[u], have[u], e.reset_stamp, px, h, pz, c, s, r0, r1, c0, c1, tc,
+                                      rowbase + (uint32_t)(k0 + 16 * u + l16), skey, socc, n_in);
+                }
+            }
+        }
+    }
+    if (KNOWN || staged) {
+    } else if (!KNOWN) {
         // phase 2: one half-warp per store half-row (a span under a 16x16 tile holds ~40 records);
         // its 16 lanes read up to IVM_RASTER_MLP x 16 consecutive records (independent 16-byte
         // loads, 256 contiguous bytes per half-warp and load) before any of them is processed
@@ -615,7 +683,8 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
                                   rowbase + (uint32_t)(k0 + 16 * u + l16), skey, socc, n_in);
             }
         }
-    } else {
+    }
+    if (KNOWN) {
         for (int i = warp; i < nrows; i += nwarps) {
             if (s_len[i] <= 0) continue;
             const int rr = row_lo + i, clo = s_clo[i], chi = s_clo[i] + s_len[i] - 1;
@@ -1173,9 +1242,12 @@ k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logi
                                // building multi-microsecond queues in front of the geometry warps' loads and atomics
 #define IVM_O_SLOTS_PRED 8     // tiles whose queue / labels a CTA holds at a time
 #define IVM_O_SLOTS_GT 16
-#define IVM_O_LOADB 8          // tiles whose depth loads are issued together
+#define IVM_O_LOADB 8          // tiles whose depth loads are issued together (refill pass)
+#define IVM_O_SUB 4            // tiles a G1 group handles per pass (16 pixels per thread in flight)
 #define IVM_O_CTAS_PER_SM 2
 #define IVM_O_TILE_CTR 40      // word of the barrier block (its second 128-byte line) that hands out raster tiles
+#define IVM_O_FIX_FLAG 48      // ... = step once CTA 0 has finished stage 1 of the edge fix-up
+#define IVM_O_FIX_ARRIVE 56    // ... arrivals of the fix-up team after the edge-line scan (monotone)
 
 struct OvlSlot {               // one tile of a chunk
     float T[12];
@@ -1302,9 +1374,9 @@ __device__ __forceinline__ bool grid_wait_group(uint32_t *bar, uint32_t target, 
 template <bool PRED>
 __global__ void __launch_bounds__(IVM_O_THREADS, IVM_O_CTAS_PER_SM)
 k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out,
-               int nenv_total, uint32_t bar_base, int max_rows, int raster_group_bytes) {
+               int nenv_total, uint32_t bar_base, int max_rows, int raster_group_bytes, int stage_cap, int team, uint32_t team_base) {
     constexpr int NG1 = 256;                               // G1 (depth scatter): warps 0..7 in both modes
-    constexpr int PX1 = IVM_O_TILE / NG1;                  // pixels per thread and tile in G1
+    constexpr int PX1 = 4;                                 // pixels per thread and tile in G1 (a tile = one group of 4 warps)
     constexpr int NG = PRED ? 128 : 256;                   // G3 (resolve) threads: warps 0..3 beside the argmax warps, or 0..7
     constexpr int NGW = NG / 32;
     constexpr int PX = IVM_O_TILE / NG;                    // refill pass of G3 (more tiles than slots)
@@ -1328,19 +1400,34 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     const bool geo = warp < NGW;
     const int nstage = ((P.debug >> 8) & 15) ? min((P.debug >> 8) & 15, IVM_O_NSTAGE) : IVM_O_NSTAGE;  // experiment: shallower ring
 
-    // the first batch of depth loads goes out before anything else (ahead of the score stream's first 80 KB)
-    OvlDepth<PX1> dv[IVM_O_LOADB];
+    // G1 runs as two groups of four warps that take whole tiles (4 pixels per thread and tile).  With a score
+    // stream, group 1 (the argmax warps) scatters only the first ~quarter of the CTA's tiles and then starts
+    // consuming the ring, so the stream is held up for a few microseconds only; group 0 does the rest.  With GT
+    // labels the two groups take alternate tiles.
+    const int g1 = warp >> 2, gt1 = tid & 127;
+    int kbase = 0, kstride = 1, nmine = 0;
+    auto assign = [&](int cn) {
+        if (PRED) {
+            const int a = (cn + 2) / 4;
+            kbase = g1 ? 0 : a; nmine = g1 ? a : cn - a; kstride = 1;
+        } else {
+            kbase = g1; kstride = 2; nmine = (cn - g1 + 1) / 2;
+        }
+    };
+    // the first batch of depth loads goes out before anything else (ahead of the score stream's first 48 KB)
+    OvlDepth<PX1> dv[IVM_O_SUB];
     if (tid < NG1) {
+        assign(min(NSLOT, my_tiles));
 #pragma unroll
-        for (int k = 0; k < IVM_O_LOADB; ++k) {
+        for (int m = 0; m < IVM_O_SUB; ++m) {
 #pragma unroll
-            for (int j = 0; j < PX1; ++j) dv[k].v[j] = 2.0f;
-            if (k < my_tiles) dv[k] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + k * grid_n) * IVM_O_TILE + tid * PX1);
+            for (int j = 0; j < PX1; ++j) dv[m].v[j] = 2.0f;
+            if (m < nmine) dv[m] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + (kbase + kstride * m) * grid_n) * IVM_O_TILE + gt1 * PX1);
         }
     }
     if (blockIdx.x == 0 && tid == 0) {
         g->tstamp[0] = global_timer(); g->tstamp[5] = 0ull;
-        P.bar[IVM_O_TILE_CTR] = 2u * (gridDim.x - (gridDim.x > 1 ? 1u : 0u));  // raster tiles handed out statically
+        P.bar[IVM_O_TILE_CTR] = 2u * (gridDim.x - (gridDim.x > 1 ? (unsigned)team : 0u));  // raster tiles handed out statically
     }
     OVL_STAMP(7, 0);
     if (tid == 0) {
@@ -1367,9 +1454,10 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             const int cn = min(NSLOT, my_tiles - c0);
             if (c0) {
                 group_bar(1, NG1);  // the previous chunk's slots are no longer read
+                assign(cn);
 #pragma unroll
-                for (int k = 0; k < IVM_O_LOADB; ++k)
-                    if (k < cn) dv[k] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + (c0 + k) * grid_n) * IVM_O_TILE + tid * PX1);
+                for (int m = 0; m < IVM_O_SUB; ++m)
+                    if (m < nmine) dv[m] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + (c0 + kbase + kstride * m) * grid_n) * IVM_O_TILE + gt1 * PX1);
             }
             {   // slot prep, 4 slots per warp at a time (8 lanes each): env decision (reset / store origin,
                 // mapper.py:310-326) by lane 0 of the octet, pose matrices by lane 1; every load of a lane is
@@ -1413,23 +1501,25 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                     if (tid < 2) P.cs_buf[2 * sl.b + tid] = sl.cs[tid];
                 }
             }
-            for (int s0 = 0; s0 < cn; s0 += IVM_O_LOADB) {
-                if (s0) {
+            for (int m0 = 0; m0 < nmine; m0 += IVM_O_SUB) {
+                if (m0) {
 #pragma unroll
-                    for (int k = 0; k < IVM_O_LOADB; ++k)
-                        if (s0 + k < cn) dv[k] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + (c0 + s0 + k) * grid_n) * IVM_O_TILE + tid * PX1);
+                    for (int m = 0; m < IVM_O_SUB; ++m)
+                        if (m0 + m < nmine)
+                            dv[m] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + (c0 + kbase + kstride * (m0 + m)) * grid_n) * IVM_O_TILE + gt1 * PX1);
                 }
                 // pass A: every pixel of the batch -- world point, filters, half-cell; the candidate word and the
                 // world record of the valid ones are PREFETCHED into L2, and the pixel is queued for G3
-                float yk[IVM_O_LOADB][PX1];
-                uint32_t cik[IVM_O_LOADB][PX1];     // cell index in the env's store window, ~0 = nothing to offer
+                float yk[IVM_O_SUB][PX1];
+                uint32_t cik[IVM_O_SUB][PX1];     // cell index in the env's store window, ~0 = nothing to offer
 #pragma unroll
-                for (int k = 0; k < IVM_O_LOADB; ++k) {
+                for (int m = 0; m < IVM_O_SUB; ++m) {
 #pragma unroll
-                    for (int j = 0; j < PX1; ++j) { yk[k][j] = 0.f; cik[k][j] = 0xFFFFFFFFu; }
-                    if (s0 + k >= cn) continue;  // uniform
-                    OvlSlot &sl = sh.slot[s0 + k];
-                    const int tp = tid * PX1, pix0 = sl.tp0 + tp;
+                    for (int j = 0; j < PX1; ++j) { yk[m][j] = 0.f; cik[m][j] = 0xFFFFFFFFu; }
+                    if (m0 + m >= nmine) continue;  // group-uniform
+                    const int k = kbase + kstride * (m0 + m);
+                    OvlSlot &sl = sh.slot[k];
+                    const int tp = gt1 * PX1, pix0 = sl.tp0 + tp;
                     const int v = pix0 / P.W, u0 = pix0 - v * P.W;
                     const float ysv = P.ys[v];
                     float x[PX1], z[PX1];
@@ -1437,9 +1527,9 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                     bool any = false;
 #pragma unroll
                     for (int j = 0; j < PX1; ++j) {
-                        const float d = dv[k].v[j];
-                        ivm_world_xyz(d, P.xs[u0 + j], ysv, sl.T, x[j], yk[k][j], z[j]);
-                        ok[j] = d > 0.01f && d < 0.99f && yk[k][j] > sl.hlo && yk[k][j] < sl.hhi;
+                        const float d = dv[m].v[j];
+                        ivm_world_xyz(d, P.xs[u0 + j], ysv, sl.T, x[j], yk[m][j], z[j]);
+                        ok[j] = d > 0.01f && d < 0.99f && yk[m][j] > sl.hlo && yk[m][j] < sl.hhi;
                         any = any || ok[j];
                     }
                     uint32_t cell[PX1];
@@ -1458,37 +1548,32 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                             if (ok[j] && !inside) { atomicOr(&g->err, IVM_ERR_STORE_OVERFLOW); ok[j] = false; }
                             if (ok[j]) {
                                 const uint32_t ci = (uint32_t)rr * (uint32_t)P.SC + (uint32_t)cc;
-                                cik[k][j] = ci; cell[j] = ((uint32_t)rr << 16) | (uint32_t)cc;
-                                if (P.debug & 8) {
-                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.cplane[ebase + ci]));
-                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.store[ebase + ci]));
-                                } else {
-                                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(&P.cplane[ebase + ci]));
-                                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(&P.store[ebase + ci]));
-                                }
+                                cik[m][j] = ci; cell[j] = ((uint32_t)rr << 16) | (uint32_t)cc;
+                                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(&P.cplane[ebase + ci]));
+                                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(&P.store[ebase + ci]));
                                 rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
                                 ++nvalid;
                             }
                         }
                         if (keep_queue) {
-                            unsigned m[PX1];
+                            unsigned mk[PX1];
                             int n = 0;
 #pragma unroll
-                            for (int j = 0; j < PX1; ++j) { m[j] = __ballot_sync(0xffffffffu, ok[j]); n += __popc(m[j]); }
+                            for (int j = 0; j < PX1; ++j) { mk[j] = __ballot_sync(0xffffffffu, ok[j]); n += __popc(mk[j]); }
                             if (n) {  // warp-uniform
                                 unsigned pos = 0;
                                 if (lane == 0) pos = atomicAdd(&sl.qn, (unsigned)n);
                                 pos = __shfl_sync(0xffffffffu, pos, 0);
                                 const unsigned below = (1u << lane) - 1u;
-                                uint32_t *qc = qcell + (s0 + k) * IVM_O_TILE;
-                                uint16_t *qp = qpix + (s0 + k) * IVM_O_TILE;
+                                uint32_t *qc = qcell + k * IVM_O_TILE;
+                                uint16_t *qp = qpix + k * IVM_O_TILE;
 #pragma unroll
                                 for (int j = 0; j < PX1; ++j) {
                                     if (ok[j]) {
-                                        const unsigned o = pos + __popc(m[j] & below);
+                                        const unsigned o = pos + __popc(mk[j] & below);
                                         qc[o] = cell[j]; qp[o] = (uint16_t)(tp + j);
                                     }
-                                    pos += __popc(m[j]);
+                                    pos += __popc(mk[j]);
                                 }
                             }
                         }
@@ -1496,22 +1581,22 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                 }
                 // pass B: ONE 64-bit RED.MAX per valid pixel into the candidate plane (its line is in L2 or on its way)
 #pragma unroll
-                for (int k = 0; k < IVM_O_LOADB; ++k) {
-                    if (s0 + k >= cn) continue;  // uniform
-                    const OvlSlot &sl = sh.slot[s0 + k];
-                    const int pix0 = sl.tp0 + tid * PX1;
+                for (int m = 0; m < IVM_O_SUB; ++m) {
+                    if (m0 + m >= nmine) continue;  // group-uniform
+                    const OvlSlot &sl = sh.slot[kbase + kstride * (m0 + m)];
+                    const int pix0 = sl.tp0 + gt1 * PX1;
 #pragma unroll
                     for (int j = 0; j < PX1; ++j)
-                        if (cik[k][j] != 0xFFFFFFFFu) {
-                            unsigned long long *w = &P.cplane[(size_t)sl.b * P.SR * P.SC + cik[k][j]];
-                            const unsigned long long key = ivm_cand_key(P, yk[k][j], (uint32_t)(pix0 + j));
-                            if (P.debug & 8) atomicMax(w, key);
-                            else asm volatile("red.relaxed.gpu.global.max.u64.L2::cache_hint [%0], %1, %2;" ::"l"(w), "l"(key), "l"(ivm_policy_keep()) : "memory");
+                        if (cik[m][j] != 0xFFFFFFFFu) {
+                            unsigned long long *w = &P.cplane[(size_t)sl.b * P.SR * P.SC + cik[m][j]];
+                            const unsigned long long key = ivm_cand_key(P, yk[m][j], (uint32_t)(pix0 + j));
+                            asm volatile("red.relaxed.gpu.global.max.u64.L2::cache_hint [%0], %1, %2;" ::"l"(w), "l"(key), "l"(ivm_policy_keep()) : "memory");
                         }
                 }
             }
         }
         OVL_STAMP(2, 0);
+        if (tid == NG) OVL_STAMP(12, NG);
         // frame bbox over ALL envs (mapper.py:465), one flush per CTA
         const unsigned wv = warp_sum(nvalid);
         if (wv) {
@@ -1749,13 +1834,15 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     // touch; then CTA 0 releases everybody with ONE add worth the three remaining arrivals, and the few
     // tiles that had to wait are rastered by the groups that hold them.  Tiles are handed out dynamically
     // (one static tile per group, then an atomic counter): their cost varies with the records under them.
-    const int first = grid_n > 1 ? 1 : 0;                 // CTAs [first, grid) start rastering at once
+    const int first = grid_n > 1 ? team : 0;              // CTAs [first, grid) start rastering at once
     const int tiles_x = (P.C + P.tile_c - 1) / P.tile_c, tiles_y = (P.R + P.tile_r - 1) / P.tile_r;
     const int per_env = tiles_x * tiles_y, units = P.B * per_env;
     const int group = tid / IVM_F_GROUP, gtid = tid - group * IVM_F_GROUP;
     uint32_t *gsm = reinterpret_cast<uint32_t *>(dyn + (size_t)group * raster_group_bytes);
     const uint32_t release_target = bar_base + 5u * gridDim.x;
-    if (cta == 0) {
+    if (cta < team) {
+        // The fix-up team: CTA 0 runs stages 1 and 2; the edge-line scan between them (thousands of scattered
+        // 4-byte loads, more misses than one SM keeps in flight) is shared by the team's CTAs.
         IvmFixScratch S;
         S.key = reinterpret_cast<unsigned long long *>(dyn);
         S.xo = S.key + IVM_FIX_SMALL;
@@ -1763,15 +1850,50 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         S.cap = IVM_FIX_SMALL;
         S.ibuf = reinterpret_cast<int32_t *>(S.ord + IVM_FIX_SMALL);
         S.lbuf = reinterpret_cast<unsigned long long *>(S.ibuf + 8);
-        ivm_fixup_program<IvmAtomics>(P, S, tid, blockDim.x);
-        __syncthreads();
-        if (tid == 0) {
-            g->tstamp[3] = global_timer();
+        auto spin_until = [&](uint32_t *word, uint32_t want, bool equal) {  // thread 0 only
+            uint32_t spins = 0;
+            for (;;) {
+                uint32_t v;
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(word) : "memory");
+                if (equal ? v == want : (int32_t)(v - want) >= 0) break;
+                if (++spins > (1u << 22)) { atomicOr(&g->err, IVM_ERR_GRID_BARRIER); break; }
+                __nanosleep(spins < 8 ? 32 : 128);
+            }
             __threadfence();
-            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(P.bar), "r"(3u * gridDim.x) : "memory");
-            g->tstamp[4] = global_timer();
+        };
+        if (cta == 0) {
+            ivm_fixup_stage1<IvmAtomics>(P, S, tid, blockDim.x);
+            __syncthreads();
+            if (team > 1 && tid == 0) {
+                __threadfence();
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&P.bar[IVM_O_FIX_FLAG]), "r"(P.step) : "memory");
+            }
+        } else {
+            if (tid == 0) spin_until(&P.bar[IVM_O_FIX_FLAG], P.step, true);
+            __syncthreads();
         }
+        if (cta == 0) IVM_TRACE(g, 3, tid);
+        ivm_fixup_scan_block<IvmAtomics>(P, S, cta, team, tid, blockDim.x);
         __syncthreads();
+        if (team > 1 && tid == 0) {
+            __threadfence();
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(&P.bar[IVM_O_FIX_ARRIVE]), "r"(1u) : "memory");
+        }
+        if (cta == 0) {
+            if (team > 1) {
+                if (tid == 0) spin_until(&P.bar[IVM_O_FIX_ARRIVE], team_base + (uint32_t)team, false);
+                __syncthreads();
+            }
+            ivm_fixup_stage2<IvmAtomics>(P, S, tid, blockDim.x);
+            __syncthreads();
+            if (tid == 0) {
+                g->tstamp[3] = global_timer();
+                __threadfence();
+                asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(P.bar), "r"(3u * gridDim.x) : "memory");
+                g->tstamp[4] = global_timer();
+            }
+            __syncthreads();
+        }
     }
     if (warp < 2 * IVM_F_GROUP / 32) {
         // group-level wait for the release (leader polls, named barrier of the group)
@@ -1795,7 +1917,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         bool released = cta == 0;                         // CTA 0 has just run the fix-up itself
         int npend = 0;
         int u = (cta - first) * 2 + group;
-        if (cta == 0 && first == 1) {                     // CTA 0 joins late: no static tile
+        if (cta < first) {                                // the fix-up team joins late: no static tile
             if (gtid == 0) sh.next[group] = (int32_t)atomicAdd(&P.bar[IVM_O_TILE_CTR], 1u);
             group_bar(2 + group, IVM_F_GROUP);
             u = sh.next[group];
@@ -1806,15 +1928,15 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             const int b = u / per_env, w = u - b * per_env;
             const int ty = w / tiles_x, tx = w - ty * tiles_x;
             if (released) {
-                raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in);
-            } else if (!raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in, true)) {
+                raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in, false, stage_cap);
+            } else if (!raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in, true, stage_cap)) {
                 if (npend < 32) {
                     if (gtid == 0) sh.pend[group][npend] = u;
                     ++npend;
                 } else {                                  // no room to remember it: wait here
                     wait_release();
                     released = true;
-                    raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in);
+                    raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in, false, stage_cap);
                 }
             }
             if (gtid == 0) sh.next[group] = unext;
@@ -1828,7 +1950,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             const int up = sh.pend[group][i];
             const int b = up / per_env, w = up - b * per_env;
             const int ty = w / tiles_x, tx = w - ty * tiles_x;
-            raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in);
+            raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in, false, stage_cap);
         }
         const unsigned wn = warp_sum(n_in);
         if (wn && lane == 0) atomicAdd(&g->stats[IVM_STAT_IN], (unsigned long long)wn);
@@ -2010,6 +2132,7 @@ struct ivm_ctx {
     int ovl_grid[2];      // same for k_step_overlap<false/true>
     size_t ovl_smem[2];
     uint32_t bar_base;    // value of IvmGlobal.bar_count before the next fused launch
+    uint32_t team_base;   // same for the fix-up team's arrival counter (k_step_overlap)
     int64_t launches;
     // known-mode scratch
     uint32_t *kfill, *ktotals;
@@ -2315,7 +2438,15 @@ static int launch_overlap(ivm_ctx *ctx, IvmParams &P, const float *logits, int n
                           cudaStream_t st) {
     const int pred = logits ? 1 : 0;
     int max_rows = raster_max_rows(P);
-    int group_bytes = (int)raster_smem_bytes(P.tile_r, P.tile_c, max_rows);
+    // staging area of a raster group: the half-cells under a rotated tile (its area in half-cells + a margin of one
+    // half-cell all round) with 25 % head-room, within what two CTAs per SM leave (tiles that still exceed it take
+    // the direct path)
+    const double hc = (double)P.res / (double)P.half_res;
+    int stage_cap = (int)(1.25 * (P.tile_r * hc + 3.0) * (P.tile_c * hc + 3.0)) + 64;
+    const int cap_max = (int)((110 * 1024 / 2 - (long)raster_smem_bytes(P.tile_r, P.tile_c, max_rows, 1)) / 16);
+    if (stage_cap > cap_max) stage_cap = cap_max;
+    if (stage_cap < 0 || ctx->cfg.reserved[2] != 2) stage_cap = 0;  // measured slower than the direct path (the raster is ALU-bound): opt-in only
+    int group_bytes = (int)raster_smem_bytes(P.tile_r, P.tile_c, max_rows, stage_cap);
     size_t smem = (size_t)2 * group_bytes;
     const size_t scratch = (size_t)IVM_FIX_SMALL * 20 + 1024;  // fix-up scratch
     if (smem < scratch) smem = scratch;
@@ -2336,11 +2467,16 @@ static int launch_overlap(ivm_ctx *ctx, IvmParams &P, const float *logits, int n
     int grid = ctx->ovl_grid[pred];
     if (grid > tiles) grid = (int)tiles;
     uint32_t bar_base = ctx->bar_base;
+    int team = grid / 16;  // CTAs that share the edge-line scan of the fix-up
+    if (team > 16) team = 16;
+    if (team < 1) team = 1;
+    uint32_t team_base = ctx->team_base;
     void *args[] = {(void *)&P, (void *)&logits, (void *)&ncls, (void *)&labels_out, (void *)&nenv_total,
-                    (void *)&bar_base, (void *)&max_rows, (void *)&group_bytes};
+                    (void *)&bar_base, (void *)&max_rows, (void *)&group_bytes, (void *)&stage_cap, (void *)&team, (void *)&team_base};
     cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(IVM_O_THREADS), args, smem, st);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaLaunchCooperativeKernel(k_step_overlap)");
     ctx->bar_base += 5u * (uint32_t)grid;
+    if (team > 1) ctx->team_base += (uint32_t)team;
     ctx->launches += 1;
     return IVM_OK;
 }

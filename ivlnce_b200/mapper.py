@@ -259,6 +259,7 @@ class _MapEngine:
                 f"the B200 mapping module runs on CUDA devices only (got {device}); there is no CPU fallback")
         self.lib = _lib.load()
         self.device = device
+        self._dev_index = device.index if device.index is not None else torch.cuda.current_device()
         self.md = map_dimensions
         self.camera = camera
         self.mode = mode
@@ -330,7 +331,8 @@ class _MapEngine:
             pass
 
     def stream(self) -> int:
-        return torch.cuda.current_stream(self.device).cuda_stream
+        # raw handle of torch's current stream on this device (no Stream object per call)
+        return torch._C._cuda_getCurrentRawStream(self._dev_index)
 
     def status(self) -> Tuple[int, List[int]]:
         st = _lib.IvmStatus()
@@ -339,10 +341,27 @@ class _MapEngine:
 
 
 def _as_u8_masks(masks: torch.Tensor, device) -> torch.Tensor:
+    if masks.dtype is torch.uint8 and masks.device == device and masks.is_contiguous():
+        return masks
     m = masks.to(device=device, non_blocking=True)
     if m.dtype != torch.uint8:
         m = (m != 0).to(torch.uint8)
     return m.contiguous()
+
+
+def _as_f32(t: torch.Tensor, device) -> torch.Tensor:
+    """`t` as a contiguous float32 tensor on `device` (no torch call at all when it already is one)."""
+    if t.dtype is torch.float32 and t.device == device and t.is_contiguous():
+        return t
+    return t.to(device=device, dtype=torch.float32, non_blocking=True).contiguous()
+
+
+class _Hold:
+    __slots__ = ("keepalive", "num_envs", "views_B", "occ_base", "occ_view", "sem_view")
+
+    def __init__(self):
+        self.keepalive, self.num_envs, self.views_B = None, 0, -1
+        self.occ_base = self.occ_view = self.sem_view = None
 
 
 class MappingModule(nn.Module):
@@ -381,10 +400,14 @@ class MappingModule(nn.Module):
                                  scatter_variant=scatter_variant)
         self._engine: Optional[_MapEngine] = None
         self._initial_max_envs = max_envs
-        self._num_envs = 0
+        self._hold = _Hold()   # per-call state kept off the nn.Module attribute machinery
         self._known_cache: Dict[str, Tuple[torch.Tensor, torch.Tensor, int, int]] = {}
         self._known_order: List[int] = []   # env indices in load order (world-cloud order in known mode)
         self._known_loaded: Dict[int, str] = {}
+
+    @property
+    def _num_envs(self) -> int:
+        return self._hold.num_envs
 
     # -- engine
     def engine(self, num_envs: int) -> _MapEngine:
@@ -398,7 +421,7 @@ class MappingModule(nn.Module):
     def _matrices(self, state: RobotCurrentState):
         pose, elev, head = state.pose, state.elevation, state.heading
         if self.trig == "kernel":
-            pose32 = pose.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+            pose32 = _as_f32(pose, self.device)
             if elev.dtype != head.dtype or head.dtype not in (torch.float32, torch.float64):
                 elev, head = elev.to(torch.float64), head.to(torch.float64)
             n = elev.shape[0]
@@ -424,30 +447,43 @@ class MappingModule(nn.Module):
         return T12.contiguous(), cs.contiguous(), pose32, None
 
     # -- forward
-    @torch.no_grad()
     def forward(self, episodes_info: EpisodesInfo, observations: Observations,
                 robot_current_state: RobotCurrentState) -> OccupancySemanticMapMemory:
+        # The step is ONE kernel of a few tens of microseconds, so the host path is kept as short: no autograd
+        # bookkeeping (nothing here builds a graph: the library is called with raw pointers), no nn.Module
+        # attribute traffic, no device context switch unless the current device really differs.
         if self.track_start_state:
             self.localize_robot(episodes_info, robot_current_state)
         else:
             self.localize_robot.current_state = robot_current_state
         B = episodes_info.num_envs
-        eng = self.engine(B)
-        lib = eng.lib
-        with torch.cuda.device(self.device):
-            T12, cs, pose, orient = self._matrices(robot_current_state)
-            self._keepalive = (T12, cs, pose, orient)
-            if self.mode == "iterative":
-                self._forward_iterative(eng, B, episodes_info, observations, T12, cs, pose, orient)
-            else:
-                self._forward_known(eng, B, episodes_info, cs, pose, orient)
-        self._num_envs = B
-        self.map_memory._occ = eng.occ[:B]
-        self.map_memory._sem = eng.sem[:B]
-        return self.map_memory
+        eng = self._engine
+        if eng is None or B > eng.max_envs:
+            eng = self.engine(B)
+        hold = self._hold
+        if torch.cuda.current_device() != eng._dev_index:
+            with torch.cuda.device(self.device):
+                return self._forward_on_device(eng, B, episodes_info, observations, robot_current_state, hold)
+        return self._forward_on_device(eng, B, episodes_info, observations, robot_current_state, hold)
+
+    def _forward_on_device(self, eng, B, episodes_info, observations, robot_current_state, hold):
+        T12, cs, pose, orient = self._matrices(robot_current_state)
+        hold.keepalive = (T12, cs, pose, orient)
+        if self.mode == "iterative":
+            self._forward_iterative(eng, B, episodes_info, observations, T12, cs, pose, orient)
+        else:
+            self._forward_known(eng, B, episodes_info, cs, pose, orient)
+        hold.num_envs = B
+        mem = self.map_memory
+        if hold.views_B != B or hold.occ_base is not eng.occ:
+            hold.views_B, hold.occ_base, hold.occ_view, hold.sem_view = B, eng.occ, eng.occ[:B], eng.sem[:B]
+        mem._occ = hold.occ_view
+        mem._sem = hold.sem_view
+        return mem
 
     def _forward_iterative(self, eng, B, episodes_info, observations, T12, cs, pose, orient):
-        H, W = (int(v) for v in self.camera_parameters.features_spatial_dimensions)
+        H, W = self.camera_parameters.features_spatial_dimensions
+        H, W = int(H), int(W)
         sem_mod = self.compute_semantics
         scores = None
         if isinstance(sem_mod, PredictSemantics):
@@ -457,20 +493,22 @@ class MappingModule(nn.Module):
         depth = observations.depth_normalized
         assert depth.shape[2] == H  # projector/point_cloud.py:68-69
         assert depth.shape[3] == W
-        depth = depth.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
+        depth = _as_f32(depth, self.device)
         masks = _as_u8_masks(episodes_info.not_done_masks, self.device)
         labels_ptr, logits_ptr, ncls = None, None, 0
         if scores is not None:
-            scores = scores.to(device=self.device, dtype=torch.float32, non_blocking=True).contiguous()
-            assert scores.shape[0] == B and tuple(scores.shape[2:]) == (H, W)
+            scores = _as_f32(scores, self.device)
+            assert scores.shape[0] == B and scores.shape[2] == H and scores.shape[3] == W
             logits_ptr, ncls = scores.data_ptr(), int(scores.shape[1])
             # side effect of PredictSemantics.forward (mapper.py:796-798)
             observations.semantics = eng.labels_out[:B].view(B, 1, H, W)
         else:
-            labels = observations.semantics.to(device=self.device, non_blocking=True)
-            if labels.dtype != torch.uint8:
-                labels = labels.to(torch.uint8)
-            labels = labels.contiguous()
+            labels = observations.semantics
+            if not (labels.dtype is torch.uint8 and labels.device == self.device and labels.is_contiguous()):
+                labels = labels.to(device=self.device, non_blocking=True)
+                if labels.dtype != torch.uint8:
+                    labels = labels.to(torch.uint8)
+                labels = labels.contiguous()
             assert labels.numel() == B * H * W
             labels_ptr = labels.data_ptr()
         args = (eng.ctx, B, depth.data_ptr(), labels_ptr, logits_ptr, ncls, eng.labels_out.data_ptr(),
