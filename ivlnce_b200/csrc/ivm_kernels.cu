@@ -1,14 +1,16 @@
 // ivm_kernels.cu -- sm_100a kernels + C ABI of the semantic-map update.
 //
-// Step pipeline (iterative mode), all on the caller's stream:
+// One step (iterative mode) on the caller's stream is ONE cooperative launch of the persistent kernel
+// k_step_overlap (see its header below) whenever the image tiles evenly and the inputs are aligned.  Otherwise
+// the same phases run as four kernels:
 //   K1 k_ingest_scatter  per-env O(1) reset / store re-centring / pose matrices (mapper.py:310-326, 127-138), then
 //      (_bulk)           [argmax ->] unproject -> transform -> filter -> half-cell ->
 //                        64-bit atomicMax into the frame-candidate plane   (mapper.py:381-474, core.py:117-230)
 //   K2 k_ingest_resolve  the owning pixel of each candidate merges into the world store
 //   K3 k_fixup           edge-collision fix-up of both de-dup stages        (mapper.py:461-474 quirk)
 //   K4 k_raster          band filter -> ego transform -> cell -> smem max/or -> u8 maps (mapper.py:555-617, 884-901)
-// Four launches per step.  No point cloud is ever written to HBM; the only per-pixel state is
-// the 8-byte candidate word of the touched half-cells.
+// No point cloud is ever written to HBM; the only per-pixel state is the 8-byte candidate word of the touched
+// half-cells.
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -732,25 +734,9 @@ __global__ void k_pose(IvmParams P) {
     if (b < P.B) ivm_pose_matrices(P, b, P.T12_buf + 12 * b, P.cs_buf + 2 * b);
 }
 
-// ------------------------------------------------------------------ fused persistent step kernel
-// The whole map update as ONE cooperative launch of co-resident CTAs (2 per SM), phases separated
-// by grid barriers instead of kernel boundaries:
-//   A  ingest-scatter  warp-specialised: warp 8 is the producer (one lane issues cp.async.bulk =
-//                      TMA 1-D copies of the class-score planes into a 6 x 16 KB shared-memory
-//                      ring, full/empty mbarriers), warps 0-7 consume (running argmax from shared
-//                      memory, labels out, unproject, atomicMax into the candidate plane).  No
-//                      block-wide barrier inside the stream.
-//   B  resolve         every CTA revisits its own tiles (depth/labels are L2-resident by now)
-//   C  edge fix-up     CTA 0 only (the others wait at the next barrier)
-//   D  raster          two 128-thread groups per CTA, one ego tile each at a time
-// CTA t owns a contiguous range of 512-pixel tiles in A and B.
-#define IVM_F_THREADS 288      // 8 consumer warps + 1 producer warp
-#define IVM_F_CONSUMERS 256
-#define IVM_F_TILE 512         // pixels per tile (= 256 consumer threads x 2)
-#define IVM_F_SP 8             // planes per ring stage (16 KB)
-#define IVM_F_NSTAGE 6         // ring depth (96 KB per CTA, 192 KB per SM)
-#define IVM_F_CTAS_PER_SM 2
-#define IVM_F_GROUP 128        // raster group
+// ------------------------------------------------------------------ persistent step kernel: helpers
+#define IVM_F_TILE 512         // pixels per tile of the persistent step kernel
+#define IVM_F_GROUP 128        // threads of one raster group (two groups per CTA)
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -794,447 +780,27 @@ __device__ __forceinline__ bool grid_barrier(uint32_t *bar, uint32_t target, int
     return grid_wait(bar, target, s_flag);
 }
 
-#define IVM_F_BR 8             // tiles per round (= consumer warps)
-#define IVM_F_DRAIN 4          // queue entries per thread and drain iteration
-struct FusedSlot {             // one tile of a round
-    float T[12];
-    float cs[2];
-    int32_t b, tp0, origin_r, origin_c, reset;
-    uint32_t reset_stamp;
-    float h, hlo, hhi;
-    int32_t box[5];            // bbox + count of the cells this CTA newly occupied in the slot's env
-};
-struct FusedShared {
-    K1Shared k1;
-    FusedSlot slot[IVM_F_BR];
-    unsigned qn;
-    uint64_t full[IVM_F_NSTAGE];
-    uint64_t empty[IVM_F_NSTAGE];
-    int flag;
-};
-
-// per-CTA timeline (profiling): slot k of this CTA <- %globaltimer, taken by thread 0.  `dep` is a
-// value the stamp must wait for (a barrier does not block the timer read by itself).
-#define CTA_STAMP(k, dep)                                                                              \
-    do {                                                                                               \
-        if (tid == 0 && blockIdx.x < IVM_TRACE_CTAS) {                                                 \
-            asm volatile("" ::"r"(dep) : "memory");                                                    \
-            P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + (k)] = global_timer();                  \
-        }                                                                                              \
-    } while (0)
-
-// Tiles are dealt round-robin (tile = CTA + j * grid): valid pixels cluster in the image rows around
-// the horizon, so contiguous ranges would give a few CTAs all the scatter / resolve work.
-template <bool PRED>
-__global__ void __launch_bounds__(IVM_F_THREADS, IVM_F_CTAS_PER_SM)
-k_step_fused(const __grid_constant__ IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out, int nenv_total,
-             uint32_t bar_base, int max_rows, int raster_group_bytes) {
-    extern __shared__ __align__(128) unsigned char dyn[];
-    __shared__ __align__(8) FusedShared sh;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tpe = P.HW / IVM_F_TILE;                     // tiles per env
-    const long long total = (long long)P.B * tpe;
-    IvmGlobal *g = P.g;
-    if (blockIdx.x == 0 && tid == 0) { g->tstamp[0] = global_timer(); g->tstamp[5] = 0ull; }
-    CTA_STAMP(7, 0);
-
-    // ================================================================ phase A: ingest
-    //   A0 (consumers)  depth -> unproject -> ONE 64-bit RED.MAX per valid pixel into the candidate plane,
-    //                   8 tiles per round so that every thread has 8 depth loads in flight; then the CTA
-    //                   ARRIVES at grid barrier 1 without waiting
-    //   A1 (PRED)       class-score stream: the producer lane keeps a 6 x 16 KB shared-memory ring full with
-    //                   cp.async.bulk (TMA 1-D) copies of the planes from the first cycle of the kernel;
-    //                   the consumers run the argmax from shared memory and write the labels
-    if (PRED && tid == 0) {
-        for (int s = 0; s < IVM_F_NSTAGE; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], IVM_F_CONSUMERS / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    // paused envs (mapper.py:315-318) are wiped by the last CTA
-    if (blockIdx.x == gridDim.x - 1)
-        for (int b = P.B; b < nenv_total; ++b) {
-            IvmEnvPrep q; q.reset = 1; q.origin_r = 0; q.origin_c = 0;
-            ivm_env_publish<IvmAtomics>(P, b, q, tid, blockDim.x);
-        }
-    __syncthreads();
-    if (warp == IVM_F_CONSUMERS / 32) {
-        // ---- producer warp: one lane keeps the ring full
-        if (PRED && lane == 0) {
-            float(*ring)[IVM_F_SP][IVM_F_TILE] = reinterpret_cast<float(*)[IVM_F_SP][IVM_F_TILE]>(dyn);
-            uint64_t policy;
-            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-            int slot = 0;
-            uint32_t round = 0;  // how many times the ring has wrapped
-            for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int eb = (int)(tile / tpe), tp0 = (int)(tile - (long long)eb * tpe) * IVM_F_TILE;
-                const float *src = logits + (size_t)eb * ncls * P.HW + tp0;
-                for (int p0 = 0; p0 < ncls; p0 += IVM_F_SP) {
-                    const int np = min(IVM_F_SP, ncls - p0);
-                    if (round > 0) mbar_wait(&sh.empty[slot], (round - 1) & 1u);
-                    mbar_expect_tx(&sh.full[slot], (uint32_t)(np * IVM_F_TILE * sizeof(float)));
-                    for (int p = 0; p < np; ++p)
-                        bulk_g2s(&ring[slot][p][0], src + (size_t)(p0 + p) * P.HW, IVM_F_TILE * sizeof(float), &sh.full[slot],
-                                 policy);
-                    if (++slot == IVM_F_NSTAGE) { slot = 0; ++round; }
-                }
-            }
-        }
-    } else {
-        // ---- consumer warps, A0: depth scatter
-        int rmin = INT32_MAX, rmax = INT32_MIN, cmin = INT32_MAX, cmax = INT32_MIN;
-        unsigned nvalid = 0;
-        if (tid == 0) { sh.k1.bb[0] = INT32_MAX; sh.k1.bb[1] = INT32_MIN; sh.k1.bb[2] = INT32_MAX; sh.k1.bb[3] = INT32_MIN; sh.k1.valid = 0; }
-        for (int j0 = 0; (long long)blockIdx.x + (long long)j0 * gridDim.x < total; j0 += IVM_F_BR) {
-            if (j0) group_bar(1, IVM_F_CONSUMERS);  // the previous round's slots are no longer read
-            {   // warp k prepares slot k: env decision (reset / store origin, mapper.py:310-326) + pose matrices
-                const long long tile = (long long)blockIdx.x + (long long)(j0 + warp) * gridDim.x;
-                FusedSlot &sl = sh.slot[warp];
-                if (tile < total) {
-                    const int b = (int)(tile / tpe);
-                    if (lane == 0) {
-                        const IvmEnvPrep q = ivm_env_decide(P, b);
-                        sl.b = b; sl.tp0 = (int)(tile - (long long)b * tpe) * IVM_F_TILE;
-                        sl.origin_r = q.origin_r; sl.origin_c = q.origin_c; sl.reset = q.reset;
-                        sl.h = P.pose[3 * b + 1];
-                    }
-                    if (P.orient != nullptr) {
-                        if (lane == 1) ivm_pose_matrices(P, b, sl.T, sl.cs);
-                    } else if (lane >= 2 && lane < 14) {
-                        sl.T[lane - 2] = P.T12[12 * b + lane - 2];
-                    }
-                } else if (lane == 0) {
-                    sl.b = -1;
-                }
-            }
-            // this round's depth loads go out before the barrier
-            float2 dv[IVM_F_BR];
-#pragma unroll
-            for (int k = 0; k < IVM_F_BR; ++k) {
-                const long long tile = (long long)blockIdx.x + (long long)(j0 + k) * gridDim.x;
-                dv[k] = make_float2(2.0f, 2.0f);
-                if (tile < total) dv[k] = __ldcg(reinterpret_cast<const float2 *>(P.depth + (size_t)tile * IVM_F_TILE + tid * 2));  // stays in L2 for phase B
-            }
-            group_bar(1, IVM_F_CONSUMERS);
-            // the CTA that owns an env's first tile publishes the env's new state (read after barrier 1 only)
-            for (int k = 0; k < IVM_F_BR; ++k) {
-                const FusedSlot &sl = sh.slot[k];
-                if (sl.b < 0 || sl.tp0 != 0) continue;  // uniform
-                IvmEnvPrep q;
-                q.reset = sl.reset; q.origin_r = sl.origin_r; q.origin_c = sl.origin_c;
-                ivm_env_publish<IvmAtomics>(P, sl.b, q, tid, IVM_F_CONSUMERS);
-                if (P.orient != nullptr) {
-                    if (tid < 12) P.T12_buf[12 * sl.b + tid] = sl.T[tid];
-                    if (tid < 2) P.cs_buf[2 * sl.b + tid] = sl.cs[tid];
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < IVM_F_BR; ++k) {
-                const FusedSlot &sl = sh.slot[k];
-                if (sl.b < 0) continue;  // uniform
-                const int pix0 = sl.tp0 + tid * 2;
-                const int v = pix0 / P.W, u0 = pix0 - v * P.W;
-                const float ysv = P.ys[v];
-                const float dd[2] = {dv[k].x, dv[k].y};
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    IvmPoint p;
-                    const int ok = ivm_unproject(dd[j], P.xs[u0 + j], ysv, sl.T, sl.h, P.half_res, p);
-                    if (ok == 0) continue;
-                    size_t idx;
-                    if (ok == 2 || !ivm_store_index(P, sl.origin_r, sl.origin_c, sl.b, p.r, p.c, idx)) {
-                        atomicOr(&g->err, IVM_ERR_STORE_OVERFLOW);
-                        continue;
-                    }
-                    if (!(P.debug & 1))
-                        ivm_cand_insert<IvmAtomics>(P, sl.b, (uint32_t)(idx - (size_t)sl.b * P.SR * P.SC), ivm_cand_key(P, p.y, (uint32_t)(pix0 + j)));
-                    // the resolve phase will read-modify-write this cell's world record: pull it into L2 now
-                    if (!(P.debug & 2)) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.store[idx]));
-                    rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
-                    ++nvalid;
-                }
-            }
-        }
-        // frame bbox over ALL envs (mapper.py:465), one flush per CTA
-        const unsigned wv = warp_sum(nvalid);
-        if (wv) {
-            rmin = warp_min(rmin); rmax = warp_max(rmax); cmin = warp_min(cmin); cmax = warp_max(cmax);
-            if (lane == 0) {
-                atomicMin(&sh.k1.bb[0], rmin); atomicMax(&sh.k1.bb[1], rmax); atomicMin(&sh.k1.bb[2], cmin); atomicMax(&sh.k1.bb[3], cmax);
-                atomicAdd(&sh.k1.valid, wv);
-            }
-        }
-        group_bar(1, IVM_F_CONSUMERS);  // every consumer's REDs and the env publication are issued
-        if (tid == 0) {
-            if (sh.k1.valid) {
-                atomicMin(&g->loc[0], sh.k1.bb[0]); atomicMax(&g->loc[1], sh.k1.bb[1]);
-                atomicMin(&g->loc[2], sh.k1.bb[2]); atomicMax(&g->loc[3], sh.k1.bb[3]);
-                atomicAdd(&g->acc_valid, (unsigned long long)sh.k1.valid);
-            }
-            grid_arrive(P.bar);  // barrier 1: arrival only; the wait comes after the score stream
-        }
-        CTA_STAMP(10, 0);
-        // ---- consumer warps, A1: PredictSemantics tail (mapper.py:795-798): running argmax over the
-        //      planes, first max wins, NaN counts as maximal (torch.argmax)
-        if (PRED) {
-            float(*ring)[IVM_F_SP][IVM_F_TILE] = reinterpret_cast<float(*)[IVM_F_SP][IVM_F_TILE]>(dyn);
-            int slot = 0;
-            uint32_t round = 0;
-            for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                float best0 = 0.f, best1 = 0.f;
-                int a0 = 0, a1 = 0;
-                for (int p0 = 0; p0 < ncls; p0 += IVM_F_SP) {
-                    mbar_wait(&sh.full[slot], round & 1u);
-                    const int np = min(IVM_F_SP, ncls - p0);
-                    if (np == IVM_F_SP) {
-                        float2 v[IVM_F_SP];
-#pragma unroll
-                        for (int p = 0; p < IVM_F_SP; ++p) v[p] = *reinterpret_cast<const float2 *>(&ring[slot][p][tid * 2]);
-#pragma unroll
-                        for (int p = 0; p < IVM_F_SP; ++p) {
-                            if (p0 + p == 0) { best0 = v[p].x; best1 = v[p].y; }
-                            else { IVM_ARGMAX_STEP(v[p].x, p0 + p, best0, a0); IVM_ARGMAX_STEP(v[p].y, p0 + p, best1, a1); }
-                        }
-                    } else {
-                        for (int p = 0; p < np; ++p) {
-                            const float2 v = *reinterpret_cast<const float2 *>(&ring[slot][p][tid * 2]);
-                            if (p0 + p == 0) { best0 = v.x; best1 = v.y; }
-                            else { IVM_ARGMAX_STEP(v.x, p0 + p, best0, a0); IVM_ARGMAX_STEP(v.y, p0 + p, best1, a1); }
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sh.empty[slot]);  // this warp is done with the stage
-                    if (++slot == IVM_F_NSTAGE) { slot = 0; ++round; }
-                }
-                uchar2 o;
-                o.x = (uint8_t)a0; o.y = (uint8_t)a1;
-                *reinterpret_cast<uchar2 *>(labels_out + (size_t)tile * IVM_F_TILE + tid * 2) = o;
-            }
-        }
-    }
-    CTA_STAMP(6, 0);
-    __syncthreads();  // the ring is drained: its memory becomes the resolve queue
-    if (!grid_wait(P.bar, bar_base + 1u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
-    if (blockIdx.x == 0 && tid == 0) g->tstamp[1] = global_timer();
-    CTA_STAMP(0, sh.flag);
-
-    // ================================================================ phase B: resolve
-    // Rounds of IVM_F_BR tiles: (1) all depth/label loads of the round are issued together and the
-    // filter survivors are compacted into ONE queue per CTA (only ~1 pixel in 4 survives, clustered in
-    // a few image rows), (2) the queue is drained by all consumer threads, IVM_F_DRAIN entries at a
-    // time: the candidate word AND the world record of every entry are loaded together (the record
-    // speculatively), so a round costs one L2 round trip however many entries it holds.
-    if (warp < IVM_F_CONSUMERS / 32) {
-        uint32_t *q_pix = reinterpret_cast<uint32_t *>(dyn);                         // (slot << 24) | pixel
-        float *q_d = reinterpret_cast<float *>(dyn + IVM_F_BR * IVM_F_TILE * 4);
-        uint8_t *q_lab = dyn + 2 * IVM_F_BR * IVM_F_TILE * 4;
-        const int32_t loc[4] = {__ldcg(&g->loc[0]), __ldcg(&g->loc[1]), __ldcg(&g->loc[2]), __ldcg(&g->loc[3])};
-        const uint8_t *labels = P.labels;
-        unsigned nlocal = 0;
-        for (int j0 = 0; (long long)blockIdx.x + (long long)j0 * gridDim.x < total; j0 += IVM_F_BR) {
-            // ---- this round's pixel loads first (they do not depend on the slots)
-            float2 dv[IVM_F_BR];
-            uchar2 lv[IVM_F_BR];
-#pragma unroll
-            for (int k = 0; k < IVM_F_BR; ++k) {
-                const long long tile = (long long)blockIdx.x + (long long)(j0 + k) * gridDim.x;
-                dv[k] = make_float2(2.0f, 2.0f);
-                lv[k] = make_uchar2(0, 0);
-                if (tile < total) {
-                    const size_t base = (size_t)tile * IVM_F_TILE + tid * 2;
-                    dv[k] = __ldcg(reinterpret_cast<const float2 *>(P.depth + base));
-                    lv[k] = __ldcg(reinterpret_cast<const uchar2 *>(labels + base));
-                }
-            }
-            // ---- per-slot env data (warp k prepares slot k; every field is loaded by its own lane)
-            {
-                const long long tile = (long long)blockIdx.x + (long long)(j0 + warp) * gridDim.x;
-                FusedSlot &sl = sh.slot[warp];
-                if (tile < total) {
-                    const int b = (int)(tile / tpe);
-                    const IvmEnv *e = &P.env[b];
-                    if (lane < 12) sl.T[lane] = __ldcg(&P.T12[12 * b + lane]);
-                    if (lane == 12) { sl.b = b; sl.tp0 = (int)(tile - (long long)b * tpe) * IVM_F_TILE; }
-                    if (lane == 13) sl.origin_r = __ldcg(&e->origin_r);
-                    if (lane == 14) sl.origin_c = __ldcg(&e->origin_c);
-                    if (lane == 15) sl.reset_stamp = __ldcg(&e->reset_stamp);
-                    if (lane == 16) {
-                        const float h = P.pose[3 * b + 1];
-                        sl.h = h; sl.hlo = ivm_sub(h, 1.0f); sl.hhi = ivm_add(h, 0.5f);
-                    }
-                    if (lane == 17) { sl.box[0] = INT32_MAX; sl.box[1] = INT32_MIN; sl.box[2] = INT32_MAX; sl.box[3] = INT32_MIN; sl.box[4] = 0; }
-                } else if (lane == 12) {
-                    sl.b = -1;
-                }
-                if (tid == 0) sh.qn = 0u;
-            }
-            group_bar(1, IVM_F_CONSUMERS);
-            if (j0 == 0) CTA_STAMP(1, *(volatile unsigned *)&sh.qn);
-            // ---- filter pass: this thread's two pixels of every tile of the round
-#pragma unroll
-            for (int k = 0; k < IVM_F_BR; ++k) {
-                const FusedSlot &sl = sh.slot[k];
-                if (sl.b < 0) continue;  // uniform
-                const int pix0 = sl.tp0 + tid * 2;
-                const int v = pix0 / P.W, u0 = pix0 - v * P.W;
-                const float ysv = P.ys[v];
-                const float dd[2] = {dv[k].x, dv[k].y};
-                const uint8_t ll[2] = {lv[k].x, lv[k].y};
-                bool ok[2];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    ok[j] = dd[j] > 0.01f && dd[j] < 0.99f;
-                    if (ok[j]) {
-                        const float z = ivm_mul(dd[j], 10.0f);
-                        float a = ivm_mul(sl.T[4], ivm_mul(z, P.xs[u0 + j]));
-                        a = ivm_fma(sl.T[5], ivm_mul(z, ysv), a);
-                        a = ivm_fma(sl.T[6], z, a);
-                        a = ivm_fma(sl.T[7], 1.0f, a);
-                        ok[j] = a > sl.hlo && a < sl.hhi;
-                    }
-                }
-                const unsigned m0 = __ballot_sync(0xffffffffu, ok[0]), m1 = __ballot_sync(0xffffffffu, ok[1]);
-                const int n0 = __popc(m0), n01 = n0 + __popc(m1);
-                if (n01 == 0) continue;
-                unsigned basepos = 0;
-                if (lane == 0) basepos = atomicAdd(&sh.qn, (unsigned)n01);
-                basepos = __shfl_sync(0xffffffffu, basepos, 0);
-                const unsigned below = (1u << lane) - 1u;
-                if (ok[0]) {
-                    const unsigned pos = basepos + __popc(m0 & below);
-                    q_pix[pos] = ((uint32_t)k << 24) | (uint32_t)pix0; q_d[pos] = dd[0]; q_lab[pos] = ll[0];
-                }
-                if (ok[1]) {
-                    const unsigned pos = basepos + n0 + __popc(m1 & below);
-                    q_pix[pos] = ((uint32_t)k << 24) | (uint32_t)(pix0 + 1); q_d[pos] = dd[1]; q_lab[pos] = ll[1];
-                }
-            }
-            group_bar(1, IVM_F_CONSUMERS);
-            if (j0 == 0) CTA_STAMP(2, *(volatile unsigned *)&sh.qn);
-            // ---- drain
-            const int n = (int)sh.qn;
-            for (int i0 = tid; i0 < n; i0 += IVM_F_DRAIN * IVM_F_CONSUMERS) {
-                IvmPoint pt[IVM_F_DRAIN];
-                size_t idx[IVM_F_DRAIN];
-                uint32_t pix[IVM_F_DRAIN];
-                int kk[IVM_F_DRAIN];
-                bool act[IVM_F_DRAIN];
-                unsigned long long cw[IVM_F_DRAIN];
-                IvmRecord old[IVM_F_DRAIN];
-#pragma unroll
-                for (int u = 0; u < IVM_F_DRAIN; ++u) {
-                    const int i = i0 + u * IVM_F_CONSUMERS;
-                    act[u] = i < n;
-                    cw[u] = 0ull; idx[u] = 0; pix[u] = 0; kk[u] = 0;
-                    old[u].x = old[u].y = old[u].z = 0.f; old[u].meta = 0u;
-                    if (act[u]) {
-                        const uint32_t qp = q_pix[i];
-                        kk[u] = (int)(qp >> 24); pix[u] = qp & 0xFFFFFFu;
-                        const FusedSlot &sl = sh.slot[kk[u]];
-                        const int v = (int)pix[u] / P.W, uu = (int)pix[u] - v * P.W;
-                        act[u] = ivm_unproject(q_d[i], P.xs[uu], P.ys[v], sl.T, sl.h, P.half_res, pt[u]) == 1 &&
-                                 ivm_store_index(P, sl.origin_r, sl.origin_c, sl.b, pt[u].r, pt[u].c, idx[u]);
-                        if (act[u]) {
-                            cw[u] = ivm_cand_lookup(P, sl.b, (uint32_t)(idx[u] - (size_t)sl.b * P.SR * P.SC));
-                            old[u] = ivm_load_record(&P.store[idx[u]]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < IVM_F_DRAIN; ++u) {
-                    if (!act[u] || cw[u] != ivm_cand_key(P, pt[u].y, pix[u])) continue;
-                    FusedSlot &sl = sh.slot[kk[u]];
-                    const uint32_t label = q_lab[i0 + u * IVM_F_CONSUMERS];
-                    if (ivm_on_frame_edge(pt[u], loc)) {
-                        ivm_push_edge1<IvmAtomics>(P, sl.b, pix[u], pt[u], label, idx[u]);
-                        continue;
-                    }
-                    IvmBoxAcc acc;
-                    acc.clear();
-                    ivm_merge_record<IvmAtomics>(P, sl.b, idx[u], pt[u].r, pt[u].c, pt[u].x, pt[u].y, pt[u].z, label, old[u],
-                                                 sl.reset_stamp, sl.origin_r, sl.origin_c, acc);
-                    ++nlocal;
-                    if (acc.n) {  // a newly occupied cell: fold into the slot's box
-                        atomicMin(&sl.box[0], acc.rmin); atomicMax(&sl.box[1], acc.rmax);
-                        atomicMin(&sl.box[2], acc.cmin); atomicMax(&sl.box[3], acc.cmax);
-                        atomicAdd(&sl.box[4], 1);
-                    }
-                }
-            }
-            group_bar(1, IVM_F_CONSUMERS);
-            if (j0 == 0) CTA_STAMP(3, *(volatile int *)&sh.slot[7].box[4]);
-            if (tid < IVM_F_BR && sh.slot[tid].b >= 0 && sh.slot[tid].box[4] > 0) {
-                IvmBoxAcc t;
-                const FusedSlot &sl = sh.slot[tid];
-                t.rmin = sl.box[0]; t.rmax = sl.box[1]; t.cmin = sl.box[2]; t.cmax = sl.box[3]; t.n = sl.box[4];
-                ivm_box_flush<IvmAtomics>(&P.env[sl.b], t);
-            }
-            group_bar(1, IVM_F_CONSUMERS);
-            if (j0 == 0) CTA_STAMP(4, *(volatile unsigned *)&sh.qn);
-        }
-        const unsigned wl = warp_sum(nlocal);
-        if (wl && lane == 0) atomicAdd(&g->acc_local, (unsigned long long)wl);
-    }
-    if (!grid_barrier(P.bar, bar_base + 2u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
-    if (blockIdx.x == 0 && tid == 0) g->tstamp[2] = global_timer();
-    CTA_STAMP(5, sh.flag);
-
-    // ================================================================ phase C: edge fix-up
-    // C1 (CTA 0): stage-1 collision classes + merges, world bbox, edge-line segments
-    // C2 (all):   the live records on the edge lines, one cell per thread
-    // C3 (CTA 0): stage-2 classes, deletions, bookkeeping
-    IvmFixScratch S;
-    S.key = reinterpret_cast<unsigned long long *>(dyn);
-    S.xo = S.key + IVM_FIX_SMALL;
-    S.ord = reinterpret_cast<uint32_t *>(S.xo + IVM_FIX_SMALL);
-    S.cap = IVM_FIX_SMALL;
-    S.ibuf = reinterpret_cast<int32_t *>(S.ord + IVM_FIX_SMALL);
-    S.lbuf = reinterpret_cast<unsigned long long *>(S.ibuf + 8);
-    if (blockIdx.x == 0) ivm_fixup_stage1<IvmAtomics>(P, S, tid, blockDim.x);
-    if (!grid_barrier(P.bar, bar_base + 3u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
-    if (blockIdx.x == 0 && tid == 0) g->ttrace[3] = global_timer();
-    ivm_fixup_scan<IvmAtomics>(P, blockIdx.x, gridDim.x, tid, blockDim.x);
-    if (!grid_barrier(P.bar, bar_base + 4u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
-    if (blockIdx.x == 0) {
-        ivm_fixup_stage2<IvmAtomics>(P, S, tid, blockDim.x);
-        if (tid == 0) g->tstamp[3] = global_timer();
-    }
-    if (!grid_barrier(P.bar, bar_base + 5u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
-    if (blockIdx.x == 0 && tid == 0) g->tstamp[4] = global_timer();
-    CTA_STAMP(8, sh.flag);
-
-    // ================================================================ phase D: raster
-    if (warp < IVM_F_CONSUMERS / 32) {
-        const int group = tid / IVM_F_GROUP, gtid = tid - group * IVM_F_GROUP;
-        uint32_t *gsm = reinterpret_cast<uint32_t *>(dyn + (size_t)group * raster_group_bytes);
-        const int tiles_x = (P.C + P.tile_c - 1) / P.tile_c, tiles_y = (P.R + P.tile_r - 1) / P.tile_r;
-        const int per_env = tiles_x * tiles_y, units = P.B * per_env;
-        unsigned n_in = 0;
-        for (int u = blockIdx.x * 2 + group; u < units; u += 2 * gridDim.x) {
-            const int b = u / per_env, w = u - b * per_env;
-            const int ty = w / tiles_x, tx = w - ty * tiles_x;
-            raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in);
-        }
-        const unsigned wn = warp_sum(n_in);
-        if (wn && lane == 0) atomicAdd(&g->stats[IVM_STAT_IN], (unsigned long long)wn);
-    }
-    __syncthreads();
-    CTA_STAMP(9, 0);
-    if (tid == 0) atomicMax(&g->tstamp[5], global_timer());
-}
-
-// ------------------------------------------------------------------ overlapped persistent step kernel
-// Same phases as k_step_fused, but the class-score stream no longer sits BETWEEN the depth scatter
-// and the resolve: it runs beside them on its own warps, so that the only thing left on the critical
-// path after the last score plane has arrived is the merge of the last tile's winners.
-//   warps 0..NG/32-1  geometry:  G1 depth -> unproject -> RED.MAX into the candidate plane, valid pixels
-//                                   queued per tile in shared memory -> grid barrier 1 ->
-//                                G3 per tile: candidate word + world record + depth loads of the queued
-//                                   pixels go out, THEN the tile's labels are awaited (mbarrier), winners
-//                                   merge into the world store -> grid barrier 2
-//   warps 4..7 (PRED) argmax:    running argmax over the staged planes (4 pixels per thread, LDS.128),
-//                                labels to shared memory (for G3) and to labels_out
-//   warp 8 (PRED)     producer:  one lane keeps a 5 x 16 KB ring full with cp.async.bulk (TMA 1-D)
-// GT labels (PRED = false): there is no stream; warps 0..7 are all geometry warps.
-// Then edge fix-up and raster exactly as in k_step_fused.
+// ------------------------------------------------------------------ persistent step kernel
+// The whole map update as ONE cooperative launch of co-resident CTAs (2 per SM, 9 warps each).  CTA t owns the
+// 512-pixel tiles t, t + grid, ... (valid pixels cluster in a few image rows, so tiles are dealt round-robin).
+// The class-score stream does not sit between the depth scatter and the resolve: it runs beside them on its
+// own warps, so that the only thing left after the last score plane has arrived is the merge of the last
+// tile's winners.
+//   G1 scatter (warps 0..7 as two groups of four; a group takes whole tiles, 4 pixels per thread):
+//        depth -> world point -> filters -> half-cell; pass A prefetches the candidate word and the world record
+//        of every valid pixel into L2 and queues the pixel per tile in shared memory; pass B issues ONE 64-bit
+//        RED.MAX per valid pixel into the candidate plane.  With a score stream, group 1 (the argmax warps)
+//        scatters only the first ~quarter of the tiles and then starts consuming the ring.  -> grid barrier 1
+//   G3 resolve (warps 0..3 beside the stream, warps 0..7 with GT labels), per tile: candidate word + world
+//        record + depth of the queued pixels are loaded, THEN the tile's labels are awaited (mbarrier) and the
+//        winners merge into the world store.  -> grid barrier 2
+//   argmax (warps 4..7, score stream only): running argmax over the staged planes (4 pixels per thread,
+//        LDS.128), labels to shared memory (for G3) and to labels_out
+//   producer (warp 8, one lane): keeps a 3 x 16 KB ring full with cp.async.bulk (TMA 1-D copies, SASS UBLKCP),
+//        full/empty mbarriers; no block-wide barrier inside the stream
+//   edge fix-up beside the raster: a small team of CTAs (CTA 0 = stages 1 and 2, the team = edge-line scan)
+//        fixes the bounding-box edge collisions while every other CTA already rasters the ego tiles the fix-up
+//        cannot touch; two 128-thread groups per CTA, one ego tile each at a time, tiles handed out dynamically.
 #define IVM_O_THREADS 288
 #define IVM_O_TILE 512         // pixels per tile
 #define IVM_O_SP 8             // planes per ring stage (16 KB)
@@ -1346,6 +912,22 @@ __device__ __forceinline__ void ovl_tile_pixels(const IvmParams &P, OvlSlot &sl,
     }
 }
 
+// A frame winner on the frame bbox edge: the fix-up decides its cell later.  The ego tiles of the pending point
+// and of the record it may replace are rastered only after the fix-up.  Rare, so kept out of line.
+__device__ __noinline__ void ovl_defer_edge(const IvmParams &P, int b, uint32_t pix, float x, float y, float z, int32_t r, int32_t c,
+                                            uint32_t label, size_t idx, float ox, float oy, float oz, uint32_t ometa,
+                                            uint32_t reset_stamp, float h) {
+    IvmPoint pt;
+    pt.x = x; pt.y = y; pt.z = z; pt.r = r; pt.c = c;
+    IvmRecord old;
+    old.x = ox; old.y = oy; old.z = oz; old.meta = ometa;
+    ivm_push_edge1<IvmAtomics>(P, b, pix, pt, label, idx);
+    const float epx = P.pose[3 * b + 0], epz = P.pose[3 * b + 2];
+    const float ec = __ldcg(&P.cs[2 * b + 0]), es = __ldcg(&P.cs[2 * b + 1]);
+    ivm_mark_tile(P, b, pt.x, pt.y, pt.z, epx, h, epz, ec, es);
+    if (ivm_live(old.meta, reset_stamp)) ivm_mark_tile(P, b, old.x, old.y, old.z, epx, h, epz, ec, es);
+}
+
 // wait of a thread GROUP (named barrier 1, nthr threads, leader = thread 0) on the grid barrier
 __device__ __forceinline__ bool grid_wait_group(uint32_t *bar, uint32_t target, int *s_flag, int nthr) {
     if (threadIdx.x == 0) {
@@ -1392,7 +974,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     // tiles are dealt round-robin: tile = CTA + j * grid (valid pixels cluster in a few image rows)
     const int grid_n = (int)gridDim.x, cta = (int)blockIdx.x;
     const int my_tiles = (total - cta + grid_n - 1) / grid_n;
-    const bool keep_queue = my_tiles <= NSLOT;             // the queue built by G1 is still there in G3
+    const int nslot = (P.debug & 128) ? 2 : NSLOT;         // tiles per chunk (debug bit 128: tiny chunks, to test the multi-chunk path)
+    const bool keep_queue = my_tiles <= nslot;             // the queue built by G1 is still there in G3
     uint32_t *qcell = reinterpret_cast<uint32_t *>(dyn + RING_BYTES);
     uint16_t *qpix = reinterpret_cast<uint16_t *>(dyn + RING_BYTES + (size_t)NSLOT * IVM_O_TILE * 4);
     uint8_t *slab = dyn + RING_BYTES + (size_t)NSLOT * IVM_O_TILE * 6;
@@ -1408,7 +991,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     int kbase = 0, kstride = 1, nmine = 0;
     auto assign = [&](int cn) {
         if (PRED) {
-            const int a = (cn + 2) / 4;
+            int a = (cn + 2) / 4;
+            if ((P.debug >> 4) & 3) a = min((P.debug >> 4) & 3, cn);  // experiment: the argmax group's share
             kbase = g1 ? 0 : a; nmine = g1 ? a : cn - a; kstride = 1;
         } else {
             kbase = g1; kstride = 2; nmine = (cn - g1 + 1) / 2;
@@ -1417,7 +1001,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     // the first batch of depth loads goes out before anything else (ahead of the score stream's first 48 KB)
     OvlDepth<PX1> dv[IVM_O_SUB];
     if (tid < NG1) {
-        assign(min(NSLOT, my_tiles));
+        assign(min(nslot, my_tiles));
 #pragma unroll
         for (int m = 0; m < IVM_O_SUB; ++m) {
 #pragma unroll
@@ -1450,8 +1034,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         // ============================================================ G1: depth scatter (warps 0..7)
         int rmin = INT32_MAX, rmax = INT32_MIN, cmin = INT32_MAX, cmax = INT32_MIN;
         unsigned nvalid = 0;
-        for (int c0 = 0; c0 < my_tiles; c0 += NSLOT) {
-            const int cn = min(NSLOT, my_tiles - c0);
+        for (int c0 = 0; c0 < my_tiles; c0 += nslot) {
+            const int cn = min(nslot, my_tiles - c0);
             if (c0) {
                 group_bar(1, NG1);  // the previous chunk's slots are no longer read
                 assign(cn);
@@ -1629,8 +1213,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         const int32_t loc[4] = {__ldcg(&g->loc[0]), __ldcg(&g->loc[1]), __ldcg(&g->loc[2]), __ldcg(&g->loc[3])};
         unsigned nlocal = 0;
         int chunk = 0;
-        for (int c0 = 0; c0 < my_tiles; c0 += NSLOT, ++chunk) {
-            const int cn = min(NSLOT, my_tiles - c0);
+        for (int c0 = 0; c0 < my_tiles; c0 += nslot, ++chunk) {
+            const int cn = min(nslot, my_tiles - c0);
             if (!keep_queue) {
                 // more tiles than slots: rebuild this chunk's slots (from the published env state) and queues
                 group_bar(1, NG);
@@ -1712,13 +1296,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                     pt.r = sl.origin_r + (int32_t)(ce[u] >> 16); pt.c = sl.origin_c + (int32_t)(ce[u] & 0xFFFFu);
                     const uint32_t label = PRED ? (uint32_t)slab[k * IVM_O_TILE + px[u]] : lab[u];
                     if (ivm_on_frame_edge(pt, loc)) {
-                        ivm_push_edge1<IvmAtomics>(P, sl.b, pix, pt, label, ebase + ci[u]);
-                        // the fix-up decides this cell later: the ego tiles of the pending point and of the record it
-                        // may replace are rastered after the fix-up
-                        const float epx = P.pose[3 * sl.b + 0], epz = P.pose[3 * sl.b + 2];
-                        const float ec = __ldcg(&P.cs[2 * sl.b + 0]), es = __ldcg(&P.cs[2 * sl.b + 1]);
-                        ivm_mark_tile(P, sl.b, pt.x, pt.y, pt.z, epx, sl.h, epz, ec, es);
-                        if (ivm_live(old[u].meta, sl.reset_stamp)) ivm_mark_tile(P, sl.b, old[u].x, old[u].y, old[u].z, epx, sl.h, epz, ec, es);
+                        ovl_defer_edge(P, sl.b, pix, pt.x, pt.y, pt.z, pt.r, pt.c, label, ebase + ci[u], old[u].x, old[u].y, old[u].z,
+                                       old[u].meta, sl.reset_stamp, sl.h);
                         continue;
                     }
                     IvmBoxAcc acc;
@@ -1759,7 +1338,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         uint32_t round = 0;
         for (int j = 0; j < my_tiles; ++j) {
             const int tile = cta + j * grid_n;
-            const int ls = j % NSLOT, chunk = j / NSLOT;
+            const int ls = j % nslot, chunk = j / nslot;
             float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
             int a0 = 0, a1 = 0, a2 = 0, a3 = 0;
             for (int p0 = 0; p0 < ncls; p0 += IVM_O_SP) {
@@ -2127,9 +1706,7 @@ struct ivm_ctx {
     int bulk_attr_set;
     int num_sms;
     int coop;             // device supports cooperative launches
-    int fused_grid[2];    // co-resident CTAs of k_step_fused<false/true> (0 = not queried yet)
-    size_t fused_smem[2];
-    int ovl_grid[2];      // same for k_step_overlap<false/true>
+    int ovl_grid[2];      // co-resident CTAs of k_step_overlap<false/true> (0 = not queried yet)
     size_t ovl_smem[2];
     uint32_t bar_base;    // value of IvmGlobal.bar_count before the next fused launch
     uint32_t team_base;   // same for the fix-up team's arrival counter (k_step_overlap)
@@ -2379,48 +1956,11 @@ static int raster_max_rows(const IvmParams &P) {
 
 // The fused persistent kernel applies when the image tiles evenly and the inputs are aligned.
 static bool fused_applies(const ivm_ctx *ctx, const IvmParams &P, const float *depth, const uint8_t *labels, const float *logits) {
-    if (!ctx->coop || (ctx->cfg.reserved[0] != 0 && ctx->cfg.reserved[0] != 3)) return false;
+    if (!ctx->coop || ctx->cfg.reserved[0] != 0) return false;
     if (P.HW % IVM_F_TILE != 0 || (P.W & 1) || P.HW > (1 << 24)) return false;
     if (((uintptr_t)depth & 7) || ((uintptr_t)labels & 1) || (logits && ((uintptr_t)logits & 15))) return false;
     const size_t rb = 2 * raster_smem_bytes(P.tile_r, P.tile_c, raster_max_rows(P));
     return rb <= 96 * 1024;
-}
-
-static int launch_fused(ivm_ctx *ctx, IvmParams &P, const float *logits, int ncls, uint8_t *labels_out, int nenv_total,
-                        cudaStream_t st) {
-    const int pred = logits ? 1 : 0;
-    int max_rows = raster_max_rows(P);
-    int group_bytes = (int)raster_smem_bytes(P.tile_r, P.tile_c, max_rows);
-    size_t smem = (size_t)2 * group_bytes;
-    const size_t scratch = (size_t)IVM_F_BR * IVM_F_TILE * 9 + 1024;  // resolve queue (36 KB) > fix-up scratch (10.3 KB)
-    if (smem < scratch) smem = scratch;
-    if (pred) {
-        const size_t ring = (size_t)IVM_F_NSTAGE * IVM_F_SP * IVM_F_TILE * sizeof(float);
-        if (smem < ring) smem = ring;
-    }
-    const void *fn = pred ? (const void *)k_step_fused<true> : (const void *)k_step_fused<false>;
-    if (!ctx->fused_grid[pred] || ctx->fused_smem[pred] != smem) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(k_step_fused)");
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, IVM_F_THREADS, smem);
-        if (e != cudaSuccess) return cuda_fail(ctx, e, "occupancy(k_step_fused)");
-        if (per_sm < 1) { snprintf(ctx->err, sizeof(ctx->err), "k_step_fused does not fit on an SM"); return IVM_E_CUDA; }
-        if (per_sm > IVM_F_CTAS_PER_SM) per_sm = IVM_F_CTAS_PER_SM;
-        ctx->fused_grid[pred] = per_sm * ctx->num_sms;
-        ctx->fused_smem[pred] = smem;
-    }
-    long long tiles = (long long)P.B * (P.HW / IVM_F_TILE);
-    int grid = ctx->fused_grid[pred];
-    if (grid > tiles) grid = (int)tiles;
-    uint32_t bar_base = ctx->bar_base;
-    void *args[] = {(void *)&P, (void *)&logits, (void *)&ncls, (void *)&labels_out, (void *)&nenv_total,
-                    (void *)&bar_base, (void *)&max_rows, (void *)&group_bytes};
-    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(IVM_F_THREADS), args, smem, st);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaLaunchCooperativeKernel(k_step_fused)");
-    ctx->bar_base += 5u * (uint32_t)grid;
-    ctx->launches += 1;
-    return IVM_OK;
 }
 
 // The overlapped kernel additionally needs 4-pixel groups inside one image row, 16-byte aligned depth and
@@ -2522,13 +2062,6 @@ int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const
         T_END(1);
         return rc;
     }
-    if (fused_applies(ctx, P, depth, P.labels, logits)) {
-        T_BEGIN(1);
-        rc = launch_fused(ctx, P, logits, num_classes, labels_out, nenv, st);
-        T_END(1);
-        return rc;
-    }
-
     const bool vec4 = (P.W % 4 == 0) && (((uintptr_t)depth & 15) == 0) && (((uintptr_t)P.labels & 3) == 0) &&
                       (!logits || ((uintptr_t)logits & 15) == 0);
     const int vec = vec4 ? 4 : 1;

@@ -209,3 +209,52 @@ def test_smoke_entry():
     import __graft_entry__ as g
 
     g.smoke()
+
+
+@pytest.mark.parametrize("name", ["iid_f64", "scene_overlap", "identical_envs", "degenerate", "batch_shrink_grow", "predicted"])
+def test_step_kernel_multi_chunk_path(name, monkeypatch):
+    """Debug bit 128 makes the persistent step kernel hold only 2 tiles per CTA at a time, so that CTAs with more
+    tiles take the multi-chunk path (queues rebuilt in the resolve phase, label slots recycled between the argmax
+    and the resolve warps) -- the path a GPU takes with more than ~18 (scores) / ~37 (GT labels) 256x256 envs."""
+    monkeypatch.setenv("IVM_DEBUG_FLAGS", "128")
+    scn = load_golden(name)
+    cs, outs, sizes = _run_cuda(scn)
+    for t, (o, s) in enumerate(outs):
+        B = o.shape[0]
+        assert np.array_equal(o, scn["ref_occupancy"][t, :B]), f"occupancy differs at step {t}"
+        assert np.array_equal(s, scn["ref_semantic"][t, :B]), f"semantic differs at step {t}"
+    cs.mm.check_errors()
+    assert sizes == scn["ref_world_sizes"].tolist()
+    b, xyz, sem = cs.world()
+    assert np.array_equal(b, scn["ref_world_b"])
+    assert np.array_equal(xyz.view(np.uint32), scn["ref_world_xyz"].view(np.uint32))
+    assert np.array_equal(sem, scn["ref_world_sem"])
+
+
+def test_many_envs_against_oracle():
+    """48 envs of 128x128 depth (GT labels) and 24 envs with class scores: more tiles than co-resident CTAs, every
+    CTA holds several tiles of different envs; envs reset at different steps."""
+    from ivlnce_b200.synthetic import ScenarioConfig, make_scenario
+    from oracle.oracle import OracleMapper, argmax_labels
+    from scenarios import _wrap
+
+    for pred, nenv in ((False, 48), (True, 24)):
+        c = ScenarioConfig(num_envs=nenv, height=128, width=128, steps=5, resolution=0.1, num_labels=13,
+                           reset_steps={2: [1, 7], 3: [0]}, seed=91 + nenv)
+        scn = _wrap(c, make_scenario(c))
+        if pred:
+            rng = np.random.default_rng(6)
+            lg = np.round(rng.standard_normal((c.steps, c.num_envs, 13, 128, 128)).astype(np.float32) * 4) / 4
+            scn["logits"] = lg
+            scn["labels_for_map"] = np.stack([argmax_labels(lg[t]) for t in range(c.steps)])
+            scn["labels"] = scn["labels_for_map"]
+        orc = OracleMapper(c.height, c.width, c.vfov_radians, c.map_meters, c.map_meters, c.resolution)
+        ref_outs, _ = run_mapper(orc.step, scn)
+        cs, outs, _ = _run_cuda(scn, store_cells=1024)
+        for t in range(c.steps):
+            assert np.array_equal(outs[t][0], ref_outs[t][0]), (pred, t)
+            assert np.array_equal(outs[t][1], ref_outs[t][1]), (pred, t)
+        b1, x1, s1 = orc.world()
+        b2, x2, s2 = cs.world()
+        assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(s1, s2)
+        cs.mm.check_errors()
