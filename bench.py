@@ -314,24 +314,23 @@ def main():
     _, stats = mm.status()
     fused = any(mm.phase_ns())
     phase_us = None
-    if fused:  # split inside the fused kernel: %globaltimer stamps of the phase boundaries, averaged over 32 steps
-        acc = np.zeros(5)
+    if fused:  # split inside the persistent kernel: %globaltimer stamps of the phase boundaries, averaged over 32 steps
+        acc = np.zeros(4)
         facc = np.zeros(7)
-        bacc = np.zeros(5)
         for _ in range(32):
             step(t); t += 1
-            ns = mm.phase_ns()
-            acc += np.diff(np.asarray(ns[:6], dtype=np.float64))
+            ns = np.asarray(mm.phase_ns()[:6], dtype=np.float64)
+            # 0 start, 1 grid barrier 1 passed (depth scatter done), 2 grid barrier 2 passed (score stream + resolve
+            # done), 3 edge fix-up done on CTA 0 (runs beside the raster), 5 end (max over CTAs)
+            acc += np.asarray([ns[1] - ns[0], ns[2] - ns[1], ns[5] - ns[2], ns[3] - ns[2]])
             tr = mm.fixup_trace_ns()
             facc += np.diff(np.asarray([ns[2]] + tr[:7], dtype=np.float64))
-            bacc += np.diff(np.asarray([ns[1]] + tr[8:12] + [ns[2]], dtype=np.float64))
-        phase_us = dict(zip(["ingest_scatter", "resolve", "edge_fixup", "raster_release", "raster"], (acc / 32e3).tolist()))
-        phase_us["fixup_split_cta0"] = dict(zip(["enter", "stage1", "bbox_segments", "grid_barrier", "edge_scan+grid_barrier",
+        phase_us = dict(zip(["scatter", "stream+resolve", "raster_beside_fixup", "fixup_cta0"], (acc / 32e3).tolist()))
+        phase_us["fixup_split_cta0"] = dict(zip(["enter", "stage1", "bbox_segments", "stage1_flag", "team_scan",
                                                  "stage2", "publish"], (facc / 32e3).tolist()))
-        phase_us["resolve_split_cta0"] = dict(zip(["slot_setup", "filter", "drain", "box_flush", "grid_barrier"], (bacc / 32e3).tolist()))
         phase_us["edge_entries"] = {"e1": int(stats[4]), "e2": int(stats[5]), "merged_total": int(stats[6]),
                                     "scan_segments": int(stats[7]) >> 32, "scan_cells": int(stats[7]) & 0xFFFFFFFF}
-    names_k = ["prep", "step_fused" if fused else "ingest_scatter", "ingest_resolve", "edge_fixup", "raster"]
+    names_k = ["prep", "step_overlap" if fused else "ingest_scatter", "ingest_resolve", "edge_fixup", "raster"]
     per_kernel = {n: (stage_ms[i] / max(stage_n[i], 1)) for i, n in enumerate(names_k)}
     dom = max(per_kernel, key=per_kernel.get)
     HW = cfg["H"] * cfg["W"]
@@ -341,7 +340,7 @@ def main():
     bytes_in = HW * 4 + (HW * 4 * cfg["classes"] if cfg["pred"] else HW)
     bytes_frame = bytes_in + 2 * R * R + 16 * (2 * p_local + p_in)
     kernel_bytes = {  # per launch (B env-frames); see DESIGN.md "Kernels"
-        "step_fused": B * bytes_frame,
+        "step_overlap": B * bytes_frame,
         "ingest_scatter": B * (bytes_in + (HW if cfg["pred"] else 0)),
         "ingest_resolve": B * (HW * 5 + 16 * 2 * p_local),
         "raster": B * (16 * p_in + 2 * R * R),
@@ -370,7 +369,8 @@ def main():
     if phase_us is not None:
         roofline["phase_us"] = phase_us
         ing = B * (bytes_in + (HW if cfg["pred"] else 0))
-        roofline["ingest_phase_gbs"] = ing / (phase_us["ingest_scatter"] * 1e-6) / 1e9 if phase_us["ingest_scatter"] > 0 else None
+        t_in = phase_us["scatter"] + phase_us["stream+resolve"]  # every input byte is read between the start and grid barrier 2
+        roofline["ingest_phase_gbs"] = ing / (t_in * 1e-6) / 1e9 if t_in > 0 else None
 
     # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region
     e2e = None
@@ -458,7 +458,7 @@ def main():
                 "warmup": max(Wm, 3), "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
                 "gpu_launches": int(launches), "roofline": roofline}
-        line["config"]["step"] = ("one fused persistent kernel per step" if fused else "four kernels per step") + f" (variant {args.variant})"
+        line["config"]["step"] = ("one persistent kernel per step (k_step_overlap)" if fused else "four kernels per step") + f" (variant {args.variant})"
         if e2e is not None:
             line["e2e"] = e2e
         if cpu is not None:
