@@ -52,8 +52,11 @@ typedef struct ivm_config {
     int32_t mode;         /* 0 = iterative (depth ingested every step), 1 = known map */
     int64_t known_capacity; /* known mode: max points per env */
     int32_t tile_rows, tile_cols;   /* ego tile per raster CTA; 0 = choose */
-    int32_t reserved[4];  /* [0] step variant: 0 = auto (fused persistent kernel when it applies), 1 = four
-                           * kernels with register-staged score loads, 2 = four kernels with the bulk-async ring */
+    int32_t reserved[4];  /* [0] step variant: 0 = auto (the persistent step kernel when it applies), 1 = four
+                           * kernels with register-staged score loads, 2 = four kernels with the bulk-async ring;
+                           * [1] profiling / test switches of the persistent kernel (0 in production; bit 128 =
+                           * two tiles per chunk, exercises the multi-chunk path); [2] 2 = stage raster tiles in
+                           * shared memory with cp.async (measured slower; off by default) */
 } ivm_config;
 
 typedef struct ivm_status {
@@ -116,24 +119,25 @@ int ivm_read_status(ivm_ctx *ctx, ivm_status *host_out, ivm_stream_t stream);
 /* Per-kernel device timing: when enabled, CUDA events bracket each kernel of the next
  * steps; ivm_stage_times returns the accumulated milliseconds per stage since the last
  * reset (synchronises the events).  Stages: 0 prep, 1 ingest-scatter, 2 ingest-resolve,
- * 3 edge fix-up, 4 raster.  When a step runs as the single fused persistent kernel
+ * 3 edge fix-up, 4 raster.  When a step runs as the single persistent kernel
  * (config.reserved[0] == 0 and the image tiles evenly), the whole step is booked under
  * stage 1 and stages 2-4 stay empty; ivm_read_phase_ns gives the split inside it. */
 int ivm_set_timing(ivm_ctx *ctx, int32_t enabled);
 int ivm_stage_times(ivm_ctx *ctx, float *ms_out5, int32_t *launches_out5, int32_t reset);
 
-/* Fused step kernel only: %globaltimer (ns) at the phase boundaries of the LAST step --
- * [0] start, [1] ingest-scatter done, [2] resolve done, [3] edge fix-up done, [4] raster
- * released, [5] end (max over CTAs), [6..7] unused; [8..23] milestones inside the edge
- * fix-up (start, stage-1 classes, stage-1 merges, bbox + segments, edge-line scan, stage-2
- * classes, end; rest unused).  [0..7] are all zero if the last step took the multi-kernel
- * path.  `ns_out24` has room for 24 values.  Synchronises `stream`. */
+/* Persistent step kernel only: %globaltimer (ns) at the phase boundaries of the LAST step --
+ * [0] start, [1] grid barrier 1 passed (depth scatter done), [2] grid barrier 2 passed (score stream and
+ * resolve done), [3] edge fix-up done on CTA 0 (it runs beside the raster), [4] raster release issued,
+ * [5] end (max over CTAs), [6..7] unused; [8..23] milestones inside the edge fix-up (start, stage-1 classes +
+ * merges, bbox + segments, scan start, stage-2 start, stage-2 classes, end; rest unused).  [0..7] are all
+ * zero if the last step took the multi-kernel path.  `ns_out24` has room for 24 values.  Synchronises `stream`. */
 int ivm_read_phase_ns(ivm_ctx *ctx, uint64_t *ns_out24, ivm_stream_t stream);
 
-/* Fused step kernel only: per-CTA timeline of the LAST step, 16 %globaltimer values (ns) per CTA
- * for the first `num_ctas` CTAs (<= 1024): [0] resolve start, [1] slots ready, [2] filter done,
- * [3] drain done, [4] boxes flushed, [5] past the grid barrier, [6] ingest done, [7] kernel start,
- * [8] raster start, [9] end; rest unused.  Synchronises `stream`. */
+/* Persistent step kernel only: per-CTA timeline of the LAST step, 16 %globaltimer values (ns) per CTA for the
+ * first `num_ctas` CTAs (<= 1024): [7] kernel start, [1] slots prepared, [2] scatter passes done, [12] argmax
+ * group's scatter share done, [10] arrived at grid barrier 1, [0] barrier 1 passed, [3] resolve done,
+ * [6] argmax warps done, [5] barrier 2 passed, [11] first raster pass done, [8] released, [9] end; rest
+ * unused.  Synchronises `stream`. */
 int ivm_read_cta_trace(ivm_ctx *ctx, uint64_t *ns_out, int32_t num_ctas, ivm_stream_t stream);
 
 /* Number of kernels launched by this context so far. */
