@@ -900,6 +900,8 @@ struct IvmTileGeom {
     float px, pz, c, s;
     float xe_lo, xe_hi, ze_lo, ze_hi;  // ego-frame metric bounds of the tile, with slack
     float hr;
+    float inv_hr, inv_a0, inv_a1;      // reciprocals used by ivm_row_span (spans are conservative bounds, not results:
+                                       // an ulp of difference against a true division disappears in the slack)
     int32_t row_lo, row_hi;            // absolute half-rows to visit
 };
 
@@ -907,6 +909,9 @@ IVM_HD void ivm_tile_geom(const IvmParams &P, float px, float pz, float c, float
                           IvmTileGeom &G) {
     const float slack = 2.0e-3f;  // metres; covers fp32 rounding of the reference transform (<1e-5 m at 100 m)
     G.px = px; G.pz = pz; G.c = c; G.s = s; G.hr = P.half_res;
+    G.inv_hr = 1.0f / P.half_res;
+    G.inv_a0 = fabsf(c) < 1.0e-6f ? 0.0f : 1.0f / c;
+    G.inv_a1 = fabsf(s) < 1.0e-6f ? 0.0f : 1.0f / (-s);
     G.xe_lo = ((float)c0 - 0.5f) * P.res - P.half_w - slack;
     G.xe_hi = ((float)c1 - 0.5f) * P.res - P.half_w + slack;
     G.ze_lo = ((float)r0 - 0.5f) * P.res - P.half_h - slack;
@@ -924,27 +929,26 @@ IVM_HD void ivm_tile_geom(const IvmParams &P, float px, float pz, float c, float
     G.row_hi = (fabsf(q1) < 1.0e9f) ? (int32_t)ceilf(q1) : -1;
 }
 
-// one slab  L <= a*x1 + b*z1 <= U  with z1 in [za, zb]: tighten [xlo, xhi]
-IVM_HD void ivm_slab(float a, float b, float L, float U, float za, float zb, float &xlo, float &xhi) {
+// one slab  L <= a*x1 + b*z1 <= U  with z1 in [za, zb]: tighten [xlo, xhi]  (inv_a = 1/a, or 0 if a ~ 0)
+IVM_HD void ivm_slab(float a, float inv_a, float b, float L, float U, float za, float zb, float &xlo, float &xhi) {
     const float bz0 = b * za, bz1 = b * zb;
     const float bzmin = fminf(bz0, bz1), bzmax = fmaxf(bz0, bz1);
-    if (fabsf(a) < 1.0e-6f) {
+    if (inv_a == 0.0f) {
         if (bzmax < L || bzmin > U) { xlo = 1.0f; xhi = -1.0f; }  // empty
         return;
     }
-    float lo = (L - bzmax) / a, hi = (U - bzmin) / a;
-    if (a < 0.0f) { lo = (U - bzmin) / a; hi = (L - bzmax) / a; }
-    xlo = fmaxf(xlo, lo); xhi = fminf(xhi, hi);
+    const float p = (L - bzmax) * inv_a, q = (U - bzmin) * inv_a;
+    xlo = fmaxf(xlo, a < 0.0f ? q : p); xhi = fminf(xhi, a < 0.0f ? p : q);
 }
 
 IVM_HD void ivm_row_span(const IvmTileGeom &G, int32_t rr, int32_t &clo, int32_t &chi) {
     // records of half-row rr have z/hr within rr +- 0.5 (rint of an fp32 quotient)
     const float za = ((float)rr - 0.55f) * G.hr - G.pz, zb = ((float)rr + 0.55f) * G.hr - G.pz;
     float xlo = -1.0e30f, xhi = 1.0e30f;
-    ivm_slab(G.c, G.s, G.xe_lo, G.xe_hi, za, zb, xlo, xhi);    // xe =  c*x1 + s*z1
-    ivm_slab(-G.s, G.c, G.ze_lo, G.ze_hi, za, zb, xlo, xhi);   // ze = -s*x1 + c*z1
+    ivm_slab(G.c, G.inv_a0, G.s, G.xe_lo, G.xe_hi, za, zb, xlo, xhi);    // xe =  c*x1 + s*z1
+    ivm_slab(-G.s, G.inv_a1, G.c, G.ze_lo, G.ze_hi, za, zb, xlo, xhi);   // ze = -s*x1 + c*z1
     if (!(xlo <= xhi)) { clo = 0; chi = -1; return; }
-    const float q0 = (xlo + G.px) / G.hr - 0.55f, q1 = (xhi + G.px) / G.hr + 0.55f;
+    const float q0 = (xlo + G.px) * G.inv_hr - 0.55f, q1 = (xhi + G.px) * G.inv_hr + 0.55f;
     clo = (q0 > -1.0e9f) ? (int32_t)floorf(q0) : -1000000000;
     chi = (q1 < 1.0e9f) ? (int32_t)ceilf(q1) : 1000000000;
 }

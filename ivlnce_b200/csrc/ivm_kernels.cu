@@ -541,6 +541,14 @@ __device__ __forceinline__ size_t raster_fixed_bytes_dev(int tile_r, int tile_c,
     return (((size_t)tile_r * tile_c * 5 + (size_t)max_rows * 8 + 16) + 15) & ~(size_t)15;
 }
 
+#define RTRACE_DECL unsigned long long rt_[4] = {0ull, 0ull, 0ull, 0ull}
+#define RTRACE(k)                                                                                          \
+    do {                                                                                                   \
+        if (!KNOWN && tid == 0 && bar_id == 2 && blockIdx.x < IVM_TRACE_CTAS) {                            \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(rt_[k]));                                     \
+            if ((k) > 0) P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + 12 + (k)] += rt_[k] - rt_[(k) - 1]; \
+        }                                                                                                  \
+    } while (0)
 // safe_only: the tile is rastered only if nothing under it can still be changed by the edge fix-up, i.e. no
 // frame-edge winner is pending in it (tile_dirty stamp) and its store footprint stays strictly inside the
 // env's bounding box (stage-2 collisions live on the bbox edge lines).  Returns false if the tile was skipped.
@@ -557,7 +565,9 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
     int32_t *s_maxlen = s_len + max_rows;
     uint8_t *socc = reinterpret_cast<uint8_t *>(s_maxlen + 4);
     const int r1 = min(r0 + tr, P.R), c1 = min(c0 + tc, P.C);
+    RTRACE_DECL;
     group_bar(bar_id, nthr);  // the group's previous tile has been written out
+    RTRACE(0);
     for (int i = tid; i < tr * tc; i += nthr) { skey[i] = 0u; socc[i] = 0; }
     if (tid == 0) { s_maxlen[0] = 0; s_maxlen[1] = 0; }
     const IvmEnv e = P.env[b];
@@ -591,6 +601,7 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
         if (__ldcg(&P.tile_dirty[(size_t)b * (tiles_x * tiles_y) + (r0 / P.tile_r) * tiles_x + c0 / P.tile_c]) == P.step) s_maxlen[1] = 1;
     }
     group_bar(bar_id, nthr);
+    RTRACE(1);
     if (!KNOWN && safe_only && s_maxlen[1]) return false;  // uniform
     bool staged = false;
     if (!KNOWN && stage_cap > 0) {
@@ -662,10 +673,18 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
                 asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(env_store + first + seg * 8));
             }
         }
-        for (int i = hw; i < nrows; i += nhw) {
-            const int len = s_len[i];
-            const uint32_t rowbase = (uint32_t)(row_lo + i - e.origin_r) * (uint32_t)P.SC + (uint32_t)(s_clo[i] - e.origin_c);
-            for (int k0 = 0; k0 < len; k0 += 16 * IVM_RASTER_MLP) {
+        // the two half-warps of a warp take neighbouring half-rows and stay in step (warp-uniform loops), so that
+        // a 16-record chunk neither of them has is skipped by the whole warp: spans under a rotated tile are
+        // 1..45 records long, and a chunk costs ~80 instructions per lane whether its lanes hold records or not.
+        // (Measured: prefetching the next rows' records while a batch is evaluated does not pay inside the
+        // 96-register budget of the persistent kernel -- the loop is bound by its dependent arithmetic.)
+        (void)hw; (void)nhw;
+        for (int i0 = 2 * warp; i0 < nrows; i0 += 2 * nwarps) {
+            const int i = i0 + (lane >> 4);
+            const int len = i < nrows ? s_len[i] : 0;
+            const int lenmax = max(len, __shfl_xor_sync(0xffffffffu, len, 16));
+            const uint32_t rowbase = len > 0 ? (uint32_t)(row_lo + i - e.origin_r) * (uint32_t)P.SC + (uint32_t)(s_clo[i] - e.origin_c) : 0u;
+            for (int k0 = 0; k0 < lenmax; k0 += 16 * IVM_RASTER_MLP) {
                 uint4 raw[IVM_RASTER_MLP];
                 bool have[IVM_RASTER_MLP];
 #pragma unroll
@@ -673,7 +692,7 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
                     const int off = k0 + 16 * u + l16;
                     have[u] = off < len;
                     raw[u] = make_uint4(0, 0, 0, 0);
-                    // L2-only load: in the fused kernel the records were written earlier in the same launch
+                    // L2-only load: in the persistent kernel the records were written earlier in the same launch
                     if (have[u]) {
                         const IvmRecord q = ivm_load_record(env_store + rowbase + off);
                         raw[u] = make_uint4(__float_as_uint(q.x), __float_as_uint(q.y), __float_as_uint(q.z), q.meta);
@@ -681,8 +700,9 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
                 }
 #pragma unroll
                 for (int u = 0; u < IVM_RASTER_MLP; ++u)
-                    raster_record(P, raw[u], have[u], e.reset_stamp, px, h, pz, c, s, r0, r1, c0, c1, tc,
-                                  rowbase + (uint32_t)(k0 + 16 * u + l16), skey, socc, n_in);
+                    if (k0 + 16 * u < lenmax)  // warp-uniform
+                        raster_record(P, raw[u], have[u], e.reset_stamp, px, h, pz, c, s, r0, r1, c0, c1, tc,
+                                      rowbase + (uint32_t)(k0 + 16 * u + l16), skey, socc, n_in);
             }
         }
     }
@@ -709,6 +729,7 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
         }
     }
     group_bar(bar_id, nthr);
+    RTRACE(2);
     const int wr = r1 - r0, wc = c1 - c0;
     for (int i = tid; i < wr * wc; i += nthr) {
         const int rr = i / wc, cc = i - rr * wc;
@@ -716,6 +737,7 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
         P.occ[o] = socc[rr * tc + cc];
         P.sem[o] = (uint8_t)(skey[rr * tc + cc] & 0xFFu);
     }
+    RTRACE(3);
     return true;
 }
 
@@ -1014,6 +1036,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         P.bar[IVM_O_TILE_CTR] = 2u * (gridDim.x - (gridDim.x > 1 ? (unsigned)team : 0u));  // raster tiles handed out statically
     }
     OVL_STAMP(7, 0);
+    if (tid == 0 && blockIdx.x < IVM_TRACE_CTAS) { for (int k = 13; k < 16; ++k) P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + k] = 0ull; }
     if (tid == 0) {
         if (PRED) {
             for (int s = 0; s < IVM_O_NSTAGE; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], NCW); }

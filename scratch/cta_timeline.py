@@ -20,6 +20,7 @@ for t in range(300, 300 + N):
     tr = mm.cta_trace_ns(296).astype(np.float64)
     t0 = tr[:, 7].min()
     rel = (tr[:, :16] - t0) / 1e3
+    rel[:, 13:16] = tr[:, 13:16] / 1e3
     acc = rel if acc is None else acc + rel
 acc /= N
 # stamps of k_step_overlap: 7 start, 10 G1 (scatter) done, 0 past barrier 1, 3 G3 (resolve) done, 6 argmax warps done,
@@ -32,3 +33,7 @@ d = lambda a, b: acc[:, a] - acc[:, b]
 for nm, a, b in [("G1 prep", 1, 7), ("G1 pixels", 2, 1), ("G1 flush", 10, 2), ("G1 work", 10, 7), ("barrier1 wait", 0, 10), ("G3 work", 3, 0), ("argmax total", 6, 7), ("G3 tail after argmax", 3, 6), ("barrier2 wait", 5, 3), ("safe raster / fix-up", 11, 5), ("release wait", 8, 11), ("D2 work", 9, 8)]:
     x = d(a, b)
     print(f"{nm:22s} min {x.min():6.2f} mean {x.mean():6.2f} max {x.max():6.2f}")
+
+for nm, k in [("raster: zero+geom+spans (sum over the group's tiles)", 13), ("raster: record loop", 14), ("raster: write-out", 15)]:
+    x = acc[1:, k]
+    print(f"{nm:55s} min {x.min():6.2f} mean {x.mean():6.2f} max {x.max():6.2f}")
