@@ -258,3 +258,55 @@ def test_many_envs_against_oracle():
         b2, x2, s2 = cs.world()
         assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(s1, s2)
         cs.mm.check_errors()
+
+
+def test_tour_accumulation_against_oracle():
+    """BASELINE config 3 shape, shortened: ONE env walks a coherent scene for 3 episodes x 40 steps with a single
+    reset at the tour start (iterative map), 128x128 depth, 0.05 m cells, into a 2048 x 2048 half-cell store."""
+    from ivlnce_b200.synthetic import ScenarioConfig, make_scenario
+    from oracle.oracle import OracleMapper
+    from scenarios import _wrap
+
+    c = ScenarioConfig(num_envs=1, height=128, width=128, steps=120, resolution=0.05, num_labels=27, depth_mode="scene",
+                       roam_radius=6.0, seed=301)
+    scn = _wrap(c, make_scenario(c))
+    assert int((scn["masks"] == 0).sum()) == 1  # the tour is reset once, at its start
+    orc = OracleMapper(c.height, c.width, c.vfov_radians, c.map_meters, c.map_meters, c.resolution)
+    ref_outs, ref_sizes = run_mapper(orc.step, scn, world_fn=orc.world)
+    cs, outs, sizes = _run_cuda(scn, store_cells=2048)
+    for t in range(c.steps):
+        assert np.array_equal(outs[t][0], ref_outs[t][0]), t
+        assert np.array_equal(outs[t][1], ref_outs[t][1]), t
+    assert sizes == ref_sizes and sizes[-1] > sizes[10]  # the world cloud keeps growing over the tour
+    b1, x1, s1 = orc.world()
+    b2, x2, s2 = cs.world()
+    assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(s1, s2)
+    cs.mm.check_errors()
+
+
+def test_known_map_64_envs_against_oracle():
+    """BASELINE config 5 shape: known-map registration + rotated ego crop at 64 envs, 0.05 m cells (1024 x 1024
+    half-cell stores), 60 k-point scene clouds, scenes swapped mid-run."""
+    from ivlnce_b200.synthetic import ScenarioConfig, make_known_cloud, make_scenario
+    from oracle.oracle import OracleMapper
+    from scenarios import _wrap
+
+    T, B = 4, 64
+    c = ScenarioConfig(name="known64", num_envs=B, height=8, width=8, steps=T, resolution=0.05, env_spacing=0.0, seed=411)
+    s = make_scenario(c)
+    known = {f"scene{i}": make_known_cloud(60000, 16.0, 27, seed=5000 + i) for i in range(6)}
+    names = [[f"scene{(b + (t >= 2)) % 6}" for b in range(B)] for t in range(T)]
+    s["masks"][2, :] = 0  # every env moves to another scene at t = 2
+    scn = _wrap(c, s, mode="known")
+    scn["env_names"] = names
+    scn["known"] = known
+    del scn["depth"], scn["labels"]
+    orc = OracleMapper(c.height, c.width, c.vfov_radians, c.map_meters, c.map_meters, c.resolution, mode="known",
+                       known_clouds=known)
+    ref_outs, _ = run_mapper(orc.step, scn)
+    cs, outs, _ = _run_cuda(scn, store_cells=1024)
+    for t in range(T):
+        assert np.array_equal(outs[t][0], ref_outs[t][0]), t
+        assert np.array_equal(outs[t][1], ref_outs[t][1]), t
+        assert outs[t][0].any()
+    cs.mm.check_errors()
