@@ -449,10 +449,22 @@ IVM_HD double ivm_cos(double a) { return cos(a); }
 IVM_HD double ivm_sin(double a) { return sin(a); }
 IVM_HD float ivm_cos(float a) { return cosf(a); }
 IVM_HD float ivm_sin(float a) { return sinf(a); }
+// both at once: on the device sincos() shares the argument reduction of sin() and cos() and evaluates the same
+// two polynomials, so the values are the ones sin() / cos() return (checked bitwise on the GPU by
+// tests/test_gpu_parity.py::test_device_trig_f64_matches and the kernel-trig parity tests)
+#if defined(__CUDA_ARCH__)
+IVM_HD void ivm_sincos(double a, double &sn, double &cs) { sincos(a, &sn, &cs); }
+IVM_HD void ivm_sincos(float a, float &sn, float &cs) { sincosf(a, &sn, &cs); }
+#else
+IVM_HD void ivm_sincos(double a, double &sn, double &cs) { sn = sin(a); cs = cos(a); }
+IVM_HD void ivm_sincos(float a, float &sn, float &cs) { sn = sinf(a); cs = cosf(a); }
+#endif
 template <class F>
 IVM_HD void ivm_pose_matrices_t(const float *pose, F elevation, F heading, float *T, float *cs) {
     const F ex = elevation + (F)3.141592653589793238462643383279502884;
-    const F cx = ivm_cos(ex), sx = ivm_sin(ex), cy = ivm_cos(heading), sy = ivm_sin(heading);
+    F cx, sx, cy, sy;
+    ivm_sincos(ex, sx, cx);
+    ivm_sincos(heading, sy, cy);
     T[0] = (float)cy; T[1] = (float)(sx * sy); T[2] = (float)(cx * sy); T[3] = pose[0];
     T[4] = 0.0f;      T[5] = (float)cx;        T[6] = (float)(-sx);     T[7] = pose[1];
     T[8] = (float)(-sy); T[9] = (float)(cy * sx); T[10] = (float)(cy * cx); T[11] = pose[2];

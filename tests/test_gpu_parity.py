@@ -250,14 +250,17 @@ def test_many_envs_against_oracle():
             scn["labels"] = scn["labels_for_map"]
         orc = OracleMapper(c.height, c.width, c.vfov_radians, c.map_meters, c.map_meters, c.resolution)
         ref_outs, _ = run_mapper(orc.step, scn)
-        cs, outs, _ = _run_cuda(scn, store_cells=1024)
-        for t in range(c.steps):
-            assert np.array_equal(outs[t][0], ref_outs[t][0]), (pred, t)
-            assert np.array_equal(outs[t][1], ref_outs[t][1]), (pred, t)
         b1, x1, s1 = orc.world()
-        b2, x2, s2 = cs.world()
-        assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(s1, s2)
-        cs.mm.check_errors()
+        # "host": pose matrices from the host's libm; "kernel": derived in the kernel's prep phase (sincos in f64) --
+        # the world records (their x / z bits come straight from the matrix entries) must agree bitwise either way
+        for trig in ("host", "kernel"):
+            cs, outs, _ = _run_cuda(scn, store_cells=1024, trig=trig)
+            for t in range(c.steps):
+                assert np.array_equal(outs[t][0], ref_outs[t][0]), (pred, trig, t)
+                assert np.array_equal(outs[t][1], ref_outs[t][1]), (pred, trig, t)
+            b2, x2, s2 = cs.world()
+            assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(s1, s2), trig
+            cs.mm.check_errors()
 
 
 def test_tour_accumulation_against_oracle():
