@@ -136,7 +136,7 @@ struct IvmGlobal {
     uint32_t any_dirty;
     uint32_t n_seg;
     uint32_t scan_chunks;         // chunks of IVM_SCAN_CHUNK cells per edge-line segment (longest segment)
-    uint32_t pad1[2];
+    uint32_t prev_n_seg, prev_scan_chunks;  // last step's edge-line segments (still in P.segs): prefetch hints for the scan
     unsigned long long acc_valid, acc_local;  // per-step accumulators (K1 / K2+F), published and zeroed by F
     unsigned long long stats[IVM_NSTATS];     // published figures of the last step; stats[IN] accumulates in K4
     // fused step kernel only
@@ -773,6 +773,28 @@ IVM_HD void ivm_fixup_scan(const IvmParams &P, int blk, int nblk, int tid, int n
     }
 }
 
+#if defined(__CUDACC__)
+// Pull LAST step's edge lines towards L2 (the world bbox rarely moves between steps, so they are almost always
+// this step's lines as well): run by the scan team while stage 1 of the fix-up is still busy.  Hints only.
+__device__ __forceinline__ void ivm_fixup_scan_prefetch(const IvmParams &P, int blk, int nblk, int tid, int nthreads) {
+    const IvmGlobal *g = P.g;
+    const int nseg = (int)g->prev_n_seg, nchunks = (int)g->prev_scan_chunks;
+    if (nseg <= 0 || nchunks <= 0 || nseg > 4 * P.maxB || (long long)nchunks * IVM_SCAN_CHUNK * nseg > (1ll << 24)) return;
+    const int span = nchunks * IVM_SCAN_CHUNK, total = span * nseg;
+    for (int i = blk * nthreads + tid; i < total; i += nblk * nthreads) {
+        const int q = i / span, off = i - q * span;
+        const int b = P.segs[4 * q + 0], is_col = P.segs[4 * q + 1], line = P.segs[4 * q + 2], len = P.segs[4 * q + 3];
+        if (b < 0 || b >= P.B || off >= len) continue;
+        if (!is_col && (off & 1)) continue;  // a row segment is contiguous: one prefetch per 32-byte sector
+        const IvmEnv &e = P.env[b];
+        const int32_t v = (is_col ? e.rmin : e.cmin) + off;
+        size_t idx;
+        if (!ivm_store_index(P, e.origin_r, e.origin_c, b, is_col ? v : line, is_col ? line : v, idx)) continue;
+        asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(&P.store[idx]));
+    }
+}
+#endif
+
 // The same scan by one thread block (or a few: block `blk` of `nblk`).  The segment headers (and what is needed of their envs) are staged in
 // block memory first; then every thread loads the metas of IVM_SCAN_MLP cells together (independent loads)
 // before any live cell is appended, so the whole scan costs a few memory round trips.
@@ -887,6 +909,7 @@ IVM_HD void ivm_fixup_stage2(const IvmParams &P, const IvmFixScratch &S, int tid
         g->stats[IVM_STAT_E1] = n1;
         g->stats[IVM_STAT_E2] = n2;
         g->stats[7] = ((unsigned long long)g->n_seg << 32) | ((unsigned long long)g->scan_chunks * IVM_SCAN_CHUNK);
+        g->prev_n_seg = g->n_seg; g->prev_scan_chunks = g->scan_chunks;
         ivm_reset_step_globals(g);
     }
     IVM_TRACE(g, 6, tid);

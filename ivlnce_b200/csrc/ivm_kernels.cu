@@ -506,7 +506,9 @@ __device__ __forceinline__ void group_bar(int bar_id, int nthr) {
         case 0: asm volatile("bar.sync 0, %0;" ::"r"(nthr) : "memory"); break;
         case 1: asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory"); break;
         case 2: asm volatile("bar.sync 2, %0;" ::"r"(nthr) : "memory"); break;
-        default: asm volatile("bar.sync 3, %0;" ::"r"(nthr) : "memory"); break;
+        case 3: asm volatile("bar.sync 3, %0;" ::"r"(nthr) : "memory"); break;
+        case 4: asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory"); break;
+        default: asm volatile("bar.sync 5, %0;" ::"r"(nthr) : "memory"); break;
     }
 }
 
@@ -803,27 +805,31 @@ __device__ __forceinline__ bool grid_barrier(uint32_t *bar, uint32_t target, int
 }
 
 // ------------------------------------------------------------------ persistent step kernel
-// The whole map update as ONE cooperative launch of co-resident CTAs (2 per SM, 9 warps each).  CTA t owns the
-// 512-pixel tiles t, t + grid, ... (valid pixels cluster in a few image rows, so tiles are dealt round-robin).
-// The class-score stream does not sit between the depth scatter and the resolve: it runs beside them on its
-// own warps, so that the only thing left after the last score plane has arrived is the merge of the last
-// tile's winners.
-//   G1 scatter (warps 0..7 as two groups of four; a group takes whole tiles, 4 pixels per thread):
+// The whole map update as ONE cooperative launch of co-resident CTAs.  With a class-score stream (PRED): 2 CTAs
+// per SM of 13 warps (8 geometry + 4 argmax + 1 producer); with GT labels: 3 CTAs per SM of 9 warps (8 geometry).
+// CTA t owns the 512-pixel tiles t, t + grid, ... (valid pixels cluster in a few image rows, so tiles are dealt
+// round-robin).  The score stream does not sit between the depth scatter and the resolve: it runs beside them on
+// its own warps from the first cycle, so that the only thing left after the last score plane has arrived is the
+// merge of the last tile's winners.
+//   G1 scatter (warps 0..7 as two groups of four; the groups take alternate tiles, 4 pixels per thread):
 //        depth -> world point -> filters -> half-cell; pass A prefetches the candidate word and the world record
 //        of every valid pixel into L2 and queues the pixel per tile in shared memory; pass B issues ONE 64-bit
-//        RED.MAX per valid pixel into the candidate plane.  With a score stream, group 1 (the argmax warps)
-//        scatters only the first ~quarter of the tiles and then starts consuming the ring.  -> grid barrier 1
-//   G3 resolve (warps 0..3 beside the stream, warps 0..7 with GT labels), per tile: candidate word + world
-//        record + depth of the queued pixels are loaded, THEN the tile's labels are awaited (mbarrier) and the
-//        winners merge into the world store.  -> grid barrier 2
-//   argmax (warps 4..7, score stream only): running argmax over the staged planes (4 pixels per thread,
-//        LDS.128), labels to shared memory (for G3) and to labels_out
-//   producer (warp 8, one lane): keeps a 3 x 16 KB ring full with cp.async.bulk (TMA 1-D copies, SASS UBLKCP),
-//        full/empty mbarriers; no block-wide barrier inside the stream
+//        RED.MAX per valid pixel into the candidate plane.  -> grid barrier 1
+//   G3 resolve (warps 0..7), per tile: candidate word + world record + depth of the queued pixels are loaded,
+//        THEN the tile's labels are awaited (mbarrier) and the winners merge into the world store.
+//        -> grid barrier 2
+//   argmax (warps 8..11, PRED): running argmax over the staged planes (4 pixels per thread, LDS.128), labels to
+//        shared memory (for G3) and to labels_out
+//   producer (warp 12, one lane, PRED): keeps a 3 x 16 KB ring full with cp.async.bulk (TMA 1-D copies, SASS
+//        UBLKCP), full/empty mbarriers; no block-wide barrier inside the stream
 //   edge fix-up beside the raster: a small team of CTAs (CTA 0 = stages 1 and 2, the team = edge-line scan)
 //        fixes the bounding-box edge collisions while every other CTA already rasters the ego tiles the fix-up
-//        cannot touch; two 128-thread groups per CTA, one ego tile each at a time, tiles handed out dynamically.
-#define IVM_O_THREADS 288
+//        cannot touch; 128-thread groups (3 per CTA with PRED, 2 with GT), one ego tile each at a time, tiles
+//        handed out dynamically.
+#define IVM_O_THREADS_GT 288    // GT labels: 8 geometry warps (+1 idle)
+#define IVM_O_THREADS_PRED 416  // score stream: 8 geometry warps + 4 argmax warps + 1 producer warp
+#define IVM_O_RGROUPS_PRED 3    // raster groups of 128 threads per CTA
+#define IVM_O_RGROUPS_GT 2
 #define IVM_O_TILE 512         // pixels per tile
 #define IVM_O_SP 8             // planes per ring stage (16 KB)
 #define IVM_O_NSTAGE 3         // ring depth: 48 KB per CTA; <= 64 KB per SM in flight keeps HBM saturated (measured) without
@@ -855,9 +861,9 @@ struct OvlShared {
     int flag;
     uint64_t full[IVM_O_NSTAGE], empty[IVM_O_NSTAGE];
     uint64_t lab_full[NSLOT], lab_empty[NSLOT];
-    int32_t next[2];           // raster: the group's next ego tile (dynamic distribution)
-    int32_t gflag[2];
-    int32_t pend[2][32];       // raster: tiles of the group that wait for the edge fix-up
+    int32_t next[4];           // raster: the group's next ego tile (dynamic distribution)
+    int32_t gflag[4];
+    int32_t pend[4][32];       // raster: tiles of the group that wait for the edge fix-up
 };
 
 static inline size_t ovl_stream_bytes(bool pred) {
@@ -977,12 +983,13 @@ __device__ __forceinline__ bool grid_wait_group(uint32_t *bar, uint32_t target, 
     } while (0)
 
 template <bool PRED>
-__global__ void __launch_bounds__(IVM_O_THREADS, PRED ? IVM_O_CTAS_PER_SM_PRED : IVM_O_CTAS_PER_SM_GT)
+__global__ void __launch_bounds__(PRED ? IVM_O_THREADS_PRED : IVM_O_THREADS_GT, PRED ? IVM_O_CTAS_PER_SM_PRED : IVM_O_CTAS_PER_SM_GT)
 k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out,
                int nenv_total, uint32_t bar_base, int max_rows, int raster_group_bytes, int stage_cap, int team, uint32_t team_base) {
     constexpr int NG1 = 256;                               // G1 (depth scatter): warps 0..7 in both modes
     constexpr int PX1 = 4;                                 // pixels per thread and tile in G1 (a tile = one group of 4 warps)
-    constexpr int NG = PRED ? 128 : 256;                   // G3 (resolve) threads: warps 0..3 beside the argmax warps, or 0..7
+    constexpr int NG = 256;                                // G3 (resolve) threads: warps 0..7
+    constexpr int RG = PRED ? IVM_O_RGROUPS_PRED : IVM_O_RGROUPS_GT;  // raster groups per CTA
     constexpr int NGW = NG / 32;
     constexpr int PX = IVM_O_TILE / NG;                    // refill pass of G3 (more tiles than slots)
     constexpr int NSLOT = PRED ? IVM_O_SLOTS_PRED : IVM_O_SLOTS_GT;
@@ -1006,21 +1013,10 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     const bool geo = warp < NGW;
     const int nstage = ((P.debug >> 8) & 15) ? min((P.debug >> 8) & 15, IVM_O_NSTAGE) : IVM_O_NSTAGE;  // experiment: shallower ring
 
-    // G1 runs as two groups of four warps that take whole tiles (4 pixels per thread and tile).  With a score
-    // stream, group 1 (the argmax warps) scatters only the first ~quarter of the CTA's tiles and then starts
-    // consuming the ring, so the stream is held up for a few microseconds only; group 0 does the rest.  With GT
-    // labels the two groups take alternate tiles.
+    // G1 runs as two groups of four warps that take whole tiles (4 pixels per thread and tile), alternately.
     const int g1 = warp >> 2, gt1 = tid & 127;
     int kbase = 0, kstride = 1, nmine = 0;
-    auto assign = [&](int cn) {
-        if (PRED) {
-            int a = (cn + 2) / 4;
-            if ((P.debug >> 4) & 3) a = min((P.debug >> 4) & 3, cn);  // experiment: the argmax group's share
-            kbase = g1 ? 0 : a; nmine = g1 ? a : cn - a; kstride = 1;
-        } else {
-            kbase = g1; kstride = 2; nmine = (cn - g1 + 1) / 2;
-        }
-    };
+    auto assign = [&](int cn) { kbase = g1; kstride = 2; nmine = (cn - g1 + 1) / 2; };
     // the first batch of depth loads goes out before anything else (ahead of the score stream's first 48 KB)
     OvlDepth<PX1> dv[IVM_O_SUB];
     if (tid < NG1) {
@@ -1034,7 +1030,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     }
     if (blockIdx.x == 0 && tid == 0) {
         g->tstamp[0] = global_timer(); g->tstamp[5] = 0ull;
-        P.bar[IVM_O_TILE_CTR] = 2u * (gridDim.x - (gridDim.x > 1 ? (unsigned)team : 0u));  // raster tiles handed out statically
+        P.bar[IVM_O_TILE_CTR] = (unsigned)RG * (gridDim.x - (gridDim.x > 1 ? (unsigned)team : 0u));  // raster tiles handed out statically
     }
     OVL_STAMP(7, 0);
     if (tid == 0 && blockIdx.x < IVM_TRACE_CTAS) { for (int k = 13; k < 16; ++k) P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + k] = 0ull; }
@@ -1204,7 +1200,6 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             }
         }
         OVL_STAMP(2, 0);
-        if (tid == NG) OVL_STAMP(12, NG);
         // frame bbox over ALL envs (mapper.py:465), one flush per CTA
         const unsigned wv = warp_sum(nvalid);
         if (wv) {
@@ -1214,10 +1209,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                 atomicAdd(&sh.valid, wv);
             }
         }
-        // every G1 thread's REDs, queue entries and the env publication are issued; the argmax warps only arrive
-        // (bar.arrive orders their earlier writes like bar.sync does) and go straight to the score stream
-        if (PRED && warp >= NGW) asm volatile("bar.arrive 1, %0;" ::"r"(NG1) : "memory");
-        else group_bar(1, NG1);
+        group_bar(1, NG1);  // every G1 thread's REDs, queue entries and the env publication are issued
         if (tid == 0) {
             if (sh.valid) {
                 atomicMin(&g->loc[0], sh.bb[0]); atomicMax(&g->loc[1], sh.bb[1]);
@@ -1459,8 +1451,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                 uint32_t v;
                 asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(word) : "memory");
                 if (equal ? v == want : (int32_t)(v - want) >= 0) break;
-                if (++spins > (1u << 22)) { atomicOr(&g->err, IVM_ERR_GRID_BARRIER); break; }
-                __nanosleep(spins < 8 ? 32 : 128);
+                if (++spins > (1u << 24)) { atomicOr(&g->err, IVM_ERR_GRID_BARRIER); break; }
             }
             __threadfence();
         };
@@ -1472,6 +1463,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                 asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(&P.bar[IVM_O_FIX_FLAG]), "r"(P.step) : "memory");
             }
         } else {
+            ivm_fixup_scan_prefetch(P, cta - 1, team - 1, tid, blockDim.x);  // while CTA 0 is in stage 1
             if (tid == 0) spin_until(&P.bar[IVM_O_FIX_FLAG], P.step, true);
             __syncthreads();
         }
@@ -1498,7 +1490,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             __syncthreads();
         }
     }
-    if (warp < 2 * IVM_F_GROUP / 32) {
+    if (warp < RG * IVM_F_GROUP / 32) {
         // group-level wait for the release (leader polls, named barrier of the group)
         auto wait_release = [&]() {
             if (gtid == 0) {
@@ -1519,7 +1511,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         unsigned n_in = 0;
         bool released = cta == 0;                         // CTA 0 has just run the fix-up itself
         int npend = 0;
-        int u = (cta - first) * 2 + group;
+        int u = (cta - first) * RG + group;
         if (cta < first) {                                // the fix-up team joins late: no static tile
             if (gtid == 0) sh.next[group] = (int32_t)atomicAdd(&P.bar[IVM_O_TILE_CTR], 1u);
             group_bar(2 + group, IVM_F_GROUP);
@@ -2011,7 +2003,7 @@ static int launch_overlap(ivm_ctx *ctx, IvmParams &P, const float *logits, int n
     if (stage_cap > cap_max) stage_cap = cap_max;
     if (stage_cap < 0 || ctx->cfg.reserved[2] != 2) stage_cap = 0;  // measured slower than the direct path (the raster is ALU-bound): opt-in only
     int group_bytes = (int)raster_smem_bytes(P.tile_r, P.tile_c, max_rows, stage_cap);
-    size_t smem = (size_t)2 * group_bytes;
+    size_t smem = (size_t)(pred ? IVM_O_RGROUPS_PRED : IVM_O_RGROUPS_GT) * group_bytes;
     const size_t scratch = (size_t)IVM_FIX_SMALL * 20 + 1024;  // fix-up scratch
     if (smem < scratch) smem = scratch;
     if (smem < ovl_stream_bytes(pred != 0)) smem = ovl_stream_bytes(pred != 0);
@@ -2020,7 +2012,7 @@ static int launch_overlap(ivm_ctx *ctx, IvmParams &P, const float *logits, int n
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(k_step_overlap)");
         int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, IVM_O_THREADS, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, pred ? IVM_O_THREADS_PRED : IVM_O_THREADS_GT, smem);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "occupancy(k_step_overlap)");
         if (per_sm < 1) { snprintf(ctx->err, sizeof(ctx->err), "k_step_overlap does not fit on an SM"); return IVM_E_CUDA; }
         const int want = pred ? IVM_O_CTAS_PER_SM_PRED : IVM_O_CTAS_PER_SM_GT;
@@ -2038,7 +2030,7 @@ static int launch_overlap(ivm_ctx *ctx, IvmParams &P, const float *logits, int n
     uint32_t team_base = ctx->team_base;
     void *args[] = {(void *)&P, (void *)&logits, (void *)&ncls, (void *)&labels_out, (void *)&nenv_total,
                     (void *)&bar_base, (void *)&max_rows, (void *)&group_bytes, (void *)&stage_cap, (void *)&team, (void *)&team_base};
-    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(IVM_O_THREADS), args, smem, st);
+    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(pred ? IVM_O_THREADS_PRED : IVM_O_THREADS_GT), args, smem, st);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaLaunchCooperativeKernel(k_step_overlap)");
     ctx->bar_base += 5u * (uint32_t)grid;
     if (team > 1) ctx->team_base += (uint32_t)team;
