@@ -837,7 +837,7 @@ __device__ __forceinline__ bool grid_barrier(uint32_t *bar, uint32_t target, int
 #define IVM_O_SLOTS_PRED 8     // tiles whose queue / labels a CTA holds at a time
 #define IVM_O_SLOTS_GT 16
 #define IVM_O_LOADB 8          // tiles whose depth loads are issued together (refill pass)
-#define IVM_O_SUB 4            // tiles a G1 group handles per pass (16 pixels per thread in flight)
+#define IVM_O_SUB 3            // tiles a G1 group handles per pass (12 pixels per thread in flight; no spills at 72 registers)
 #define IVM_O_CTAS_PER_SM_PRED 2  // with the score stream: two CTAs per SM (ring + queues = 76 KB each)
 #define IVM_O_CTAS_PER_SM_GT 3    // GT labels: every phase is latency-bound, a third CTA per SM (72 registers) pays: measured 85 -> 79 us at 32 envs
 #define IVM_O_TILE_CTR 40      // word of the barrier block (its second 128-byte line) that hands out raster tiles

@@ -37,3 +37,6 @@ for nm, a, b in [("G1 prep", 1, 7), ("G1 pixels", 2, 1), ("G1 flush", 10, 2), ("
 for nm, k in [("raster: zero+geom+spans (sum over the group's tiles)", 13), ("raster: record loop", 14), ("raster: write-out", 15)]:
     x = acc[1:, k]
     print(f"{nm:55s} min {x.min():6.2f} mean {x.mean():6.2f} max {x.max():6.2f}")
+
+order_end = np.argsort(-acc[:, 9])[:5]
+print("slowest CTAs (D.end):", [(int(i), round(float(acc[i, 9]), 2)) for i in order_end])
