@@ -484,11 +484,12 @@ IVM_HD_COLD void ivm_pose_matrices(const IvmParams &P, int b, float *T, float *c
 
 // Per-step scratch of IvmGlobal: reset once at context start and then by the fix-up program at
 // the end of every step (so that no kernel has to run before the ingest of the next step).
-IVM_HD void ivm_reset_step_globals(IvmGlobal *g) {
+IVM_HD void ivm_reset_step_globals(IvmGlobal *g, bool reset_rastered = true) {
     g->loc[0] = INT32_MAX; g->loc[1] = INT32_MIN; g->loc[2] = INT32_MAX; g->loc[3] = INT32_MIN;
     g->n_e1 = 0; g->n_e2 = 0; g->n_seg = 0; g->any_dirty = 0;
     g->acc_valid = 0; g->acc_local = 0;
-    g->stats[IVM_STAT_IN] = 0;
+    // (the persistent step kernel rasters BESIDE the fix-up: it zeroes this one at its start instead)
+    if (reset_rastered) g->stats[IVM_STAT_IN] = 0;
 }
 
 // ---------------------------------------------------------------------------
@@ -556,6 +557,8 @@ struct IvmFixScratch {
     uint32_t cap;
     int32_t *ibuf;                 // [8]: 0..3 world bbox, 4 segment count, 5 any-dirty, 6 longest segment
     unsigned long long *lbuf;      // [2]: 0 live-record total
+    uint32_t *release;             // persistent step kernel: counter that releases the deferred raster tiles as soon as
+    uint32_t release_add;          // the store is final (before the bookkeeping that follows); NULL elsewhere
 };
 
 // many entries: open-addressing hash in global memory
@@ -889,6 +892,16 @@ IVM_HD void ivm_fixup_stage2(const IvmParams &P, const IvmFixScratch &S, int tid
             if (S.ibuf[5]) ivm_rebuild_dirty_boxes<A>(P, tid, nthreads);
         }
         IVM_TRACE(g, 5, tid);
+    }
+#if defined(__CUDA_ARCH__)
+    // the world store and the env boxes are final from here on: let the deferred ego tiles go before the bookkeeping
+    A::sync();
+    if (S.release != nullptr && tid == 0) {
+        __threadfence();
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(S.release), "r"(S.release_add) : "memory");
+    }
+#endif
+    if (alive) {
         for (int b = tid; b < P.B; b += nthreads) {
             const int32_t c = P.env[b].count;
             if (c > 0) A::add_ull(&S.lbuf[0], (unsigned long long)c);
@@ -910,7 +923,7 @@ IVM_HD void ivm_fixup_stage2(const IvmParams &P, const IvmFixScratch &S, int tid
         g->stats[IVM_STAT_E2] = n2;
         g->stats[7] = ((unsigned long long)g->n_seg << 32) | ((unsigned long long)g->scan_chunks * IVM_SCAN_CHUNK);
         g->prev_n_seg = g->n_seg; g->prev_scan_chunks = g->scan_chunks;
-        ivm_reset_step_globals(g);
+        ivm_reset_step_globals(g, S.release == nullptr);
     }
     IVM_TRACE(g, 6, tid);
 }

@@ -490,6 +490,7 @@ __global__ void __launch_bounds__(1024) k_fixup(const __grid_constant__ IvmParam
     __shared__ int32_t s_i[8];
     IvmFixScratch S;
     S.key = s_key; S.xo = s_xo; S.ord = s_ord; S.cap = IVM_FIX_SMALL; S.ibuf = s_i; S.lbuf = s_l;
+    S.release = nullptr; S.release_add = 0u;
     ivm_fixup_program<IvmAtomics>(P, S, threadIdx.x, blockDim.x);
 }
 
@@ -1030,6 +1031,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     }
     if (blockIdx.x == 0 && tid == 0) {
         g->tstamp[0] = global_timer(); g->tstamp[5] = 0ull;
+        g->stats[IVM_STAT_IN] = 0ull;  // this step's rastered-record count (added to after grid barrier 2)
         P.bar[IVM_O_TILE_CTR] = (unsigned)RG * (gridDim.x - (gridDim.x > 1 ? (unsigned)team : 0u));  // raster tiles handed out statically
     }
     OVL_STAMP(7, 0);
@@ -1445,6 +1447,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         S.cap = IVM_FIX_SMALL;
         S.ibuf = reinterpret_cast<int32_t *>(S.ord + IVM_FIX_SMALL);
         S.lbuf = reinterpret_cast<unsigned long long *>(S.ibuf + 8);
+        S.release = P.bar; S.release_add = 3u * gridDim.x;  // stage 2 releases the deferred tiles itself
         auto spin_until = [&](uint32_t *word, uint32_t want, bool equal) {  // thread 0 only
             uint32_t spins = 0;
             for (;;) {
@@ -1481,12 +1484,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             }
             ivm_fixup_stage2<IvmAtomics>(P, S, tid, blockDim.x);
             __syncthreads();
-            if (tid == 0) {
-                g->tstamp[3] = global_timer();
-                __threadfence();
-                asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(P.bar), "r"(3u * gridDim.x) : "memory");
-                g->tstamp[4] = global_timer();
-            }
+            if (tid == 0) { g->tstamp[3] = global_timer(); g->tstamp[4] = g->tstamp[3]; }
             __syncthreads();
         }
     }

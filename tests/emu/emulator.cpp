@@ -228,6 +228,7 @@ int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels,
         unsigned long long lbuf[2];
         IvmFixScratch S;
         S.key = key.data(); S.xo = xo.data(); S.ord = ord.data(); S.cap = (uint32_t)m->fix_cap; S.ibuf = ibuf; S.lbuf = lbuf;
+        S.release = nullptr; S.release_add = 0u;
         ivm_fixup_program<IvmAtomics>(P, S, 0, 1);
     }
     // K4: raster

@@ -313,3 +313,30 @@ def test_known_map_64_envs_against_oracle():
         assert np.array_equal(outs[t][1], ref_outs[t][1]), t
         assert outs[t][0].any()
     cs.mm.check_errors()
+
+
+@pytest.mark.parametrize("variant", [0, 2])
+def test_step_statistics_match_oracle(variant):
+    """The counters the roofline is computed from -- valid pixels, frame de-dup survivors, live world records and
+    world records rastered into the ego windows -- equal the oracle's after every step (persistent kernel, where the
+    raster runs beside the fix-up, and four-kernel path)."""
+    from ivlnce_b200.synthetic import ScenarioConfig, make_scenario
+    from oracle.oracle import OracleMapper
+    from scenarios import _wrap
+    from cuda_stepper import CudaStepper
+
+    c = ScenarioConfig(num_envs=6, height=128, width=128, steps=6, resolution=0.05, num_labels=27, depth_mode="scene",
+                       reset_steps={3: [2]}, seed=512)
+    scn = _wrap(c, make_scenario(c))
+    orc = OracleMapper(c.height, c.width, c.vfov_radians, c.map_meters, c.map_meters, c.resolution)
+    cs = CudaStepper(scn["cfg"], max_envs=c.num_envs, scatter_variant=variant)
+    for t in range(c.steps):
+        a = (scn["masks"][t], scn["pose"][t], scn["orientation"][t])
+        kw = dict(depth=scn["depth"][t], labels=scn["labels"][t])
+        o1, s1 = orc.step(*a, **kw)
+        o2, s2 = cs.step(*a, **kw)
+        assert np.array_equal(o1, o2) and np.array_equal(s1, s2), t
+        flags, stats = cs.mm.status()
+        assert flags == 0
+        want = [orc.counters[k] for k in ("n_valid", "n_local", "n_world", "n_in")]
+        assert [int(v) for v in stats[:4]] == want, (t, stats[:4], want)
