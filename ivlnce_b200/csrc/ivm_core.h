@@ -99,7 +99,8 @@ struct IvmEnv {                   // 64 bytes
     int32_t rmin, rmax, cmin, cmax; // exact bbox of live records (absolute), if count>0
     int32_t dirty;                // bbox must be rebuilt from rowcount/colcount
     int32_t known_n;              // known-map mode: points in this env's CSR store
-    int32_t pad[6];
+    int32_t nb[4];                // bbox under reconstruction (ivm_rebuild_dirty_boxes): rmin, rmax, cmin, cmax
+    int32_t pad[2];
 };
 
 // A de-dup winner sitting on a bounding-box edge cell, waiting for the fix-up.
@@ -649,11 +650,14 @@ IVM_HD_COLD void ivm_scan_edge_cell(const IvmParams &P, int b, int32_t r, int32_
 }
 
 // exact bbox of the envs that lost records, from the per-row / per-column live counts
+// The new box is built in the scratch fields `nb` and then stored field by field: in the persistent step kernel
+// other CTAs raster ego tiles meanwhile and read rmin..cmax; they must see the old or the new value of a field
+// (both bound the live records; deletions only shrink the box), never an intermediate one.
 template <class A>
 IVM_HD_COLD void ivm_rebuild_dirty_boxes(const IvmParams &P, int tid, int nthreads) {
     for (int b = tid; b < P.B; b += nthreads) {
         IvmEnv *e = &P.env[b];
-        if (e->dirty) { e->rmin = INT32_MAX; e->rmax = INT32_MIN; e->cmin = INT32_MAX; e->cmax = INT32_MIN; }
+        if (e->dirty) { e->nb[0] = INT32_MAX; e->nb[1] = INT32_MIN; e->nb[2] = INT32_MAX; e->nb[3] = INT32_MIN; }
     }
     A::sync();
     const long long per_env = (long long)P.SR + P.SC;
@@ -663,14 +667,19 @@ IVM_HD_COLD void ivm_rebuild_dirty_boxes(const IvmParams &P, int tid, int nthrea
         if (!e->dirty) continue;
         const int j = (int)(i - (long long)b * per_env);
         if (j < P.SR) {
-            if (P.rowcount[(size_t)b * P.SR + j] > 0) { A::min_i(&e->rmin, e->origin_r + j); A::max_i(&e->rmax, e->origin_r + j); }
+            if (P.rowcount[(size_t)b * P.SR + j] > 0) { A::min_i(&e->nb[0], e->origin_r + j); A::max_i(&e->nb[1], e->origin_r + j); }
         } else {
             const int jc = j - P.SR;
-            if (P.colcount[(size_t)b * P.SC + jc] > 0) { A::min_i(&e->cmin, e->origin_c + jc); A::max_i(&e->cmax, e->origin_c + jc); }
+            if (P.colcount[(size_t)b * P.SC + jc] > 0) { A::min_i(&e->nb[2], e->origin_c + jc); A::max_i(&e->nb[3], e->origin_c + jc); }
         }
     }
     A::sync();
-    for (int b = tid; b < P.B; b += nthreads) P.env[b].dirty = 0;
+    for (int b = tid; b < P.B; b += nthreads) {
+        IvmEnv *e = &P.env[b];
+        if (!e->dirty) continue;
+        e->rmin = e->nb[0]; e->rmax = e->nb[1]; e->cmin = e->nb[2]; e->cmax = e->nb[3];
+        e->dirty = 0;
+    }
 }
 
 // F: the edge fix-up of both de-dup stages + bbox bookkeeping, in three parts so that the fused

@@ -1758,9 +1758,23 @@ static uint32_t edge_capacity(const ivm_config *c) {
 }
 static uint32_t hash_size(uint32_t ecap) { uint32_t h = 1024; while (h < 2 * ecap) h <<= 1; return h; }
 
+// Ego tile of one raster group.  0 = choose: the smallest tile with which all the context's envs together fit the
+// raster groups of one B200 in a single wave (2 x 148 x 3 groups, less the fix-up team's) -- tiles are handed out
+// one per group, so a second, partial wave costs more than larger tiles do.  Measured (us per step, 16 / 32 envs):
+// 16x16 65.5 / 78.5, 24x16 61.4 / 75.9, 32x16 61.4 / 80.6, 32x32 67.2 / 75.4; 1 env: 8x8 37.2, 16x16 39.6;
+// 64 envs: 32x32 159.6, 64x32 154.2.
 static void tile_dims(const ivm_config *c, int *tr_out, int *tc_out) {
     int tr = c->tile_rows, tc = c->tile_cols;
-    if (tr <= 0 || tc <= 0) { tr = 16; tc = 16; }
+    if (tr <= 0 || tc <= 0) {
+        static const int cand[][2] = {{8, 8}, {16, 16}, {24, 16}, {32, 16}, {32, 32}, {64, 32}};
+        const long long wave = 840;
+        tr = 64; tc = 32;
+        for (unsigned i = 0; i < sizeof(cand) / sizeof(cand[0]); ++i) {
+            const long long units = (long long)c->max_envs * ((c->map_rows + cand[i][0] - 1) / cand[i][0]) *
+                                    ((c->map_cols + cand[i][1] - 1) / cand[i][1]);
+            if (units <= wave) { tr = cand[i][0]; tc = cand[i][1]; break; }
+        }
+    }
     if (tr > c->map_rows) tr = c->map_rows;
     if (tc > c->map_cols) tc = c->map_cols;
     *tr_out = tr; *tc_out = tc;
