@@ -140,6 +140,14 @@ int ivm_read_phase_ns(ivm_ctx *ctx, uint64_t *ns_out24, ivm_stream_t stream);
  * unused.  Synchronises `stream`. */
 int ivm_read_cta_trace(ivm_ctx *ctx, uint64_t *ns_out, int32_t num_ctas, ivm_stream_t stream);
 
+/* Consumer-side epilogue: SemanticMapEncoder.generate_map_features
+ * (ivlnce_baselines/models/encoders/map_encoder.py:85-90) = cat(occupancy, one_hot(semantic, num_classes)) as
+ * float32 [B, 1 + num_classes, R, C].  occ, sem: u8 [B,R,C] (the outputs of a step); out: f32 device buffer.
+ * Stateless (no context).  err_flag_dev (u32, device, may be NULL): bit 0 is set if a semantic value is
+ * >= num_classes (F.one_hot raises there); the planes of such a cell are all zero. */
+int ivm_map_features(const uint8_t *occ, const uint8_t *sem, int32_t num_envs, int32_t rows, int32_t cols,
+                     int32_t num_classes, float *out, uint32_t *err_flag_dev, ivm_stream_t stream);
+
 /* Number of kernels launched by this context so far. */
 int64_t ivm_kernel_launches(const ivm_ctx *ctx);
 

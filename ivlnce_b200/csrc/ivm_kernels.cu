@@ -1710,6 +1710,43 @@ __global__ void k_rebase_env(IvmParams P) {
     if (b < P.maxB) P.env[b].reset_stamp = 1u;
 }
 
+// ------------------------------------------------------------------ map features
+// SemanticMapEncoder.generate_map_features (models/encoders/map_encoder.py:85-90): occupancy plane + one-hot of the
+// semantic map, float32 [B, 1 + K, R, C].  Pure write stream (4 (1 + K) bytes out per 2 bytes in): one thread per
+// 4 consecutive cells, one 128-bit store per thread and channel plane (coalesced), evict-first.
+__global__ void __launch_bounds__(256) k_map_features(const uint8_t *__restrict__ occ, const uint8_t *__restrict__ sem, long long ncell,
+                                                      int planes_cells, int num_classes, float *__restrict__ out,
+                                                      uint32_t *__restrict__ err) {
+    // ncell = B * R * C (multiple of 4 here), planes_cells = R * C (multiple of 4)
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i0 = q * 4;
+    if (i0 >= ncell) return;
+    const uchar4 o = *reinterpret_cast<const uchar4 *>(occ + i0);
+    const uchar4 l = *reinterpret_cast<const uchar4 *>(sem + i0);
+    const long long b = i0 / planes_cells, within = i0 - b * planes_cells;
+    float *dst = out + (b * (1 + num_classes)) * (long long)planes_cells + within;
+    __stcs(reinterpret_cast<float4 *>(dst), make_float4((float)o.x, (float)o.y, (float)o.z, (float)o.w));
+    for (int k = 0; k < num_classes; ++k) {
+        dst += planes_cells;
+        __stcs(reinterpret_cast<float4 *>(dst), make_float4(l.x == k ? 1.f : 0.f, l.y == k ? 1.f : 0.f, l.z == k ? 1.f : 0.f, l.w == k ? 1.f : 0.f));
+    }
+    // F.one_hot raises on class values >= num_classes: flag it (the planes of such a cell are all zero)
+    if (err != nullptr && (l.x >= num_classes || l.y >= num_classes || l.z >= num_classes || l.w >= num_classes)) atomicOr(err, 1u);
+}
+// scalar variant for maps whose plane size is not a multiple of 4 (or unaligned pointers)
+__global__ void __launch_bounds__(256) k_map_features_scalar(const uint8_t *__restrict__ occ, const uint8_t *__restrict__ sem, long long ncell,
+                                                             int planes_cells, int num_classes, float *__restrict__ out,
+                                                             uint32_t *__restrict__ err) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncell) return;
+    const int o = occ[i], l = sem[i];
+    const long long b = i / planes_cells, within = i - b * planes_cells;
+    float *dst = out + (b * (1 + num_classes)) * (long long)planes_cells + within;
+    dst[0] = (float)o;
+    for (int k = 0; k < num_classes; ++k) dst[(long long)(k + 1) * planes_cells] = l == k ? 1.f : 0.f;
+    if (err != nullptr && l >= num_classes) atomicOr(err, 1u);
+}
+
 // ------------------------------------------------------------------ host side
 struct ivm_ctx {
     ivm_config cfg;
@@ -2251,6 +2288,22 @@ int ivm_read_cta_trace(ivm_ctx *ctx, uint64_t *ns_out, int32_t num_ctas, ivm_str
     e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return cuda_fail(ctx, e, "read_cta_trace sync");
     return IVM_OK;
+}
+
+int ivm_map_features(const uint8_t *occ, const uint8_t *sem, int32_t num_envs, int32_t rows, int32_t cols, int32_t num_classes,
+                     float *out, uint32_t *err_flag_dev, ivm_stream_t stream) {
+    if (!occ || !sem || !out || num_envs < 1 || rows < 1 || cols < 1 || num_classes < 1 || num_classes > 255) return IVM_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long plane = (long long)rows * cols, ncell = plane * num_envs;
+    if (plane > (1ll << 30)) return IVM_E_INVALID;
+    const bool vec = (plane % 4 == 0) && (((uintptr_t)occ | (uintptr_t)sem) % 4 == 0) && ((uintptr_t)out % 16 == 0);
+    if (vec) {
+        const long long threads = ncell / 4;
+        k_map_features<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(occ, sem, ncell, (int)plane, num_classes, out, err_flag_dev);
+    } else {
+        k_map_features_scalar<<<(unsigned)((ncell + 255) / 256), 256, 0, st>>>(occ, sem, ncell, (int)plane, num_classes, out, err_flag_dev);
+    }
+    return cudaGetLastError() == cudaSuccess ? IVM_OK : IVM_E_CUDA;
 }
 
 int ivm_copy_state(ivm_ctx *dst, const ivm_ctx *src, ivm_stream_t stream) {

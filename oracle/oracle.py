@@ -205,3 +205,19 @@ def argmax_labels(scores: np.ndarray) -> np.ndarray:
     out = np.zeros((B, H, W), dtype=np.uint8)
     lib().orc_argmax_labels(_p(scores, ctypes.c_float), B, K, H * W, _p(out, ctypes.c_uint8))
     return out
+
+
+def map_features_oracle(occupancy: np.ndarray, semantic: np.ndarray, num_classes: int = 13) -> np.ndarray:
+    """CPU restatement of SemanticMapEncoder.generate_map_features
+    (ivlnce_baselines/models/encoders/map_encoder.py:85-90): cat(occupancy, one_hot(semantic)) as float32
+    [B, 1 + K, R, C].  Raises like F.one_hot if a class value is out of range.  Test infrastructure only."""
+    occupancy = np.asarray(occupancy)
+    semantic = np.asarray(semantic).astype(np.int64)
+    if semantic.size and semantic.max() >= num_classes:
+        raise RuntimeError("Class values must be smaller than num_classes.")
+    B, R, C = occupancy.shape
+    out = np.zeros((B, 1 + num_classes, R, C), dtype=np.float32)
+    out[:, 0] = occupancy.astype(np.float32)
+    for k in range(num_classes):
+        out[:, 1 + k] = (semantic == k).astype(np.float32)
+    return out
