@@ -1717,21 +1717,25 @@ __global__ void k_rebase_env(IvmParams P) {
 __global__ void __launch_bounds__(256) k_map_features(const uint8_t *__restrict__ occ, const uint8_t *__restrict__ sem, long long ncell,
                                                       int planes_cells, int num_classes, float *__restrict__ out,
                                                       uint32_t *__restrict__ err) {
-    // ncell = B * R * C (multiple of 4 here), planes_cells = R * C (multiple of 4)
+    // ncell = B * R * C (multiple of 4 here), planes_cells = R * C (multiple of 4); blockIdx.y = output channel
+    // (0 = occupancy, 1 + k = class k): the 2 input bytes per cell are re-read per channel from L1 / L2, the
+    // 4 output bytes per cell and channel are what the kernel is bound by
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long i0 = q * 4;
     if (i0 >= ncell) return;
-    const uchar4 o = *reinterpret_cast<const uchar4 *>(occ + i0);
-    const uchar4 l = *reinterpret_cast<const uchar4 *>(sem + i0);
+    const int ch = blockIdx.y;
     const long long b = i0 / planes_cells, within = i0 - b * planes_cells;
-    float *dst = out + (b * (1 + num_classes)) * (long long)planes_cells + within;
-    __stcs(reinterpret_cast<float4 *>(dst), make_float4((float)o.x, (float)o.y, (float)o.z, (float)o.w));
-    for (int k = 0; k < num_classes; ++k) {
-        dst += planes_cells;
-        __stcs(reinterpret_cast<float4 *>(dst), make_float4(l.x == k ? 1.f : 0.f, l.y == k ? 1.f : 0.f, l.z == k ? 1.f : 0.f, l.w == k ? 1.f : 0.f));
+    float *dst = out + (b * (1 + num_classes) + ch) * (long long)planes_cells + within;
+    if (ch == 0) {
+        const uchar4 o = *reinterpret_cast<const uchar4 *>(occ + i0);
+        __stcs(reinterpret_cast<float4 *>(dst), make_float4((float)o.x, (float)o.y, (float)o.z, (float)o.w));
+        return;
     }
+    const uchar4 l = *reinterpret_cast<const uchar4 *>(sem + i0);
+    const int k = ch - 1;
+    __stcs(reinterpret_cast<float4 *>(dst), make_float4(l.x == k ? 1.f : 0.f, l.y == k ? 1.f : 0.f, l.z == k ? 1.f : 0.f, l.w == k ? 1.f : 0.f));
     // F.one_hot raises on class values >= num_classes: flag it (the planes of such a cell are all zero)
-    if (err != nullptr && (l.x >= num_classes || l.y >= num_classes || l.z >= num_classes || l.w >= num_classes)) atomicOr(err, 1u);
+    if (ch == 1 && err != nullptr && (l.x >= num_classes || l.y >= num_classes || l.z >= num_classes || l.w >= num_classes)) atomicOr(err, 1u);
 }
 // scalar variant for maps whose plane size is not a multiple of 4 (or unaligned pointers)
 __global__ void __launch_bounds__(256) k_map_features_scalar(const uint8_t *__restrict__ occ, const uint8_t *__restrict__ sem, long long ncell,
@@ -2299,7 +2303,7 @@ int ivm_map_features(const uint8_t *occ, const uint8_t *sem, int32_t num_envs, i
     const bool vec = (plane % 4 == 0) && (((uintptr_t)occ | (uintptr_t)sem) % 4 == 0) && ((uintptr_t)out % 16 == 0);
     if (vec) {
         const long long threads = ncell / 4;
-        k_map_features<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(occ, sem, ncell, (int)plane, num_classes, out, err_flag_dev);
+        k_map_features<<<dim3((unsigned)((threads + 255) / 256), (unsigned)(1 + num_classes)), 256, 0, st>>>(occ, sem, ncell, (int)plane, num_classes, out, err_flag_dev);
     } else {
         k_map_features_scalar<<<(unsigned)((ncell + 255) / 256), 256, 0, st>>>(occ, sem, ncell, (int)plane, num_classes, out, err_flag_dev);
     }
