@@ -1028,6 +1028,11 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             for (int j = 0; j < PX1; ++j) dv[m].v[j] = 2.0f;
             if (m < nmine) dv[m] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + (kbase + kstride * m) * grid_n) * IVM_O_TILE + gt1 * PX1);
         }
+        // the later passes' depth (loaded when their turn comes) is pulled towards L2 now, ahead of the stream's traffic:
+        // one prefetch per 128-byte line
+        if ((lane & 7) == 0)
+            for (int m = IVM_O_SUB; m < nmine; ++m)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.depth + (size_t)(cta + (kbase + kstride * m) * grid_n) * IVM_O_TILE + gt1 * PX1));
     }
     if (blockIdx.x == 0 && tid == 0) {
         g->tstamp[0] = global_timer(); g->tstamp[5] = 0ull;
