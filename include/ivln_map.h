@@ -55,7 +55,7 @@ typedef struct ivm_config {
     int32_t reserved[4];  /* [0] step variant: 0 = auto (the persistent step kernel when it applies), 1 = four
                            * kernels with register-staged score loads, 2 = four kernels with the bulk-async ring;
                            * [1] profiling / test switches of the persistent kernel (0 in production; bit 128 =
-                           * two tiles per chunk, exercises the multi-chunk path); [2] 2 = stage raster tiles in
+                           * two tiles per chunk, exercises the multi-chunk path; bits 8..11 = ring depth); [2] 2 = stage raster tiles in
                            * shared memory with cp.async (measured slower; off by default) */
 } ivm_config;
 

@@ -913,9 +913,9 @@ __device__ __forceinline__ void ovl_tile_pixels(const IvmParams &P, OvlSlot &sl,
         okv[j] = true; cell[j] = ((uint32_t)rr << 16) | (uint32_t)cc;
         if (SCATTER) {
             const uint32_t ci = (uint32_t)rr * (uint32_t)P.SC + (uint32_t)cc;
-            if (!(P.debug & 1)) ivm_cand_insert<IvmAtomics>(P, sl.b, ci, ivm_cand_key(P, p.y, (uint32_t)(pix0 + j)));
+            ivm_cand_insert<IvmAtomics>(P, sl.b, ci, ivm_cand_key(P, p.y, (uint32_t)(pix0 + j)));
             // the resolve will read-modify-write this cell's world record: pull it into L2 now
-            if (!(P.debug & 2)) asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.store[(size_t)sl.b * P.SR * P.SC + ci]));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.store[(size_t)sl.b * P.SR * P.SC + ci]));
             rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
             ++nvalid;
         }
