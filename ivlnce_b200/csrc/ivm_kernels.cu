@@ -1812,7 +1812,7 @@ static uint32_t hash_size(uint32_t ecap) { uint32_t h = 1024; while (h < 2 * eca
 static void tile_dims(const ivm_config *c, int *tr_out, int *tc_out) {
     int tr = c->tile_rows, tc = c->tile_cols;
     if ((tr <= 0 || tc <= 0) && c->mode == 1) {
-        tr = 32; tc = 32;  // known-map mode: stand-alone raster kernel, no wave to fit (64 envs: 8x8 128, 16x16 94, 32x32 88, 64x32 99 us)
+        tr = 32; tc = 32;  // known-map mode: stand-alone raster kernel, no wave to fit (64 envs: 8x8 128, 16x16 94, 32x32 88-94, 64x32 99 us)
     } else if (tr <= 0 || tc <= 0) {
         static const int cand[][2] = {{8, 8}, {16, 16}, {24, 16}, {32, 16}, {32, 32}, {64, 32}};
         const long long wave = 840;
