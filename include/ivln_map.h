@@ -56,7 +56,9 @@ typedef struct ivm_config {
                            * kernels with register-staged score loads, 2 = four kernels with the bulk-async ring;
                            * [1] profiling / test switches of the persistent kernel (0 in production; bit 128 =
                            * two tiles per chunk, exercises the multi-chunk path; bits 8..11 = ring depth); [2] 2 = stage raster tiles in
-                           * shared memory with cp.async (measured slower; off by default) */
+                           * shared memory with cp.async (measured slower; off by default);
+                           * [3] test switch: period of the candidate-plane stamp (0 = the longest the pixel index leaves
+                           * room for, 65 535 steps at 256x256; the plane is cleared once per period) */
 } ivm_config;
 
 typedef struct ivm_status {
@@ -153,6 +155,10 @@ int64_t ivm_kernel_launches(const ivm_ctx *ctx);
 
 /* Rewrites all live stamps to 1 (call when IVM_E_STEP_OVERFLOW is returned). */
 int ivm_rebase_stamps(ivm_ctx *ctx, ivm_stream_t stream);
+
+/* Test hook: sets the 24-bit step counter of a context that has not stepped yet (so that a test can reach the
+ * IVM_E_STEP_OVERFLOW / ivm_rebase_stamps path without 2^24 calls). */
+int ivm_debug_set_step(ivm_ctx *ctx, uint32_t step);
 
 /* Copies the whole map state of `src` into `dst` (same config except dst.max_envs >=
  * src.max_envs; dst freshly created over a zero-filled workspace).  Lets the host grow the

@@ -85,10 +85,10 @@ struct IvmRecord {
 };
 
 // Frame candidate plane: one 64-bit word per half-cell of every env's store window,
-//   word = stamp << 56 | orderable(height) << 24 | (0xFFFFFF - pixel index)
-// stamp = 1..255 cycles with the step counter, so words of earlier steps lose every atomicMax of the
-// current step: the plane is never cleaned between steps (the host clears it once per 255 steps,
-// when the stamp wraps).  Offering a point is ONE fire-and-forget 64-bit RED.MAX (no tag to claim,
+//   word = stamp << (32 + pb) | orderable(height) << pb | (2^pb - 1 - pixel index),   pb = bits of a pixel index
+// stamp = 1..2^(32-pb)-1 cycles with the step counter, so words of earlier steps lose every atomicMax of the
+// current step: the plane is never cleaned between steps (the host clears it when the stamp wraps: once per
+// 65 535 steps for 256x256 images).  Offering a point is ONE fire-and-forget 64-bit RED.MAX (no tag to claim,
 // no dependent round trip); a frame touches ~11 k distinct cells per env, so the live part of the
 // plane is a few hundred KB per env and stays in L2 between the scatter and the resolve.
 
@@ -158,7 +158,8 @@ struct IvmParams {
     // persistent device memory
     IvmRecord *store;             // [maxB][SR][SC]
     unsigned long long *cplane;   // [maxB][SR][SC] frame candidate plane (see above)
-    uint32_t cstamp;              // per step: 1..255
+    uint32_t cstamp;              // per step: 1..stamp period (see the candidate plane above)
+    int32_t pix_bits;             // pb: bits of a pixel index, ceil(log2(HW)) (<= 24)
     IvmEnv *env;                  // [maxB]
     int32_t *rowcount, *colcount; // [maxB][SR], [maxB][SC] live records per store row / col
     IvmGlobal *g;
@@ -329,10 +330,16 @@ IVM_HD int ivm_unproject(float d, float xs_u, float ys_v, const float *T, float 
 // frame de-dup candidate: highest point wins, lowest pixel index on ties
 // (first-index rule of scatter_max; pixels are listed in (v,u) order, mapper.py:32-35).
 IVM_HD unsigned long long ivm_cand_key(const IvmParams &P, float y, uint32_t pix) {
-    return ((unsigned long long)P.cstamp << 56) | ((unsigned long long)ivm_orderable(y) << 24) |
-           (unsigned long long)(0xFFFFFFu - pix);
+    const int pb = P.pix_bits;
+    return ((unsigned long long)P.cstamp << (32 + pb)) | ((unsigned long long)ivm_orderable(y) << pb) |
+           (unsigned long long)(((1u << pb) - 1u) - pix);
 }
-IVM_HD uint32_t ivm_cand_hash(uint32_t cell) { return (cell * 0x9E3779B1u) >> 7; }  // neighbours land far apart
+// bits of a pixel index and the longest stamp period they leave in a 64-bit candidate word
+IVM_HD int ivm_pix_bits(long long hw) { int pb = 1; while (pb < 24 && (1ll << pb) < hw) ++pb; return pb; }
+IVM_HD uint32_t ivm_stamp_period(int pix_bits, uint32_t override_period) {
+    const uint32_t most = (uint32_t)((1ull << (32 - pix_bits)) - 1ull);
+    return (override_period >= 1u && override_period < most) ? override_period : most;
+}
 
 IVM_HD bool ivm_store_index(const IvmParams &P, int32_t origin_r, int32_t origin_c, int b, int32_t r, int32_t c,
                             size_t &idx) {

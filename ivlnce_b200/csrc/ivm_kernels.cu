@@ -553,14 +553,16 @@ __device__ __forceinline__ size_t raster_fixed_bytes_dev(int tile_r, int tile_c,
         }                                                                                                  \
     } while (0)
 // safe_only: the tile is rastered only if nothing under it can still be changed by the edge fix-up, i.e. no
-// frame-edge winner is pending in it (tile_dirty stamp) and its store footprint stays strictly inside the
-// env's bounding box (stage-2 collisions live on the bbox edge lines).  Returns false if the tile was skipped.
+// frame-edge winner is pending in it (tile_dirty stamp) and its store footprint stays clear of the edge lines of
+// the batch-global bounding box, where the stage-2 collisions live.  Those lines are known (as narrow bands,
+// `gband`, see ovl_global_bands) as soon as grid barrier 2 has passed.  Returns false if the tile was skipped.
 // stage_cap > 0: the records under the tile are first copied into shared memory with cp.async (every copy of the
 // tile in flight at once, no registers held), so that a tile costs ONE memory round trip instead of one per
 // batch of rows; tiles with more records than stage_cap take the direct path.
 template <bool KNOWN>
 __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, int b, int r0, int c0, uint32_t *smem, int tid,
-                                            int nthr, int bar_id, unsigned &n_in, bool safe_only = false, int stage_cap = 0) {
+                                            int nthr, int bar_id, unsigned &n_in, bool safe_only = false, int stage_cap = 0,
+                                            const int32_t *gband = nullptr) {
     const int tr = P.tile_r, tc = P.tile_c;
     uint32_t *skey = smem;
     int32_t *s_clo = reinterpret_cast<int32_t *>(skey + tr * tc);   // first store column of each half-row's span
@@ -595,9 +597,12 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
         const int len = chi >= clo ? chi - clo + 1 : 0;
         s_clo[i] = clo; s_len[i] = len;
         if (len > 0) atomicMax(s_maxlen, len);
-        if (!KNOWN && safe_only && len > 0 &&
-            (row_lo + i <= e.rmin || row_lo + i >= e.rmax || clo <= e.cmin || chi >= e.cmax))
-            s_maxlen[1] = 1;
+        if (!KNOWN && safe_only && len > 0) {
+            const int row = row_lo + i;
+            if ((row >= gband[0] && row <= gband[1]) || (row >= gband[2] && row <= gband[3]) ||
+                (chi >= gband[4] && clo <= gband[5]) || (chi >= gband[6] && clo <= gband[7]))
+                s_maxlen[1] = 1;
+        }
     }
     if (!KNOWN && safe_only && tid == 0) {
         const int tiles_x = (P.C + P.tile_c - 1) / P.tile_c, tiles_y = (P.R + P.tile_r - 1) / P.tile_r;
@@ -865,6 +870,7 @@ struct OvlShared {
     int32_t next[4];           // raster: the group's next ego tile (dynamic distribution)
     int32_t gflag[4];
     int32_t pend[4][32];       // raster: tiles of the group that wait for the edge fix-up
+    int32_t gband[8];          // raster: bands of half-rows / half-cols that hold the global bbox edge lines (ovl_global_bands)
 };
 
 static inline size_t ovl_stream_bytes(bool pred) {
@@ -975,6 +981,28 @@ __device__ __forceinline__ bool grid_wait_group(uint32_t *bar, uint32_t target, 
     }
     group_bar(1, nthr);
     return *s_flag != 0;
+}
+
+// Where can the edge lines of the stage-2 (world) bounding box lie?  The box that the fix-up will compute
+// (ivm_fixup_stage1) is the union of the env boxes as they stand at grid barrier 2 and of the frame-edge winners
+// that stage 1 still merges; those lie inside the frame box `loc`.  So its first row is in
+// [min(Rb2, loc.rmin), Rb2] with Rb2 = first row over the env boxes at barrier 2 (exactly Rb2 when the frame did
+// not reach beyond the known world: the usual case), and likewise for the other three sides.  Reads that race
+// with stage 1's merges only move Rb2 inside that band.  Called by one warp right after grid barrier 2;
+// band[0..1] first-row band, [2..3] last-row band, [4..5] first-col band, [6..7] last-col band.
+__device__ __forceinline__ void ovl_global_bands(const IvmParams &P, int lane, int32_t *band) {
+    int rmin = INT32_MAX, rmax = INT32_MIN, cmin = INT32_MAX, cmax = INT32_MIN;
+    for (int b = lane; b < P.B; b += 32) {
+        const IvmEnv *e = &P.env[b];
+        const int4 bx = __ldcg(reinterpret_cast<const int4 *>(&e->rmin));
+        if (__ldcg(&e->count) > 0) { rmin = min(rmin, bx.x); rmax = max(rmax, bx.y); cmin = min(cmin, bx.z); cmax = max(cmax, bx.w); }
+    }
+    rmin = warp_min(rmin); rmax = warp_max(rmax); cmin = warp_min(cmin); cmax = warp_max(cmax);
+    if (lane == 0) {
+        const int32_t l0 = __ldcg(&P.g->loc[0]), l1 = __ldcg(&P.g->loc[1]), l2 = __ldcg(&P.g->loc[2]), l3 = __ldcg(&P.g->loc[3]);
+        band[0] = min(rmin, l0); band[1] = rmin; band[2] = rmax; band[3] = max(rmax, l1);
+        band[4] = min(cmin, l2); band[5] = cmin; band[6] = cmax; band[7] = max(cmax, l3);
+    }
 }
 
 #define OVL_STAMP(k, who)                                                                              \
@@ -1429,6 +1457,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     if (!grid_wait(P.bar, bar_base + 2u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
     if (blockIdx.x == 0 && tid == 0) g->tstamp[2] = global_timer();
     OVL_STAMP(5, 0);
+    if (warp == 0) ovl_global_bands(P, lane, sh.gband);  // before anything of the fix-up can have moved an env box for good
+    __syncthreads();
 
     // ================================================================ edge fix-up beside the raster
     // CTA 0 runs the whole fix-up program (stage-1 classes + merges, edge-line scan, stage-2 classes) on its
@@ -1527,7 +1557,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             const int ty = w / tiles_x, tx = w - ty * tiles_x;
             if (released) {
                 raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in, false, stage_cap);
-            } else if (!raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in, true, stage_cap)) {
+            } else if (!raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in, true, stage_cap, sh.gband)) {
                 if (npend < 32) {
                     if (gtid == 0) sh.pend[group][npend] = u;
                     ++npend;
@@ -1761,6 +1791,7 @@ struct ivm_ctx {
     ivm_config cfg;
     IvmParams P;       // persistent part filled at create
     uint32_t step;     // 24-bit stamp of the last call
+    unsigned long long cstep;  // calls so far (never rebased): the candidate-plane stamp cycles with it
     int hi_water;      // envs [0, hi_water) may hold records
     int first_call;
     int bulk_attr_set;
@@ -1918,6 +1949,7 @@ int ivm_create(const ivm_config *cfg, void *workspace_dev, size_t workspace_byte
     tile_dims(cfg, &tr, &tc);
     P.tile_r = tr; P.tile_c = tc;
     P.debug = cfg->reserved[1];
+    P.pix_bits = ivm_pix_bits((long long)cfg->height * cfg->width);
     ctx->first_call = 1;
     ctx->num_sms = 148;
     {
@@ -2112,8 +2144,10 @@ int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const
     cudaStream_t st = (cudaStream_t)stream;
     IvmParams P = ctx->P;
     P.B = num_envs; P.step = ctx->step;
-    P.cstamp = (ctx->step - 1u) % 255u + 1u;
-    if (P.cstamp == 1u && ctx->step > 1u) {  // the 8-bit stamp wrapped: forget the last 255 steps' candidates
+    ctx->cstep += 1ull;
+    const uint32_t period = ivm_stamp_period(P.pix_bits, (uint32_t)(ctx->cfg.reserved[3] > 0 ? ctx->cfg.reserved[3] : 0));
+    P.cstamp = (uint32_t)((ctx->cstep - 1ull) % period) + 1u;
+    if (P.cstamp == 1u && ctx->cstep > 1ull) {  // the stamp wrapped: forget the candidates of the last `period` steps
         cudaError_t e = cudaMemsetAsync(P.cplane, 0, sizeof(unsigned long long) * (size_t)ctx->cfg.max_envs * P.SR * P.SC,
                                         (cudaStream_t)stream);
         if (e != cudaSuccess) return cuda_fail(ctx, e, "candidate plane clear");
@@ -2346,6 +2380,12 @@ int ivm_copy_state(ivm_ctx *dst, const ivm_ctx *src, ivm_stream_t stream) {
 #undef IVM_COPY
     dst->step = src->step;
     dst->hi_water = src->hi_water;
+    return IVM_OK;
+}
+
+int ivm_debug_set_step(ivm_ctx *ctx, uint32_t step) {
+    if (!ctx || ctx->step != 0 || step >= 0xFFFFFFu) return IVM_E_INVALID;  // before the first step only
+    ctx->step = step;
     return IVM_OK;
 }
 

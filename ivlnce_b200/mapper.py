@@ -252,7 +252,7 @@ class _MapEngine:
 
     def __init__(self, device: torch.device, map_dimensions: MapDimensions, camera: Optional[CameraParameters],
                  mode: str, max_envs: int, store_cells: int, known_capacity: int, tile: int = 0,
-                 scatter_variant: int = 0):
+                 scatter_variant: int = 0, stamp_period: int = 0):
         device = torch.device(device)
         if device.type != "cuda":
             raise _lib.MapLibraryError(
@@ -267,6 +267,7 @@ class _MapEngine:
         self.known_capacity = int(known_capacity)
         self.tile = int(tile)
         self.scatter_variant = int(scatter_variant)  # 0 = auto (fused persistent step kernel when it applies), 1 / 2 = four kernels (register-staged / bulk-async score loads)
+        self.stamp_period = int(stamp_period)        # test switch: period of the candidate-plane stamp (0 = longest)
         self.ctx = None
         self.workspace = None
         self.max_envs = 0
@@ -276,7 +277,8 @@ class _MapEngine:
     def _config(self, max_envs: int) -> _lib.IvmConfig:
         md = self.md
         H, W = (self.camera.features_spatial_dimensions if self.camera is not None else (0, 0))
-        reserved = (ctypes.c_int32 * 4)(self.scatter_variant, int(os.environ.get("IVM_DEBUG_FLAGS", "0")), 0, 0)
+        reserved = (ctypes.c_int32 * 4)(self.scatter_variant, int(os.environ.get("IVM_DEBUG_FLAGS", "0")), 0,
+                                        int(self.stamp_period))
         return _lib.IvmConfig(
             reserved=reserved, max_envs=max_envs, height=int(H), width=int(W), map_rows=md.num_rows, map_cols=md.num_cols,
             res=np.float32(md.resolution_meters), half_res=np.float32(md.resolution_meters / 2),
@@ -378,7 +380,7 @@ class MappingModule(nn.Module):
                  maps_location: Optional[str] = None, max_envs: Optional[int] = None,
                  store_cells: int = DEFAULT_STORE_CELLS, known_capacity: int = DEFAULT_KNOWN_CAPACITY,
                  trig: str = "kernel", host_trig: bool = False, raster_tile: int = 0,
-                 track_start_state: bool = False, scatter_variant: int = 0):
+                 track_start_state: bool = False, scatter_variant: int = 0, stamp_period: int = 0):
         super().__init__()
         assert mode in ("iterative", "known")
         self.device = torch.device(device)
@@ -397,7 +399,7 @@ class MappingModule(nn.Module):
         assert self.trig in ("kernel", "torch", "host")
         self.track_start_state = track_start_state
         self._engine_args = dict(store_cells=store_cells, known_capacity=known_capacity, tile=raster_tile,
-                                 scatter_variant=scatter_variant)
+                                 scatter_variant=scatter_variant, stamp_period=stamp_period)
         self._engine: Optional[_MapEngine] = None
         self._initial_max_envs = max_envs
         self._hold = _Hold()   # per-call state kept off the nn.Module attribute machinery

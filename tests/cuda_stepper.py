@@ -14,14 +14,14 @@ from ivlnce_b200.mapper import (CameraParameters, EpisodesInfo, MapDimensions, O
 
 class CudaStepper:
     def __init__(self, cfg, known_clouds=None, device="cuda:0", host_trig=True, pred=False, store_cells=None,
-                 max_envs=None, raster_tile=0, trig=None, scatter_variant=0):
+                 max_envs=None, raster_tile=0, trig=None, scatter_variant=0, stamp_period=0):
         self.dev = torch.device(device)
         self.cfg = cfg
         self.pred = pred
         md = MapDimensions(cfg["map_m"], cfg["map_m"], cfg["resolution"])
         if store_cells is None:
             store_cells = 2048 if cfg["resolution"] < 0.1 else 1024
-        kw = dict(store_cells=store_cells, max_envs=max_envs, raster_tile=raster_tile, scatter_variant=scatter_variant,
+        kw = dict(store_cells=store_cells, max_envs=max_envs, raster_tile=raster_tile, scatter_variant=scatter_variant, stamp_period=stamp_period,
                   trig=trig if trig is not None else ("host" if host_trig else "torch"))
         if cfg["mode"] == "iterative":
             cam = CameraParameters(cfg["vfov"], (cfg["height"], cfg["width"]), 0.1)

@@ -19,6 +19,9 @@ struct Emu {
     IvmParams P;
     int mode;
     uint32_t step;
+    unsigned long long cstep;
+    uint32_t stamp_period;  // 0 = longest
+    uint32_t last_cstamp;
     int hi_water;
     int order;  // 0 forward, 1 reverse, 2 strided
     int fix_cap;  // capacity of the fix-up's small-class fast path (0 forces the hash path)
@@ -42,12 +45,13 @@ Emu *emu_create(int H, int W, const float *xs, const float *ys, float res, float
     Emu *m = new Emu();
     memset(&m->P, 0, sizeof(m->P));
     memset(&m->g, 0, sizeof(m->g));
-    m->mode = mode; m->step = 0; m->hi_water = 0; m->order = 0; m->fix_cap = 512;
+    m->mode = mode; m->step = 0; m->cstep = 0; m->stamp_period = 0; m->last_cstamp = 0; m->hi_water = 0; m->order = 0; m->fix_cap = 512;
     ivm_reset_step_globals(&m->g);
     IvmParams &P = m->P;
     P.H = H; P.W = W; P.HW = H * W; P.R = R; P.C = C;
     P.res = res; P.half_res = half_res; P.half_h = half_h; P.half_w = half_w;
     P.SR = SR; P.SC = SC; P.maxB = maxB;
+    P.pix_bits = ivm_pix_bits((long long)H * W);
     P.tile_r = tile_r > R ? R : tile_r; P.tile_c = tile_c > C ? C : tile_c;
     const size_t cells = (size_t)maxB * SR * SC;
     m->env.assign(maxB, IvmEnv());
@@ -85,7 +89,8 @@ Emu *emu_create(int H, int W, const float *xs, const float *ys, float res, float
 
 void emu_destroy(Emu *m) { delete m; }
 void emu_set_order(Emu *m, int order) { m->order = order; }
-void emu_set_step(Emu *m, unsigned step) { m->step = step; }  // before the first step only (tests the stamp wrap)
+void emu_set_step(Emu *m, unsigned step) { m->step = step; m->cstep = step; }  // before the first step only (tests the stamp wrap)
+void emu_set_stamp_period(Emu *m, unsigned period) { m->stamp_period = period; }
 void emu_set_fix_cap(Emu *m, int cap) { m->fix_cap = cap < 1 ? 1 : cap; }
 
 static inline int visit(const Emu *m, int i, int n) {
@@ -173,8 +178,11 @@ int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels,
     m->step += 1;
     IvmParams P = m->P;
     P.B = B; P.step = m->step;
-    P.cstamp = (m->step - 1u) % 255u + 1u;
-    if (P.cstamp == 1u && m->step > 1u) std::fill(m->cand.begin(), m->cand.end(), 0ull);
+    m->cstep += 1ull;
+    const uint32_t period = ivm_stamp_period(P.pix_bits, m->stamp_period);
+    P.cstamp = (uint32_t)((m->cstep - 1ull) % period) + 1u;
+    m->last_cstamp = P.cstamp;
+    if (P.cstamp == 1u && m->cstep > 1ull) std::fill(m->cand.begin(), m->cand.end(), 0ull);
     P.depth = depth; P.labels = labels; P.T12 = T12; P.pose = pose; P.cs = cs; P.masks = masks;
     P.occ = occ; P.sem = sem;
     if (orient) {  // the K0 path that derives the matrices from the angles
@@ -309,8 +317,8 @@ void emu_status(const Emu *m, uint32_t *err, unsigned long long *stats8) {
 // words of the candidate plane that carry the stamp of the last step (= half-cells the last frame touched)
 long long emu_cand_current(const Emu *m) {
     long long n = 0;
-    const uint32_t stamp = (m->step - 1u) % 255u + 1u;
-    for (size_t i = 0; i < m->cand.size(); ++i) n += (uint32_t)(m->cand[i] >> 56) == stamp;
+    const int sh = 32 + m->P.pix_bits;
+    for (size_t i = 0; i < m->cand.size(); ++i) n += (uint32_t)(m->cand[i] >> sh) == m->last_cstamp;
     return n;
 }
 

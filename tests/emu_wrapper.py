@@ -44,6 +44,7 @@ def lib():
         L.emu_export_world.restype = ctypes.c_longlong
         L.emu_export_world.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, i64p, f32p, u8p, u64p]
         L.emu_status.argtypes = [ctypes.c_void_p, u32p, u64p]
+        L.emu_set_stamp_period.argtypes = [ctypes.c_void_p, ctypes.c_uint]
         L.emu_cand_current.restype = ctypes.c_longlong
         L.emu_cand_current.argtypes = [ctypes.c_void_p]
         _lib = L
@@ -133,6 +134,9 @@ class EmuMapper:
 
     def set_step(self, step):
         lib().emu_set_step(self._h, ctypes.c_uint(step))
+
+    def set_stamp_period(self, period):
+        lib().emu_set_stamp_period(self._h, ctypes.c_uint(period))
 
     def cand_current(self):
         return int(lib().emu_cand_current(self._h))

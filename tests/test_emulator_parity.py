@@ -43,10 +43,12 @@ def test_emulator_matches_golden(name, order):
 
 @pytest.mark.parametrize("name", ["iid_f64", "scene_overlap", "batch_shrink_grow"])
 def test_candidate_table_stamp_wrap(name):
-    """The frame candidate table is never cleared between steps: entries carry an 8-bit step stamp
-    that wraps every 255 steps.  Start just below the wrap so that it happens in mid-run."""
+    """The frame candidate plane is never cleared between steps: its words carry a step stamp that
+    wraps (65 535 steps at 256x256; the period is shortened here).  Start just below the wrap so that it
+    happens in mid-run."""
     scn = load_golden(name)
     emu = _emu(scn)
+    emu.set_stamp_period(255)
     emu.set_step(255 * 3 - 4)
     outs, sizes = run_mapper(emu.step, scn, world_fn=emu.world)
     for t, (o, s) in enumerate(outs):

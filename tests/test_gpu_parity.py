@@ -127,8 +127,8 @@ def test_predicted_full_size_against_oracle():
 
 @pytest.mark.parametrize("variant", [0, 2])
 def test_candidate_table_stamp_wrap(variant):
-    """300 steps of a small scenario: the 8-bit stamp of the frame candidate table wraps (and the
-    table is cleared by the host) at step 256; results must stay bit-exact against the oracle."""
+    """300 steps of a small scenario with the stamp period of the frame candidate plane shortened to 255 / 7 steps:
+    the stamp wraps (and the plane is cleared by the host) in mid-run; results must stay bit-exact against the oracle."""
     from ivlnce_b200.synthetic import ScenarioConfig, make_scenario
     from oracle.oracle import OracleMapper
     from scenarios import _wrap
@@ -140,11 +140,12 @@ def test_candidate_table_stamp_wrap(variant):
     ref_outs, _ = run_mapper(orc.step, scn)
     from cuda_stepper import CudaStepper
 
-    cs = CudaStepper(scn["cfg"], max_envs=2, scatter_variant=variant)
-    for t in range(c.steps):
-        o, s = cs.step(scn["masks"][t], scn["pose"][t], scn["orientation"][t], depth=scn["depth"][t], labels=scn["labels"][t])
-        assert np.array_equal(o, ref_outs[t][0]) and np.array_equal(s, ref_outs[t][1]), t
-    cs.mm.check_errors()
+    for period in (255, 7):
+        cs = CudaStepper(scn["cfg"], max_envs=2, scatter_variant=variant, stamp_period=period)
+        for t in range(c.steps):
+            o, s = cs.step(scn["masks"][t], scn["pose"][t], scn["orientation"][t], depth=scn["depth"][t], labels=scn["labels"][t])
+            assert np.array_equal(o, ref_outs[t][0]) and np.array_equal(s, ref_outs[t][1]), (period, t)
+        cs.mm.check_errors()
 
 
 def test_device_trig_f64_matches():
