@@ -98,7 +98,8 @@ def build_module(cfg, device, max_envs, variant=0):
 
     cam = CameraParameters(math.pi / 2, (cfg["H"], cfg["W"]), 0.1)
     md = MapDimensions(cfg["map_m"], cfg["map_m"], cfg["res"])
-    kw = dict(store_cells=cfg["store"], max_envs=max_envs, trig="kernel", scatter_variant=variant)
+    kw = dict(store_cells=cfg["store"], max_envs=max_envs, trig="kernel", scatter_variant=variant,
+              pipelined=os.environ.get("IVM_PIPELINED", "1") != "0")
     if cfg["pred"]:
         return create_iterative_mapper(device, cam, md, PrecomputedScores(), **kw)
     return create_gt_semantics_iterative_mapper(device, cam, md, **kw)

@@ -156,6 +156,15 @@ int64_t ivm_kernel_launches(const ivm_ctx *ctx);
 /* Rewrites all live stamps to 1 (call when IVM_E_STEP_OVERFLOW is returned). */
 int ivm_rebase_stamps(ivm_ctx *ctx, ivm_stream_t stream);
 
+/* Pipelined stepping.  Off (default): a step touches nothing -- not even its inputs -- before the previous kernel
+ * of the stream has completed.  On: the caller promises that the INPUT buffers of every ivm_step_iterative call
+ * (depth, labels / logits, pose, angles, masks) are complete before the PREVIOUS step of this context was enqueued
+ * (true for resident or replayed inputs, and for inputs staged by copy-engine transfers rather than kernels).
+ * Consecutive steps enqueued back to back on one stream then overlap: the next step's score stream, pose matrices
+ * and depth filter run while the last ego tiles of the current step are rastered, and the next step waits for the
+ * current one through a counter of finished CTAs instead of the kernel boundary.  Results are identical. */
+int ivm_set_pipelined(ivm_ctx *ctx, int32_t enabled);
+
 /* Test hook: sets the 24-bit step counter of a context that has not stepped yet (so that a test can reach the
  * IVM_E_STEP_OVERFLOW / ivm_rebase_stamps path without 2^24 calls). */
 int ivm_debug_set_step(ivm_ctx *ctx, uint32_t step);

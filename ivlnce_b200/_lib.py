@@ -77,6 +77,7 @@ def load() -> ctypes.CDLL:
     L.ivm_kernel_launches.argtypes = [_vp]
     L.ivm_rebase_stamps.argtypes = [_vp, _vp]
     L.ivm_debug_set_step.argtypes = [_vp, ctypes.c_uint32]
+    L.ivm_set_pipelined.argtypes = [_vp, ctypes.c_int32]
     L.ivm_read_phase_ns.argtypes = [_vp, ctypes.POINTER(ctypes.c_uint64), _vp]
     L.ivm_read_cta_trace.argtypes = [_vp, ctypes.POINTER(ctypes.c_uint64), ctypes.c_int32, _vp]
     L.ivm_copy_state.argtypes = [_vp, _vp, _vp]
@@ -86,7 +87,7 @@ def load() -> ctypes.CDLL:
     L.ivm_version.restype = ctypes.c_char_p
     for name in ("ivm_create", "ivm_destroy", "ivm_set_camera", "ivm_step_iterative", "ivm_known_load", "ivm_known_clear",
                  "ivm_step_known", "ivm_export_world", "ivm_read_status", "ivm_set_timing", "ivm_stage_times",
-                 "ivm_rebase_stamps", "ivm_debug_set_step", "ivm_copy_state", "ivm_read_phase_ns", "ivm_read_cta_trace", "ivm_map_features"):
+                 "ivm_rebase_stamps", "ivm_debug_set_step", "ivm_set_pipelined", "ivm_copy_state", "ivm_read_phase_ns", "ivm_read_cta_trace", "ivm_map_features"):
         getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L

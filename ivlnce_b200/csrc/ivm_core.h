@@ -312,6 +312,18 @@ IVM_HD void ivm_world_xyz(float d, float xs_u, float ys_v, const float *T, float
     x = w[0]; y = w[1]; z = w[2];
 }
 
+// the height (row 1 of T) alone: the same operations in the same order as ivm_world_xyz, so the same bits
+IVM_HD float ivm_world_y(float d, float xs_u, float ys_v, const float *T) {
+    const float zc = ivm_mul(d, 10.0f);
+    const float xc = ivm_mul(zc, xs_u);
+    const float yc = ivm_mul(zc, ys_v);
+    float acc = ivm_mul(T[4], xc);
+    acc = ivm_fma(T[5], yc, acc);
+    acc = ivm_fma(T[6], zc, acc);
+    acc = ivm_fma(T[7], 1.0f, acc);
+    return acc;
+}
+
 // returns 0 = filtered out, 1 = valid point, 2 = valid but its cell index is not representable
 // (non-finite / absurd coordinates; the caller flags IVM_ERR_STORE_OVERFLOW)
 IVM_HD int ivm_unproject(float d, float xs_u, float ys_v, const float *T, float h, float half_res, IvmPoint &p) {

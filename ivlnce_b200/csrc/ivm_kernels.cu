@@ -841,14 +841,13 @@ __device__ __forceinline__ bool grid_barrier(uint32_t *bar, uint32_t target, int
 #define IVM_O_NSTAGE 3         // ring depth: 48 KB per CTA; <= 64 KB per SM in flight keeps HBM saturated (measured) without
                                // building multi-microsecond queues in front of the geometry warps' loads and atomics
 #define IVM_O_SLOTS_PRED 8     // tiles whose queue / labels a CTA holds at a time
-#define IVM_O_SLOTS_GT 16
-#define IVM_O_LOADB 8          // tiles whose depth loads are issued together (refill pass)
-#define IVM_O_SUB 3            // tiles a G1 group handles per pass (12 pixels per thread in flight; no spills at 72 registers)
+#define IVM_O_SLOTS_GT 12     // 12 x 512 x 10 B of queues = 60 KB per CTA, three CTAs per SM
 #define IVM_O_CTAS_PER_SM_PRED 2  // with the score stream: two CTAs per SM (ring + queues = 76 KB each)
 #define IVM_O_CTAS_PER_SM_GT 3    // GT labels: every phase is latency-bound, a third CTA per SM (72 registers) pays: measured 85 -> 79 us at 32 envs
 #define IVM_O_TILE_CTR 40      // word of the barrier block (its second 128-byte line) that hands out raster tiles
 #define IVM_O_FIX_FLAG 48      // ... = step once CTA 0 has finished stage 1 of the edge fix-up
 #define IVM_O_FIX_ARRIVE 56    // ... arrivals of the fix-up team after the edge-line scan (monotone)
+#define IVM_O_DONE 64          // word of the barrier block (its third 128-byte line): CTAs that are done with the map state (monotone)
 
 struct OvlSlot {               // one tile of a chunk
     float T[12];
@@ -870,82 +869,14 @@ struct OvlShared {
     int32_t next[4];           // raster: the group's next ego tile (dynamic distribution)
     int32_t gflag[4];
     int32_t pend[4][32];       // raster: tiles of the group that wait for the edge fix-up
+    unsigned long long t_start; // %globaltimer when the CTA became resident
+    int32_t qoff[NSLOT + 1];   // prefix of the chunk's queue lengths
     int32_t gband[8];          // raster: bands of half-rows / half-cols that hold the global bbox edge lines (ovl_global_bands)
 };
 
 static inline size_t ovl_stream_bytes(bool pred) {
     const size_t nslot = pred ? IVM_O_SLOTS_PRED : IVM_O_SLOTS_GT;
-    return (pred ? (size_t)IVM_O_NSTAGE * IVM_O_SP * IVM_O_TILE * sizeof(float) : 0) + nslot * IVM_O_TILE * (4 + 2 + (pred ? 1 : 0));
-}
-
-template <int PX>
-struct OvlDepth { float v[PX]; };
-template <int PX>
-__device__ __forceinline__ OvlDepth<PX> ovl_load_depth(const float *p) {
-    OvlDepth<PX> r;
-    if (PX == 4) {
-        const float4 q = __ldcg(reinterpret_cast<const float4 *>(p));
-        r.v[0] = q.x; r.v[1 % PX] = q.y; r.v[2 % PX] = q.z; r.v[3 % PX] = q.w;
-    } else {
-        const float2 q = __ldcg(reinterpret_cast<const float2 *>(p));
-        r.v[0] = q.x; r.v[1 % PX] = q.y;
-    }
-    return r;
-}
-
-// The PX pixels of one geometry thread in one tile: unproject, (SCATTER) offer to the candidate plane +
-// prefetch the world record + fold the frame bbox, (enqueue) append the valid ones to the tile's queue as
-// (store row << 16 | store col, pixel in tile).
-template <int PX, bool SCATTER>
-__device__ __forceinline__ void ovl_tile_pixels(const IvmParams &P, OvlSlot &sl, const OvlDepth<PX> &dd, int gt, int lane,
-                                                bool enqueue, uint32_t *qc, uint16_t *qp, int &rmin, int &rmax, int &cmin,
-                                                int &cmax, unsigned &nvalid) {
-    const int tp = gt * PX, pix0 = sl.tp0 + tp;
-    const int v = pix0 / P.W, u0 = pix0 - v * P.W;
-    const float ysv = P.ys[v];
-    bool okv[PX];
-    uint32_t cell[PX];
-#pragma unroll
-    for (int j = 0; j < PX; ++j) {
-        okv[j] = false; cell[j] = 0u;
-        IvmPoint p;
-        const int ok = ivm_unproject(dd.v[j], P.xs[u0 + j], ysv, sl.T, sl.h, P.half_res, p);
-        if (ok == 0) continue;
-        const int32_t rr = p.r - sl.origin_r, cc = p.c - sl.origin_c;
-        if (ok == 2 || rr < 0 || rr >= P.SR || cc < 0 || cc >= P.SC) {
-            if (SCATTER) atomicOr(&P.g->err, IVM_ERR_STORE_OVERFLOW);
-            continue;
-        }
-        okv[j] = true; cell[j] = ((uint32_t)rr << 16) | (uint32_t)cc;
-        if (SCATTER) {
-            const uint32_t ci = (uint32_t)rr * (uint32_t)P.SC + (uint32_t)cc;
-            ivm_cand_insert<IvmAtomics>(P, sl.b, ci, ivm_cand_key(P, p.y, (uint32_t)(pix0 + j)));
-            // the resolve will read-modify-write this cell's world record: pull it into L2 now
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(&P.store[(size_t)sl.b * P.SR * P.SC + ci]));
-            rmin = min(rmin, p.r); rmax = max(rmax, p.r); cmin = min(cmin, p.c); cmax = max(cmax, p.c);
-            ++nvalid;
-        }
-    }
-    if (enqueue) {  // block-uniform
-        unsigned m[PX];
-        int n = 0;
-#pragma unroll
-        for (int j = 0; j < PX; ++j) { m[j] = __ballot_sync(0xffffffffu, okv[j]); n += __popc(m[j]); }
-        if (n) {  // warp-uniform
-            unsigned pos = 0;
-            if (lane == 0) pos = atomicAdd(&sl.qn, (unsigned)n);
-            pos = __shfl_sync(0xffffffffu, pos, 0);
-            const unsigned below = (1u << lane) - 1u;
-#pragma unroll
-            for (int j = 0; j < PX; ++j) {
-                if (okv[j]) {
-                    const unsigned o = pos + __popc(m[j] & below);
-                    qc[o] = cell[j]; qp[o] = (uint16_t)(tp + j);
-                }
-                pos += __popc(m[j]);
-            }
-        }
-    }
+    return (pred ? (size_t)IVM_O_NSTAGE * IVM_O_SP * IVM_O_TILE * sizeof(float) : 0) + nslot * IVM_O_TILE * (4 + 4 + 2 + (pred ? 1 : 0));
 }
 
 // A frame winner on the frame bbox edge: the fix-up decides its cell later.  The ego tiles of the pending point
@@ -1014,16 +945,14 @@ __device__ __forceinline__ void ovl_global_bands(const IvmParams &P, int lane, i
 template <bool PRED>
 __global__ void __launch_bounds__(PRED ? IVM_O_THREADS_PRED : IVM_O_THREADS_GT, PRED ? IVM_O_CTAS_PER_SM_PRED : IVM_O_CTAS_PER_SM_GT)
 k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ logits, int ncls, uint8_t *__restrict__ labels_out,
-               int nenv_total, uint32_t bar_base, int max_rows, int raster_group_bytes, int stage_cap, int team, uint32_t team_base) {
+               int nenv_total, uint32_t bar_base, int max_rows, int raster_group_bytes, int stage_cap, int team, uint32_t team_base,
+               int pipelined, uint32_t done_target) {
     constexpr int NG1 = 256;                               // G1 (depth scatter): warps 0..7 in both modes
-    constexpr int PX1 = 4;                                 // pixels per thread and tile in G1 (a tile = one group of 4 warps)
     constexpr int NG = 256;                                // G3 (resolve) threads: warps 0..7
     constexpr int RG = PRED ? IVM_O_RGROUPS_PRED : IVM_O_RGROUPS_GT;  // raster groups per CTA
     constexpr int NGW = NG / 32;
-    constexpr int PX = IVM_O_TILE / NG;                    // refill pass of G3 (more tiles than slots)
     constexpr int NSLOT = PRED ? IVM_O_SLOTS_PRED : IVM_O_SLOTS_GT;
     constexpr int NCW = 4;                                 // argmax warps (PRED)
-    constexpr int DRAIN = IVM_O_TILE / NG;                 // queue entries per G3 thread and tile
     constexpr size_t RING_BYTES = PRED ? (size_t)IVM_O_NSTAGE * IVM_O_SP * IVM_O_TILE * sizeof(float) : 0;
     extern __shared__ __align__(128) unsigned char dyn[];
     __shared__ __align__(8) OvlShared<NSLOT> sh;
@@ -1036,40 +965,141 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     const int nslot = (P.debug & 128) ? 2 : NSLOT;         // tiles per chunk (debug bit 128: tiny chunks, to test the multi-chunk path)
     const bool keep_queue = my_tiles <= nslot;             // the queue built by G1 is still there in G3
     uint32_t *qcell = reinterpret_cast<uint32_t *>(dyn + RING_BYTES);
-    uint16_t *qpix = reinterpret_cast<uint16_t *>(dyn + RING_BYTES + (size_t)NSLOT * IVM_O_TILE * 4);
-    uint8_t *slab = dyn + RING_BYTES + (size_t)NSLOT * IVM_O_TILE * 6;
+    float *qd = reinterpret_cast<float *>(dyn + RING_BYTES + (size_t)NSLOT * IVM_O_TILE * 4);
+    uint16_t *qpix = reinterpret_cast<uint16_t *>(dyn + RING_BYTES + (size_t)NSLOT * IVM_O_TILE * 8);
+    uint8_t *slab = dyn + RING_BYTES + (size_t)NSLOT * IVM_O_TILE * 10;
     IvmGlobal *g = P.g;
     const bool geo = warp < NGW;
     const int nstage = ((P.debug >> 8) & 15) ? min((P.debug >> 8) & 15, IVM_O_NSTAGE) : IVM_O_NSTAGE;  // experiment: shallower ring
 
-    // G1 runs as two groups of four warps that take whole tiles (4 pixels per thread and tile), alternately.
-    const int g1 = warp >> 2, gt1 = tid & 127;
-    int kbase = 0, kstride = 1, nmine = 0;
-    auto assign = [&](int cn) { kbase = g1; kstride = 2; nmine = (cn - g1 + 1) / 2; };
-    // the first batch of depth loads goes out before anything else (ahead of the score stream's first 48 KB)
-    OvlDepth<PX1> dv[IVM_O_SUB];
-    if (tid < NG1) {
-        assign(min(nslot, my_tiles));
-#pragma unroll
-        for (int m = 0; m < IVM_O_SUB; ++m) {
-#pragma unroll
-            for (int j = 0; j < PX1; ++j) dv[m].v[j] = 2.0f;
-            if (m < nmine) dv[m] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + (kbase + kstride * m) * grid_n) * IVM_O_TILE + gt1 * PX1);
+    // ---- geometry warps (0..7): the depth scatter (G1) and the resolve (G3) work on a CHUNK of tiles (<= NSLOT, whose
+    // queues fit shared memory) in phases that span all tiles of the chunk, so that nothing is serialised per tile:
+    //   A1  every pixel: depth -> height of the world point -> strict depth / height filters (mapper.py:416-424); the
+    //       survivors (about one pixel in four) are compacted into the tile's queue as (pixel, depth).  Inputs only.
+    //   A2  one queue entry per thread: world x / z, half-cell (two IEEE divisions), store cell; the candidate word and
+    //       the world record of the cell are PREFETCHED into L2; frame bbox
+    //   B   ONE 64-bit RED.MAX per queue entry into the candidate plane                          -> grid barrier 1
+    //   G3  one queue entry per thread: candidate word + world record (+ GT label) loads in flight together, then the
+    //       tile's labels are awaited and the winners merge into the world store                 -> grid barrier 2
+    constexpr int F4T = IVM_O_TILE / 4;                    // 128-bit depth loads per tile
+    constexpr int A1B = 4;                                 // depth loads in flight per thread
+    constexpr int E3 = 4;                                  // queue entries in flight per thread in G3
+    const int cn0 = min(nslot, my_tiles);                  // tiles of the first chunk
+    // input half of the slot prep (pose, camera height, pose matrices): 4 slots per warp at a time, 8 lanes each
+    auto prep_inputs = [&](int c0, int cn) {
+        const int role = lane & 7, k = warp + (lane >> 3) * (NG1 / 32);
+        if (k < cn) {
+            OvlSlot &sl = sh.slot[k];
+            const int tile = cta + (c0 + k) * grid_n;
+            const int b = tile / tpe;
+            if (role == 0) {
+                const float h = P.pose[3 * b + 1];
+                sl.b = b; sl.tp0 = (tile - b * tpe) * IVM_O_TILE;
+                sl.h = h; sl.hlo = ivm_sub(h, 1.0f); sl.hhi = ivm_add(h, 0.5f);
+                sl.qn = 0u;
+                sl.box[0] = INT32_MAX; sl.box[1] = INT32_MIN; sl.box[2] = INT32_MAX; sl.box[3] = INT32_MIN; sl.box[4] = 0;
+            } else if (role == 1) {
+                if (P.orient != nullptr) ivm_pose_matrices(P, b, sl.T, sl.cs);
+                else
+                    for (int i = 0; i < 12; ++i) sl.T[i] = P.T12[12 * b + i];
+            }
         }
-        // the later passes' depth (loaded when their turn comes) is pulled towards L2 now, ahead of the stream's traffic:
-        // one prefetch per 128-byte line
-        if ((lane & 7) == 0)
-            for (int m = IVM_O_SUB; m < nmine; ++m)
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.depth + (size_t)(cta + (kbase + kstride * m) * grid_n) * IVM_O_TILE + gt1 * PX1));
+    };
+    // state half: env decision (reset / store origin, mapper.py:310-326), or the state the env's first CTA published
+    auto prep_state = [&](int c0, int cn, bool published) {
+        const int role = lane & 7, k = warp + (lane >> 3) * (NG1 / 32);
+        if (k < cn && role == 2) {
+            OvlSlot &sl = sh.slot[k];
+            const int b = (cta + (c0 + k) * grid_n) / tpe;
+            const IvmEnv *e = &P.env[b];
+            const uint32_t m = P.masks[b];
+            const int32_t cnt = __ldcg(&e->count), eor = __ldcg(&e->origin_r), eoc = __ldcg(&e->origin_c);
+            const uint32_t ers = __ldcg(&e->reset_stamp);
+            if (published) {
+                sl.origin_r = eor; sl.origin_c = eoc; sl.reset = 0; sl.reset_stamp = ers;
+            } else {
+                const IvmEnvPrep q = ivm_env_decide_vals(P, m, cnt, eor, eoc, P.pose[3 * b + 0], P.pose[3 * b + 2]);
+                sl.origin_r = q.origin_r; sl.origin_c = q.origin_c; sl.reset = q.reset;
+                sl.reset_stamp = q.reset ? P.step : ers;
+            }
+        }
+    };
+    auto a1_load = [&](int c0, int cn, int f0, float4 *dv) {
+#pragma unroll
+        for (int q = 0; q < A1B; ++q) {
+            const int f = f0 + q * NG1 + tid;
+            dv[q] = make_float4(2.0f, 2.0f, 2.0f, 2.0f);
+            if (f < cn * F4T)
+                dv[q] = __ldcg(reinterpret_cast<const float4 *>(P.depth + (size_t)(cta + (c0 + f / F4T) * grid_n) * IVM_O_TILE + (f % F4T) * 4));
+        }
+    };
+    auto a1_filter = [&](int cn, int f0, const float4 *dv) {
+#pragma unroll
+        for (int q = 0; q < A1B; ++q) {
+            if (f0 + q * NG1 + (tid & ~31) >= cn * F4T) continue;  // warp-uniform: a warp's 32 loads lie in one tile
+            const int f = f0 + q * NG1 + tid, k = f / F4T, gt = f % F4T;
+            OvlSlot &sl = sh.slot[k];
+            const int pix0 = sl.tp0 + gt * 4;
+            const int v = pix0 / P.W, u0 = pix0 - v * P.W;
+            const float ysv = P.ys[v];
+            const float dd[4] = {dv[q].x, dv[q].y, dv[q].z, dv[q].w};
+            bool ok[4];
+            unsigned mk[4];
+            int n = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float y = ivm_world_y(dd[j], P.xs[u0 + j], ysv, sl.T);
+                ok[j] = dd[j] > 0.01f && dd[j] < 0.99f && y > sl.hlo && y < sl.hhi;
+                mk[j] = __ballot_sync(0xffffffffu, ok[j]);
+                n += __popc(mk[j]);
+            }
+            if (n) {  // warp-uniform
+                unsigned pos = 0;
+                if (lane == 0) pos = atomicAdd(&sl.qn, (unsigned)n);
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                const unsigned below = (1u << lane) - 1u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (ok[j]) {
+                        const unsigned o = (unsigned)k * IVM_O_TILE + pos + __popc(mk[j] & below);
+                        qpix[o] = (uint16_t)(gt * 4 + j); qd[o] = dd[j];
+                    }
+                    pos += __popc(mk[j]);
+                }
+            }
+        }
+    };
+    auto a1_rest = [&](int c0, int cn, int f_first, float4 *dv) {  // the batches after the first (or all of them)
+        for (int f0 = f_first; f0 < cn * F4T; f0 += A1B * NG1) {
+            a1_load(c0, cn, f0, dv);
+            a1_filter(cn, f0, dv);
+        }
+    };
+    auto queue_prefix = [&](int cn) {  // warp 0, after a barrier that covers A1
+        if (warp == 0) {
+            unsigned x = lane < cn ? sh.slot[lane].qn : 0u;
+            for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane < cn) sh.qoff[lane + 1] = (int)x;
+            if (lane == 0) sh.qoff[0] = 0;
+        }
+    };
+    float4 dv[A1B];
+    if (tid < NG1) {
+        if (!pipelined) asm volatile("griddepcontrol.wait;" ::: "memory");  // nothing is read before the predecessor has completed
+        // the first batch of depth loads goes out before anything else (ahead of the score stream's first 48 KB)
+        a1_load(0, cn0, 0, dv);
+        if ((lane & 7) == 0)  // the later batches are pulled towards L2: one prefetch per 128-byte line
+            for (int f = A1B * NG1 + tid; f < cn0 * F4T; f += NG1)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.depth + (size_t)(cta + (f / F4T) * grid_n) * IVM_O_TILE + (f % F4T) * 4));
+    } else if (!pipelined) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     }
-    if (blockIdx.x == 0 && tid == 0) {
-        g->tstamp[0] = global_timer(); g->tstamp[5] = 0ull;
-        g->stats[IVM_STAT_IN] = 0ull;  // this step's rastered-record count (added to after grid barrier 2)
-        P.bar[IVM_O_TILE_CTR] = (unsigned)RG * (gridDim.x - (gridDim.x > 1 ? (unsigned)team : 0u));  // raster tiles handed out statically
-    }
-    OVL_STAMP(7, 0);
-    if (tid == 0 && blockIdx.x < IVM_TRACE_CTAS) { for (int k = 13; k < 16; ++k) P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + k] = 0ull; }
+    // In pipelined mode everything up to the dependency wait below touches only this step's INPUTS, shared memory and
+    // labels_out: the launch is programmatically serialised behind the previous step's kernel (which releases its
+    // dependents once it is past its grid barrier 2), so these CTAs become resident while the previous step still
+    // rasters -- the score stream, the pose matrices and the depth filter of this step run beside that tail.
     if (tid == 0) {
+        sh.t_start = global_timer();
         if (PRED) {
             for (int s = 0; s < IVM_O_NSTAGE; ++s) { mbar_init(&sh.full[s], 1); mbar_init(&sh.empty[s], NCW); }
             for (int s = 0; s < NSLOT; ++s) { mbar_init(&sh.lab_full[s], NCW); mbar_init(&sh.lab_empty[s], NGW); }
@@ -1077,55 +1107,60 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         }
         sh.bb[0] = INT32_MAX; sh.bb[1] = INT32_MIN; sh.bb[2] = INT32_MAX; sh.bb[3] = INT32_MIN; sh.valid = 0;
     }
-    // paused envs (mapper.py:315-318) are wiped by the last CTA
-    if (blockIdx.x == gridDim.x - 1)
-        for (int b = P.B; b < nenv_total; ++b) {
-            IvmEnvPrep q; q.reset = 1; q.origin_r = 0; q.origin_c = 0;
-            ivm_env_publish<IvmAtomics>(P, b, q, tid, blockDim.x);
-        }
     __syncthreads();
 
     if (tid < NG1) {
         // ============================================================ G1: depth scatter (warps 0..7)
         int rmin = INT32_MAX, rmax = INT32_MIN, cmin = INT32_MAX, cmax = INT32_MIN;
         unsigned nvalid = 0;
+        prep_inputs(0, cn0);
+        group_bar(1, NG1);
+        a1_filter(cn0, 0, dv);
+        a1_rest(0, cn0, A1B * NG1, dv);
+        OVL_STAMP(12, 0);
+        // ---- the previous step: its kernel has completed (griddepcontrol.wait above), or -- pipelined -- every CTA of
+        //      it has signalled that it is done with the map state
+        if (tid == 0) {
+            if (pipelined) {
+                uint32_t spins = 0;
+                for (;;) {
+                    uint32_t v;
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&P.bar[IVM_O_DONE]) : "memory");
+                    if ((int32_t)(v - done_target) >= 0) break;
+                    if (++spins > (1u << 22)) { atomicOr(&g->err, IVM_ERR_GRID_BARRIER); break; }
+                    __nanosleep(64);
+                }
+            }
+            __threadfence();  // acquire; also drops L1 lines this SM may have cached while the previous kernel was still writing
+            if (blockIdx.x == 0) {
+                g->tstamp[0] = sh.t_start; g->tstamp[5] = 0ull; g->tstamp[6] = global_timer();
+                g->stats[IVM_STAT_IN] = 0ull;  // this step's rastered-record count (added to after grid barrier 2)
+                P.bar[IVM_O_TILE_CTR] = (unsigned)RG * (gridDim.x - (gridDim.x > 1 ? (unsigned)team : 0u));  // raster tiles handed out statically
+            }
+            if (blockIdx.x < IVM_TRACE_CTAS) {
+                P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + 7] = sh.t_start;
+                P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + 4] = global_timer();
+                for (int k = 13; k < 16; ++k) P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + k] = 0ull;
+            }
+        }
+        group_bar(1, NG1);  // covers A1's queues as well
+        // paused envs (mapper.py:315-318) are wiped by the last CTA
+        if (blockIdx.x == gridDim.x - 1)
+            for (int b = P.B; b < nenv_total; ++b) {
+                IvmEnvPrep q; q.reset = 1; q.origin_r = 0; q.origin_c = 0;
+                ivm_env_publish<IvmAtomics>(P, b, q, tid, NG1);
+            }
         for (int c0 = 0; c0 < my_tiles; c0 += nslot) {
             const int cn = min(nslot, my_tiles - c0);
             if (c0) {
-                group_bar(1, NG1);  // the previous chunk's slots are no longer read
-                assign(cn);
-#pragma unroll
-                for (int m = 0; m < IVM_O_SUB; ++m)
-                    if (m < nmine) dv[m] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + (c0 + kbase + kstride * m) * grid_n) * IVM_O_TILE + gt1 * PX1);
+                group_bar(1, NG1);  // the previous chunk's slots and queues are no longer read
+                prep_inputs(c0, cn);
+                group_bar(1, NG1);
+                a1_rest(c0, cn, 0, dv);
+                group_bar(1, NG1);
             }
-            {   // slot prep, 4 slots per warp at a time (8 lanes each): env decision (reset / store origin,
-                // mapper.py:310-326) by lane 0 of the octet, pose matrices by lane 1; every load of a lane is
-                // issued before the first one is used
-                const int role = lane & 7, k = warp + (lane >> 3) * (NG1 / 32);
-                if (k < cn) {
-                    OvlSlot &sl = sh.slot[k];
-                    const int tile = cta + (c0 + k) * grid_n;
-                    const int b = tile / tpe;
-                    if (role == 0) {
-                        const IvmEnv *e = &P.env[b];
-                        const uint32_t m = P.masks[b];
-                        const int32_t cnt = e->count, eor = e->origin_r, eoc = e->origin_c;
-                        const uint32_t ers = e->reset_stamp;
-                        const float px = P.pose[3 * b + 0], h = P.pose[3 * b + 1], pz = P.pose[3 * b + 2];
-                        const IvmEnvPrep q = ivm_env_decide_vals(P, m, cnt, eor, eoc, px, pz);
-                        sl.b = b; sl.tp0 = (tile - b * tpe) * IVM_O_TILE;
-                        sl.origin_r = q.origin_r; sl.origin_c = q.origin_c; sl.reset = q.reset;
-                        sl.reset_stamp = q.reset ? P.step : ers;
-                        sl.h = h; sl.hlo = ivm_sub(h, 1.0f); sl.hhi = ivm_add(h, 0.5f);
-                        sl.qn = 0u;
-                        sl.box[0] = INT32_MAX; sl.box[1] = INT32_MIN; sl.box[2] = INT32_MAX; sl.box[3] = INT32_MIN; sl.box[4] = 0;
-                    } else if (role == 1) {
-                        if (P.orient != nullptr) ivm_pose_matrices(P, b, sl.T, sl.cs);
-                        else
-                            for (int i = 0; i < 12; ++i) sl.T[i] = P.T12[12 * b + i];
-                    }
-                }
-            }
+            prep_state(c0, cn, false);
+            queue_prefix(cn);
             group_bar(1, NG1);
             if (c0 == 0) OVL_STAMP(1, 0);
             // the CTA that owns an env's first tile publishes the env's new state (read after barrier 1 only)
@@ -1140,98 +1175,51 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                     if (tid < 2) P.cs_buf[2 * sl.b + tid] = sl.cs[tid];
                 }
             }
-            for (int m0 = 0; m0 < nmine; m0 += IVM_O_SUB) {
-                if (m0) {
-#pragma unroll
-                    for (int m = 0; m < IVM_O_SUB; ++m)
-                        if (m0 + m < nmine)
-                            dv[m] = ovl_load_depth<PX1>(P.depth + (size_t)(cta + (c0 + kbase + kstride * (m0 + m)) * grid_n) * IVM_O_TILE + gt1 * PX1);
+            const int totalq = sh.qoff[cn];
+            // A2: one queue entry per thread
+#pragma unroll 2
+            for (int e = tid; e < totalq; e += NG1) {
+                int k = 0;
+                while (e >= sh.qoff[k + 1]) ++k;
+                const unsigned o = (unsigned)k * IVM_O_TILE + (unsigned)(e - sh.qoff[k]);
+                const OvlSlot &sl = sh.slot[k];
+                const int pix = sl.tp0 + (int)qpix[o];
+                const int v = pix / P.W, u = pix - v * P.W;
+                float x, y, z;
+                ivm_world_xyz(qd[o], P.xs[u], P.ys[v], sl.T, x, y, z);
+                const float rf = rintf(ivm_div(z, P.half_res));
+                const float cf = rintf(ivm_div(x, P.half_res));
+                const bool rep = fabsf(rf) < 1.0e9f && fabsf(cf) < 1.0e9f;
+                const int32_t r = rep ? (int32_t)rf : 0, c = rep ? (int32_t)cf : 0;
+                const int32_t rr = r - sl.origin_r, cc = c - sl.origin_c;
+                uint32_t cellv = 0xFFFFFFFFu;
+                if (rep && rr >= 0 && rr < P.SR && cc >= 0 && cc < P.SC) {
+                    cellv = ((uint32_t)rr << 16) | (uint32_t)cc;
+                    const size_t w = (size_t)sl.b * P.SR * P.SC + (size_t)rr * P.SC + (size_t)cc;
+                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(&P.cplane[w]));
+                    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(&P.store[w]));
+                    rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
+                    ++nvalid;
+                } else {
+                    atomicOr(&g->err, IVM_ERR_STORE_OVERFLOW);
                 }
-                // pass A: every pixel of the batch -- world point, filters, half-cell; the candidate word and the
-                // world record of the valid ones are PREFETCHED into L2, and the pixel is queued for G3
-                float yk[IVM_O_SUB][PX1];
-                uint32_t cik[IVM_O_SUB][PX1];     // cell index in the env's store window, ~0 = nothing to offer
-#pragma unroll
-                for (int m = 0; m < IVM_O_SUB; ++m) {
-#pragma unroll
-                    for (int j = 0; j < PX1; ++j) { yk[m][j] = 0.f; cik[m][j] = 0xFFFFFFFFu; }
-                    if (m0 + m >= nmine) continue;  // group-uniform
-                    const int k = kbase + kstride * (m0 + m);
-                    OvlSlot &sl = sh.slot[k];
-                    const int tp = gt1 * PX1, pix0 = sl.tp0 + tp;
-                    const int v = pix0 / P.W, u0 = pix0 - v * P.W;
-                    const float ysv = P.ys[v];
-                    float x[PX1], z[PX1];
-                    bool ok[PX1];
-                    bool any = false;
-#pragma unroll
-                    for (int j = 0; j < PX1; ++j) {
-                        const float d = dv[m].v[j];
-                        ivm_world_xyz(d, P.xs[u0 + j], ysv, sl.T, x[j], yk[m][j], z[j]);
-                        ok[j] = d > 0.01f && d < 0.99f && yk[m][j] > sl.hlo && yk[m][j] < sl.hhi;
-                        any = any || ok[j];
-                    }
-                    uint32_t cell[PX1];
-#pragma unroll
-                    for (int j = 0; j < PX1; ++j) cell[j] = 0u;
-                    if (__any_sync(0xffffffffu, any)) {
-                        const size_t ebase = (size_t)sl.b * P.SR * P.SC;
-#pragma unroll
-                        for (int j = 0; j < PX1; ++j) {
-                            const float rf = rintf(ivm_div(z[j], P.half_res));
-                            const float cf = rintf(ivm_div(x[j], P.half_res));
-                            const bool rep = fabsf(rf) < 1.0e9f && fabsf(cf) < 1.0e9f;
-                            const int32_t r = rep ? (int32_t)rf : 0, c = rep ? (int32_t)cf : 0;
-                            const int32_t rr = r - sl.origin_r, cc = c - sl.origin_c;
-                            const bool inside = rep && rr >= 0 && rr < P.SR && cc >= 0 && cc < P.SC;
-                            if (ok[j] && !inside) { atomicOr(&g->err, IVM_ERR_STORE_OVERFLOW); ok[j] = false; }
-                            if (ok[j]) {
-                                const uint32_t ci = (uint32_t)rr * (uint32_t)P.SC + (uint32_t)cc;
-                                cik[m][j] = ci; cell[j] = ((uint32_t)rr << 16) | (uint32_t)cc;
-                                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(&P.cplane[ebase + ci]));
-                                asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(&P.store[ebase + ci]));
-                                rmin = min(rmin, r); rmax = max(rmax, r); cmin = min(cmin, c); cmax = max(cmax, c);
-                                ++nvalid;
-                            }
-                        }
-                        if (keep_queue) {
-                            unsigned mk[PX1];
-                            int n = 0;
-#pragma unroll
-                            for (int j = 0; j < PX1; ++j) { mk[j] = __ballot_sync(0xffffffffu, ok[j]); n += __popc(mk[j]); }
-                            if (n) {  // warp-uniform
-                                unsigned pos = 0;
-                                if (lane == 0) pos = atomicAdd(&sl.qn, (unsigned)n);
-                                pos = __shfl_sync(0xffffffffu, pos, 0);
-                                const unsigned below = (1u << lane) - 1u;
-                                uint32_t *qc = qcell + k * IVM_O_TILE;
-                                uint16_t *qp = qpix + k * IVM_O_TILE;
-#pragma unroll
-                                for (int j = 0; j < PX1; ++j) {
-                                    if (ok[j]) {
-                                        const unsigned o = pos + __popc(mk[j] & below);
-                                        qc[o] = cell[j]; qp[o] = (uint16_t)(tp + j);
-                                    }
-                                    pos += __popc(mk[j]);
-                                }
-                            }
-                        }
-                    }
-                }
-                // pass B: ONE 64-bit RED.MAX per valid pixel into the candidate plane (its line is in L2 or on its way)
-#pragma unroll
-                for (int m = 0; m < IVM_O_SUB; ++m) {
-                    if (m0 + m >= nmine) continue;  // group-uniform
-                    const OvlSlot &sl = sh.slot[kbase + kstride * (m0 + m)];
-                    const int pix0 = sl.tp0 + gt1 * PX1;
-#pragma unroll
-                    for (int j = 0; j < PX1; ++j)
-                        if (cik[m][j] != 0xFFFFFFFFu) {
-                            unsigned long long *w = &P.cplane[(size_t)sl.b * P.SR * P.SC + cik[m][j]];
-                            const unsigned long long key = ivm_cand_key(P, yk[m][j], (uint32_t)(pix0 + j));
-                            asm volatile("red.relaxed.gpu.global.max.u64.L2::cache_hint [%0], %1, %2;" ::"l"(w), "l"(key), "l"(ivm_policy_keep()) : "memory");
-                        }
-                }
+                qcell[o] = cellv;
+            }
+            // B: ONE 64-bit RED.MAX per queue entry into the candidate plane (its line is in L2 or on its way)
+#pragma unroll 2
+            for (int e = tid; e < totalq; e += NG1) {
+                int k = 0;
+                while (e >= sh.qoff[k + 1]) ++k;
+                const unsigned o = (unsigned)k * IVM_O_TILE + (unsigned)(e - sh.qoff[k]);
+                const uint32_t cellv = qcell[o];
+                if (cellv == 0xFFFFFFFFu) continue;
+                const OvlSlot &sl = sh.slot[k];
+                const int pix = sl.tp0 + (int)qpix[o];
+                const int v = pix / P.W, u = pix - v * P.W;
+                const float y = ivm_world_y(qd[o], P.xs[u], P.ys[v], sl.T);
+                unsigned long long *w = &P.cplane[(size_t)sl.b * P.SR * P.SC + (size_t)(cellv >> 16) * P.SC + (size_t)(cellv & 0xFFFFu)];
+                const unsigned long long key = ivm_cand_key(P, y, (uint32_t)pix);
+                asm volatile("red.relaxed.gpu.global.max.u64.L2::cache_hint [%0], %1, %2;" ::"l"(w), "l"(key), "l"(ivm_policy_keep()) : "memory");
             }
         }
         OVL_STAMP(2, 0);
@@ -1269,91 +1257,86 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             if (!keep_queue) {
                 // more tiles than slots: rebuild this chunk's slots (from the published env state) and queues
                 group_bar(1, NG);
-                {
-                    const int role = lane & 7, k = warp + (lane >> 3) * NGW;
-                    if (k < cn) {
-                        OvlSlot &sl = sh.slot[k];
-                        const int tile = cta + (c0 + k) * grid_n;
-                        const int b = tile / tpe;
-                        const IvmEnv *e = &P.env[b];
-                        if (role == 0) {
-                            sl.b = b; sl.tp0 = (tile - b * tpe) * IVM_O_TILE;
-                            sl.origin_r = __ldcg(&e->origin_r); sl.origin_c = __ldcg(&e->origin_c);
-                            sl.reset_stamp = __ldcg(&e->reset_stamp);
-                            sl.h = P.pose[3 * b + 1];
-                            sl.qn = 0u;
-                            sl.box[0] = INT32_MAX; sl.box[1] = INT32_MIN; sl.box[2] = INT32_MAX; sl.box[3] = INT32_MIN; sl.box[4] = 0;
-                        } else if (role == 1) {
-                            for (int i = 0; i < 12; ++i) sl.T[i] = __ldcg(&P.T12[12 * b + i]);
-                        }
-                    }
-                }
+                prep_inputs(c0, cn);
+                prep_state(c0, cn, true);
                 group_bar(1, NG);
-                int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-                unsigned nv = 0;
-                for (int s0 = 0; s0 < cn; s0 += IVM_O_LOADB) {
-                    OvlDepth<PX> dr[IVM_O_LOADB];
-#pragma unroll
-                    for (int k = 0; k < IVM_O_LOADB; ++k) {
-#pragma unroll
-                        for (int j = 0; j < PX; ++j) dr[k].v[j] = 2.0f;
-                        if (s0 + k < cn) dr[k] = ovl_load_depth<PX>(P.depth + (size_t)(cta + (c0 + s0 + k) * grid_n) * IVM_O_TILE + tid * PX);
-                    }
-#pragma unroll
-                    for (int k = 0; k < IVM_O_LOADB; ++k) {
-                        if (s0 + k >= cn) continue;
-                        ovl_tile_pixels<PX, false>(P, sh.slot[s0 + k], dr[k], tid, lane, true, qcell + (s0 + k) * IVM_O_TILE,
-                                                   qpix + (s0 + k) * IVM_O_TILE, r0, r1, r2, r3, nv);
-                    }
+                a1_rest(c0, cn, 0, dv);
+                group_bar(1, NG);
+                queue_prefix(cn);
+                group_bar(1, NG);
+                const int tq = sh.qoff[cn];
+                for (int e = tid; e < tq; e += NG) {
+                    int k = 0;
+                    while (e >= sh.qoff[k + 1]) ++k;
+                    const unsigned o = (unsigned)k * IVM_O_TILE + (unsigned)(e - sh.qoff[k]);
+                    const OvlSlot &sl = sh.slot[k];
+                    const int pix = sl.tp0 + (int)qpix[o];
+                    const int v = pix / P.W, u = pix - v * P.W;
+                    float x, y, z;
+                    ivm_world_xyz(qd[o], P.xs[u], P.ys[v], sl.T, x, y, z);
+                    const float rf = rintf(ivm_div(z, P.half_res));
+                    const float cf = rintf(ivm_div(x, P.half_res));
+                    const bool rep = fabsf(rf) < 1.0e9f && fabsf(cf) < 1.0e9f;
+                    const int32_t rr = (rep ? (int32_t)rf : 0) - sl.origin_r, cc = (rep ? (int32_t)cf : 0) - sl.origin_c;
+                    qcell[o] = (rep && rr >= 0 && rr < P.SR && cc >= 0 && cc < P.SC) ? (((uint32_t)rr << 16) | (uint32_t)cc) : 0xFFFFFFFFu;
                 }
                 group_bar(1, NG);
             }
-            for (int k = 0; k < cn; ++k) {
-                OvlSlot &sl = sh.slot[k];
-                const int n = (int)sl.qn;  // <= IVM_O_TILE = DRAIN * NG: one pass
-                const size_t ebase = (size_t)sl.b * P.SR * P.SC;
-                const size_t pbase = (size_t)sl.b * P.HW + sl.tp0;
-                bool act[DRAIN];
-                uint32_t ce[DRAIN], px[DRAIN], ci[DRAIN];
-                float d[DRAIN];
-                unsigned long long cw[DRAIN];
-                IvmRecord old[DRAIN];
-                uint32_t lab[DRAIN];
-                // all loads of the tile's queue entries first: pixel depth, candidate word, world record (speculative)
+            const int totalq = sh.qoff[cn];
+            for (int e0 = 0; e0 < totalq; e0 += E3 * NG) {
+                bool act[E3];
+                int kk[E3];
+                uint32_t ce[E3], px[E3], lab[E3];
+                float d[E3];
+                unsigned long long cw[E3];
+                IvmRecord old[E3];
+                // all loads of the round first: candidate word, world record (speculative), GT label
 #pragma unroll
-                for (int u = 0; u < DRAIN; ++u) {
-                    const int i = tid + u * NG;
-                    act[u] = i < n;
-                    ce[u] = 0u; px[u] = 0u; ci[u] = 0u; d[u] = 2.0f; cw[u] = 0ull; lab[u] = 0u;
+                for (int u = 0; u < E3; ++u) {
+                    const int e = e0 + u * NG + tid;
+                    act[u] = e < totalq;
+                    kk[u] = 0; ce[u] = 0u; px[u] = 0u; lab[u] = 0u; d[u] = 2.0f; cw[u] = 0ull;
                     old[u].x = old[u].y = old[u].z = 0.f; old[u].meta = 0u;
                     if (act[u]) {
-                        ce[u] = qcell[k * IVM_O_TILE + i]; px[u] = qpix[k * IVM_O_TILE + i];
-                        ci[u] = (ce[u] >> 16) * (uint32_t)P.SC + (ce[u] & 0xFFFFu);
-                        d[u] = __ldcg(P.depth + pbase + px[u]);
-                        cw[u] = ivm_load_ull(&P.cplane[ebase + ci[u]]);
-                        old[u] = ivm_load_record(&P.store[ebase + ci[u]]);
-                        if (!PRED) lab[u] = __ldcg(P.labels + pbase + px[u]);
+                        int k = 0;
+                        while (e >= sh.qoff[k + 1]) ++k;
+                        const unsigned o = (unsigned)k * IVM_O_TILE + (unsigned)(e - sh.qoff[k]);
+                        kk[u] = k; ce[u] = qcell[o]; px[u] = qpix[o]; d[u] = qd[o];
+                        act[u] = ce[u] != 0xFFFFFFFFu;  // outside the store window: flagged by the scatter
+                        if (act[u]) {
+                            const OvlSlot &sl = sh.slot[k];
+                            const size_t w = (size_t)sl.b * P.SR * P.SC + (size_t)(ce[u] >> 16) * P.SC + (size_t)(ce[u] & 0xFFFFu);
+                            cw[u] = ivm_load_ull(&P.cplane[w]);
+                            old[u] = ivm_load_record(&P.store[w]);
+                            if (!PRED) lab[u] = __ldcg(P.labels + (size_t)sl.b * P.HW + sl.tp0 + px[u]);
+                        }
                     }
                 }
-                if (PRED) mbar_wait(&sh.lab_full[k], (uint32_t)(chunk & 1));  // the tile's labels are in shared memory
 #pragma unroll
-                for (int u = 0; u < DRAIN; ++u) {
+                for (int u = 0; u < E3; ++u) {
                     if (!act[u]) continue;
+                    const int k = kk[u];
+                    OvlSlot &sl = sh.slot[k];
                     const uint32_t pix = (uint32_t)sl.tp0 + px[u];
                     const int v = (int)pix / P.W, uu = (int)pix - v * P.W;
                     IvmPoint pt;
                     ivm_world_xyz(d[u], P.xs[uu], P.ys[v], sl.T, pt.x, pt.y, pt.z);
                     if (cw[u] != ivm_cand_key(P, pt.y, pix)) continue;  // another pixel owns the cell
                     pt.r = sl.origin_r + (int32_t)(ce[u] >> 16); pt.c = sl.origin_c + (int32_t)(ce[u] & 0xFFFFu);
-                    const uint32_t label = PRED ? (uint32_t)slab[k * IVM_O_TILE + px[u]] : lab[u];
+                    const size_t w = (size_t)sl.b * P.SR * P.SC + (size_t)(ce[u] >> 16) * P.SC + (size_t)(ce[u] & 0xFFFFu);
+                    uint32_t label = lab[u];
+                    if (PRED) {
+                        mbar_wait(&sh.lab_full[k], (uint32_t)(chunk & 1));  // the tile's labels are in shared memory
+                        label = (uint32_t)slab[k * IVM_O_TILE + px[u]];
+                    }
                     if (ivm_on_frame_edge(pt, loc)) {
-                        ovl_defer_edge(P, sl.b, pix, pt.x, pt.y, pt.z, pt.r, pt.c, label, ebase + ci[u], old[u].x, old[u].y, old[u].z,
+                        ovl_defer_edge(P, sl.b, pix, pt.x, pt.y, pt.z, pt.r, pt.c, label, w, old[u].x, old[u].y, old[u].z,
                                        old[u].meta, sl.reset_stamp, sl.h);
                         continue;
                     }
                     IvmBoxAcc acc;
                     acc.clear();
-                    ivm_merge_record<IvmAtomics>(P, sl.b, ebase + ci[u], pt.r, pt.c, pt.x, pt.y, pt.z, label, old[u], sl.reset_stamp,
+                    ivm_merge_record<IvmAtomics>(P, sl.b, w, pt.r, pt.c, pt.x, pt.y, pt.z, label, old[u], sl.reset_stamp,
                                                  sl.origin_r, sl.origin_c, acc);
                     ++nlocal;
                     if (acc.n) {  // a newly occupied cell: fold into the slot's box
@@ -1362,10 +1345,14 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                         atomicAdd(&sl.box[4], 1);
                     }
                 }
-                if (PRED) {
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sh.lab_empty[k]);  // this warp no longer reads the slot's labels
-                }
+            }
+            if (PRED) {
+                // every label of the chunk has been read by this warp (it waits for the whole chunk's labels first, so that
+                // the argmax warps' protocol does not depend on which tiles had winners)
+                for (int k = 0; k < cn; ++k) mbar_wait(&sh.lab_full[k], (uint32_t)(chunk & 1));
+                __syncwarp();
+                if (lane == 0)
+                    for (int k = 0; k < cn; ++k) mbar_arrive(&sh.lab_empty[k]);
             }
             group_bar(1, NG);
             if (tid < cn && sh.slot[tid].box[4] > 0) {
@@ -1454,9 +1441,18 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         }
     }
     __syncthreads();  // ring and queues are drained: their memory becomes fix-up scratch / raster tiles
-    if (!grid_wait(P.bar, bar_base + 2u * gridDim.x, &sh.flag)) { if (tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER); return; }
+    if (!grid_wait(P.bar, bar_base + 2u * gridDim.x, &sh.flag)) {
+        if (tid == 0) {
+            atomicOr(&g->err, IVM_ERR_GRID_BARRIER);
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(&P.bar[IVM_O_DONE]), "r"(1u) : "memory");
+        }
+        return;
+    }
     if (blockIdx.x == 0 && tid == 0) g->tstamp[2] = global_timer();
     OVL_STAMP(5, 0);
+    // every resolve of this step is done: the next step's kernel may become resident as CTAs of this one exit (it
+    // touches nothing but its own inputs until this kernel has completed)
+    if (tid == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (warp == 0) ovl_global_bands(P, lane, sh.gband);  // before anything of the fix-up can have moved an env box for good
     __syncthreads();
 
@@ -1585,7 +1581,13 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     }
     __syncthreads();
     OVL_STAMP(9, 0);
-    if (tid == 0) atomicMax(&g->tstamp[5], global_timer());
+    if (tid == 0) {
+        atomicMax(&g->tstamp[5], global_timer());
+        // this CTA is done with the map state: a pipelined successor waits for all of these instead of for the
+        // completion of the whole kernel (which is signalled several microseconds after the last CTA has left)
+        __threadfence();
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(&P.bar[IVM_O_DONE]), "r"(1u) : "memory");
+    }
 }
 
 // ------------------------------------------------------------------ known-map store build
@@ -1801,6 +1803,8 @@ struct ivm_ctx {
     size_t ovl_smem[2];
     uint32_t bar_base;    // value of IvmGlobal.bar_count before the next fused launch
     uint32_t team_base;   // same for the fix-up team's arrival counter (k_step_overlap)
+    uint32_t done_base;   // same for the CTAs-done counter: CTAs of all fused launches so far
+    int pipelined;        // ivm_set_pipelined: consecutive steps may overlap (see ivln_map.h)
     int64_t launches;
     // known-mode scratch
     uint32_t *kfill, *ktotals;
@@ -1866,7 +1870,7 @@ static void carve(const ivm_config *c, void *ws, IvmParams *P, ivm_ctx *ctx, siz
     IvmParams q;
     memset(&q, 0, sizeof(q));
     q.g = cv.take<IvmGlobal>(1);
-    q.bar = cv.take<uint32_t>(64);
+    q.bar = cv.take<uint32_t>(128);
     q.cta_trace = cv.take<unsigned long long>((size_t)IVM_TRACE_CTAS * IVM_TRACE_SLOTS);
     q.env = cv.take<IvmEnv>(B);
     float *xs = cv.take<float>(c->width > 0 ? c->width : 1);
@@ -2120,11 +2124,26 @@ static int launch_overlap(ivm_ctx *ctx, IvmParams &P, const float *logits, int n
     if (team > 16) team = 16;
     if (team < 1) team = 1;
     uint32_t team_base = ctx->team_base;
+    int pipelined = ctx->pipelined;
+    uint32_t done_target = ctx->done_base;
     void *args[] = {(void *)&P, (void *)&logits, (void *)&ncls, (void *)&labels_out, (void *)&nenv_total,
-                    (void *)&bar_base, (void *)&max_rows, (void *)&group_bytes, (void *)&stage_cap, (void *)&team, (void *)&team_base};
-    cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(pred ? IVM_O_THREADS_PRED : IVM_O_THREADS_GT), args, smem, st);
-    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaLaunchCooperativeKernel(k_step_overlap)");
+                    (void *)&bar_base, (void *)&max_rows, (void *)&group_bytes, (void *)&stage_cap, (void *)&team, (void *)&team_base,
+                    (void *)&pipelined, (void *)&done_target};
+    // A plain launch of at most as many CTAs as are co-resident (the grid barriers need that, and nothing else of
+    // a cooperative launch), programmatically serialised behind the previous kernel of the stream: when that is
+    // the previous step, this step's CTAs move in while its last ego tiles are still being rastered.
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(pred ? IVM_O_THREADS_PRED : IVM_O_THREADS_GT);
+    lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at; lc.numAttrs = (ctx->cfg.reserved[1] & 64) ? 0 : 1;  // debug bit 64: fully serialised launches
+    cudaError_t e = cudaLaunchKernelExC(&lc, fn, args);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaLaunchKernelExC(k_step_overlap)");
     ctx->bar_base += 5u * (uint32_t)grid;
+    ctx->done_base += (uint32_t)grid;
     if (team > 1) ctx->team_base += (uint32_t)team;
     ctx->launches += 1;
     return IVM_OK;
@@ -2380,6 +2399,12 @@ int ivm_copy_state(ivm_ctx *dst, const ivm_ctx *src, ivm_stream_t stream) {
 #undef IVM_COPY
     dst->step = src->step;
     dst->hi_water = src->hi_water;
+    return IVM_OK;
+}
+
+int ivm_set_pipelined(ivm_ctx *ctx, int32_t enabled) {
+    if (!ctx) return IVM_E_INVALID;
+    ctx->pipelined = enabled ? 1 : 0;
     return IVM_OK;
 }
 

@@ -317,9 +317,12 @@ class _MapEngine:
                 H, W = self.camera.features_spatial_dimensions
                 self.labels_out = torch.zeros((max_envs, int(H), int(W)), dtype=torch.uint8, device=self.device)
 
-    def ensure_capacity(self, num_envs: int):
+    def ensure_capacity(self, num_envs: int) -> bool:
+        """True if a new context was created (its per-context switches have to be set again)."""
         if num_envs > self.max_envs:
             self._create(max(num_envs, 2 * self.max_envs))
+            return True
+        return False
 
     def close(self):
         if self.ctx is not None:
@@ -380,7 +383,8 @@ class MappingModule(nn.Module):
                  maps_location: Optional[str] = None, max_envs: Optional[int] = None,
                  store_cells: int = DEFAULT_STORE_CELLS, known_capacity: int = DEFAULT_KNOWN_CAPACITY,
                  trig: str = "kernel", host_trig: bool = False, raster_tile: int = 0,
-                 track_start_state: bool = False, scatter_variant: int = 0, stamp_period: int = 0):
+                 track_start_state: bool = False, scatter_variant: int = 0, stamp_period: int = 0,
+                 pipelined: bool = False):
         super().__init__()
         assert mode in ("iterative", "known")
         self.device = torch.device(device)
@@ -401,6 +405,7 @@ class MappingModule(nn.Module):
         self._engine_args = dict(store_cells=store_cells, known_capacity=known_capacity, tile=raster_tile,
                                  scatter_variant=scatter_variant, stamp_period=stamp_period)
         self._engine: Optional[_MapEngine] = None
+        self._pipelined = bool(pipelined)
         self._initial_max_envs = max_envs
         self._hold = _Hold()   # per-call state kept off the nn.Module attribute machinery
         self._known_cache: Dict[str, Tuple[torch.Tensor, torch.Tensor, int, int]] = {}
@@ -417,8 +422,21 @@ class MappingModule(nn.Module):
             n = max(num_envs, self._initial_max_envs or 0)
             self._engine = _MapEngine(self.device, self.map_dimensions, self.camera_parameters, self.mode, n,
                                       **self._engine_args)
-        self._engine.ensure_capacity(num_envs)
+            if self._pipelined and self.mode == "iterative":
+                _lib.check(self._engine.lib.ivm_set_pipelined(self._engine.ctx, 1))
+        if self._engine.ensure_capacity(num_envs) and self.mode == "iterative":
+            _lib.check(self._engine.lib.ivm_set_pipelined(self._engine.ctx, 1 if self._pipelined else 0))
         return self._engine
+
+    def set_pipelined(self, enabled: bool = True):
+        """Pipelined stepping (include/ivln_map.h, ivm_set_pipelined): the caller promises that the tensors passed to
+        a forward() call are complete on the stream before the PREVIOUS forward() call was issued (resident or replayed
+        inputs; inputs staged by copies rather than kernels).  Back-to-back calls then overlap on the GPU: the next
+        step's score stream and depth filter run beside the last ego tiles of the current step.  Same results."""
+        self._pipelined = bool(enabled)
+        if self._engine is not None and self.mode == "iterative":
+            _lib.check(self._engine.lib.ivm_set_pipelined(self._engine.ctx, 1 if self._pipelined else 0))
+        return self
 
     def _matrices(self, state: RobotCurrentState):
         pose, elev, head = state.pose, state.elevation, state.heading

@@ -346,3 +346,90 @@ def test_step_statistics_match_oracle(variant):
         assert flags == 0
         want = [orc.counters[k] for k in ("n_valid", "n_local", "n_world", "n_in")]
         assert [int(v) for v in stats[:4]] == want, (t, stats[:4], want)
+
+
+def _run_back_to_back(scn, pipelined, repeat_from=None, **kw):
+    """All inputs resident on the device first, then every step enqueued back to back with nothing in between
+    (consecutive step kernels are programmatically serialised and -- pipelined -- overlap); only the last step's
+    maps and the final world cloud are read back."""
+    from cuda_stepper import CudaStepper
+    from ivlnce_b200.mapper import EpisodesInfo, Observations, RobotCurrentState
+
+    pred = "logits" in scn
+    cs = CudaStepper(scn["cfg"], pred=pred, max_envs=int(scn["num_envs"].max()), trig="kernel", **kw)
+    cs.mm.set_pipelined(pipelined)
+    dev = cs.dev
+    T = scn["masks"].shape[0]
+    B = int(scn["num_envs"][0])
+    assert all(int(b) == B for b in scn["num_envs"])
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    masks, pose, ori = up(scn["masks"]), up(scn["pose"]), up(scn["orientation"])
+    depth = up(scn["depth"]).unsqueeze(2)                       # [T,B,1,H,W]
+    sem = up(scn["logits"]) if pred else up(scn["labels"]).unsqueeze(2)
+    names = [f"scene{b}" for b in range(B)]
+    torch.cuda.synchronize()
+    out = None
+    for t in range(T):
+        ei = EpisodesInfo(masks[t].reshape(B, 1), names)
+        obs = Observations(None, depth[t], sem[t]) if pred else Observations(sem[t], depth[t], None)
+        out = cs.mm(ei, obs, RobotCurrentState(pose[t], ori[t, :, 0], ori[t, :, 1]))
+    torch.cuda.synchronize()
+    return cs, out.occupancy.cpu().numpy(), out.semantic.cpu().numpy()
+
+
+@pytest.mark.parametrize("pipelined", [False, True])
+@pytest.mark.parametrize("name", ["iid_f64", "scene_overlap", "single_long", "identical_envs", "degenerate", "thresholds",
+                                  "predicted"])
+def test_back_to_back_steps_match_reference_golden(name, pipelined):
+    """Steps enqueued back to back overlap on the GPU (the next step's CTAs move in while the current step still
+    rasters).  The last maps and the final world cloud -- which depends on every step -- must still be the
+    reference's, bit for bit."""
+    scn = load_golden(name)
+    assert scn["orientation"].dtype == np.float64
+    cs, occ, sem = _run_back_to_back(scn, pipelined)
+    T = scn["masks"].shape[0]
+    assert np.array_equal(occ, scn["ref_occupancy"][T - 1]) and np.array_equal(sem, scn["ref_semantic"][T - 1])
+    cs.mm.check_errors()
+    b, xyz, s = cs.world()
+    assert np.array_equal(b, scn["ref_world_b"])
+    assert np.array_equal(xyz.view(np.uint32), scn["ref_world_xyz"].view(np.uint32))
+    assert np.array_equal(s, scn["ref_world_sem"])
+
+
+@pytest.mark.parametrize("flags", [128, 128 + 64])
+def test_back_to_back_multi_chunk(flags, monkeypatch):
+    """Same with two tiles per chunk (the queues are rebuilt in the resolve), pipelined."""
+    monkeypatch.setenv("IVM_DEBUG_FLAGS", str(flags))
+    scn = load_golden("iid_f32_res005") if False else load_golden("single_long")
+    cs, occ, sem = _run_back_to_back(scn, True)
+    T = scn["masks"].shape[0]
+    assert np.array_equal(occ, scn["ref_occupancy"][T - 1]) and np.array_equal(sem, scn["ref_semantic"][T - 1])
+    b, xyz, s = cs.world()
+    assert np.array_equal(xyz.view(np.uint32), scn["ref_world_xyz"].view(np.uint32)) and np.array_equal(s, scn["ref_world_sem"])
+
+
+@pytest.mark.parametrize("pred", [False, True])
+def test_back_to_back_full_size_against_oracle(pred):
+    """BASELINE shapes (256x256 depth, 0.05 m cells; 12 envs with 27 GT labels / 6 envs with 40 score planes), 10 steps
+    enqueued back to back in pipelined mode with a mid-run reset: every step kernel runs with its full grid and
+    overlaps its predecessor; final maps + world cloud against the oracle."""
+    from ivlnce_b200.synthetic import ScenarioConfig, make_scenario
+    from oracle.oracle import OracleMapper, argmax_labels
+    from scenarios import _wrap
+
+    B = 6 if pred else 12
+    c = ScenarioConfig(num_envs=B, height=256, width=256, steps=10, resolution=0.05, num_labels=40 if pred else 27,
+                       reset_steps={6: [1, B - 1]}, seed=177, env_spacing=0.0, roam_radius=4.0)
+    scn = _wrap(c, make_scenario(c))
+    if pred:
+        rng = np.random.default_rng(6)
+        scn["logits"] = np.round(rng.standard_normal((c.steps, B, 40, 256, 256)).astype(np.float32) * 4) / 4
+        scn["labels_for_map"] = np.stack([argmax_labels(scn["logits"][t]) for t in range(c.steps)])
+    orc = OracleMapper(c.height, c.width, c.vfov_radians, c.map_meters, c.map_meters, c.resolution)
+    ref_outs, _ = run_mapper(orc.step, scn)
+    cs, occ, sem = _run_back_to_back(scn, True)
+    assert np.array_equal(occ, ref_outs[-1][0]) and np.array_equal(sem, ref_outs[-1][1])
+    cs.mm.check_errors()
+    b1, x1, s1 = orc.world()
+    b2, x2, s2 = cs.world()
+    assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(s1, s2)
