@@ -1130,20 +1130,20 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                     if (++spins > (1u << 22)) { atomicOr(&g->err, IVM_ERR_GRID_BARRIER); break; }
                     __nanosleep(64);
                 }
+                __threadfence();  // acquire; also drops L1 lines this SM may have cached while the previous kernel was still writing
             }
-            __threadfence();  // acquire; also drops L1 lines this SM may have cached while the previous kernel was still writing
             if (blockIdx.x == 0) {
                 g->tstamp[0] = sh.t_start; g->tstamp[5] = 0ull; g->tstamp[6] = global_timer();
                 g->stats[IVM_STAT_IN] = 0ull;  // this step's rastered-record count (added to after grid barrier 2)
                 P.bar[IVM_O_TILE_CTR] = (unsigned)RG * (gridDim.x - (gridDim.x > 1 ? (unsigned)team : 0u));  // raster tiles handed out statically
             }
-            if (blockIdx.x < IVM_TRACE_CTAS) {
-                P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + 7] = sh.t_start;
-                P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + 4] = global_timer();
-                for (int k = 13; k < 16; ++k) P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + k] = 0ull;
-            }
         }
         group_bar(1, NG1);  // covers A1's queues as well
+        if (tid == 64 && blockIdx.x < IVM_TRACE_CTAS) {
+            P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + 7] = sh.t_start;
+            P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + 4] = global_timer();
+            for (int k = 13; k < 16; ++k) P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + k] = 0ull;
+        }
         // paused envs (mapper.py:315-318) are wiped by the last CTA
         if (blockIdx.x == gridDim.x - 1)
             for (int b = P.B; b < nenv_total; ++b) {
@@ -1839,24 +1839,31 @@ static uint32_t edge_capacity(const ivm_config *c) {
 }
 static uint32_t hash_size(uint32_t ecap) { uint32_t h = 1024; while (h < 2 * ecap) h <<= 1; return h; }
 
-// Ego tile of one raster group.  0 = choose: the smallest tile with which all the context's envs together fit the
-// raster groups of one B200 in a single wave (2 x 148 x 3 groups, less the fix-up team's) -- tiles are handed out
-// one per group, so a second, partial wave costs more than larger tiles do.  Measured (us per step, 16 / 32 envs):
-// 16x16 65.5 / 78.5, 24x16 61.4 / 75.9, 32x16 61.4 / 80.6, 32x32 67.2 / 75.4; 1 env: 8x8 37.2, 16x16 39.6;
-// 64 envs: 32x32 159.6, 64x32 154.2.
+// Ego tile of one raster group.  0 = choose.  Tiles are handed out one per group (then dynamically), so what counts
+// is the number of WAVES the context's envs need on the raster groups of one B200 (2 x 148 x 3 groups with a score
+// stream, 3 x 148 x 2 with GT labels, less the fix-up team's: ~840) and the cost of one tile: a fixed part (zeroing,
+// spans, write-out, ~1.6 us) plus the half-cells under the rotated tile (its area with a margin of ~3 cells all
+// round).  The grid of ny x nx tiles per env with the smallest waves x cost is taken; a partial wave counts as a
+// whole one below three waves.  Measured (us per step, 16 / 32 envs, round 1): 16x16 65.5 / 78.5, 24x16 61.4 / 75.9,
+// 32x16 61.4 / 80.6, 32x32 67.2 / 75.4; 1 env: 8x8 37.2, 16x16 39.6.  This picks 22x16 (16 envs), 26x26 (32), 8x8 (1).
 static void tile_dims(const ivm_config *c, int *tr_out, int *tc_out) {
     int tr = c->tile_rows, tc = c->tile_cols;
     if ((tr <= 0 || tc <= 0) && c->mode == 1) {
         tr = 32; tc = 32;  // known-map mode: stand-alone raster kernel, no wave to fit (64 envs: 8x8 128, 16x16 94, 32x32 88-94, 64x32 99 us)
     } else if (tr <= 0 || tc <= 0) {
-        static const int cand[][2] = {{8, 8}, {16, 16}, {24, 16}, {32, 16}, {32, 32}, {64, 32}};
-        const long long wave = 840;
-        tr = 64; tc = 32;
-        for (unsigned i = 0; i < sizeof(cand) / sizeof(cand[0]); ++i) {
-            const long long units = (long long)c->max_envs * ((c->map_rows + cand[i][0] - 1) / cand[i][0]) *
-                                    ((c->map_cols + cand[i][1] - 1) / cand[i][1]);
-            if (units <= wave) { tr = cand[i][0]; tc = cand[i][1]; break; }
-        }
+        const double groups = 840.0, fixed = 150.0, margin = 6.0;
+        double best = 1.0e300;
+        tr = c->map_rows < 64 ? c->map_rows : 64; tc = c->map_cols < 64 ? c->map_cols : 64;
+        for (int ny = 1; ny <= 32; ++ny)
+            for (int nx = 1; nx <= 32; ++nx) {
+                const int r = (c->map_rows + ny - 1) / ny, q = (c->map_cols + nx - 1) / nx;
+                if (r > 64 || q > 64 || (r < 8 && r < c->map_rows) || (q < 8 && q < c->map_cols)) continue;
+                if ((c->map_rows + r - 1) / r != ny || (c->map_cols + q - 1) / q != nx) continue;  // same tile, fewer of them
+                const double waves = (double)c->max_envs * ny * nx / groups;
+                const double w = waves < 3.0 ? ceil(waves) : waves + 0.5;
+                const double cost = w * (fixed + (r + margin) * (q + margin)) * (1.0 + 0.02 * fabs((double)r - q) / (r + q));
+                if (cost < best) { best = cost; tr = r; tc = q; }
+            }
     }
     if (tr > c->map_rows) tr = c->map_rows;
     if (tc > c->map_cols) tc = c->map_cols;

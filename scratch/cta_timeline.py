@@ -25,12 +25,12 @@ for t in range(300, 300 + N):
 acc /= N
 # stamps of k_step_overlap: 7 start, 10 G1 (scatter) done, 0 past barrier 1, 3 G3 (resolve) done, 6 argmax warps done,
 # 5 past barrier 2, 8 raster start, 9 end
-names = {7: "start", 1: "G1.prep", 2: "G1.pixels", 10: "G1.done", 0: "bar1.passed", 3: "G3.done", 6: "argmax.done", 5: "bar2.passed", 11: "D1.end", 8: "D.start", 9: "D.end"}
+names = {7: "start", 12: "A1.done", 4: "dep.passed", 1: "G1.prep", 2: "G1.pixels", 10: "G1.done", 0: "bar1.passed", 3: "G3.done", 6: "argmax.done", 5: "bar2.passed", 11: "D1.end", 8: "D.start", 9: "D.end"}
 print("stamp          min    mean     max   (us since first CTA start, mean over %d steps)" % N)
-for k in [7, 1, 2, 10, 0, 3, 6, 5, 11, 8, 9]:
+for k in [7, 12, 4, 1, 2, 10, 0, 3, 6, 5, 11, 8, 9]:
     print(f"{names[k]:12s} {acc[:, k].min():7.2f} {acc[:, k].mean():7.2f} {acc[:, k].max():7.2f}")
 d = lambda a, b: acc[:, a] - acc[:, b]
-for nm, a, b in [("G1 prep", 1, 7), ("G1 pixels", 2, 1), ("G1 flush", 10, 2), ("G1 work", 10, 7), ("barrier1 wait", 0, 10), ("G3 work", 3, 0), ("argmax total", 6, 7), ("G3 tail after argmax", 3, 6), ("barrier2 wait", 5, 3), ("safe raster / fix-up", 11, 5), ("release wait", 8, 11), ("D2 work", 9, 8)]:
+for nm, a, b in [("prep+A1 filter", 12, 7), ("state prep", 1, 4), ("A2+B", 2, 1), ("G1 flush", 10, 2), ("G1 work", 10, 7), ("barrier1 wait", 0, 10), ("G3 work", 3, 0), ("argmax total", 6, 7), ("G3 tail after argmax", 3, 6), ("barrier2 wait", 5, 3), ("safe raster / fix-up", 11, 5), ("release wait", 8, 11), ("D2 work", 9, 8)]:
     x = d(a, b)
     print(f"{nm:22s} min {x.min():6.2f} mean {x.mean():6.2f} max {x.max():6.2f}")
 

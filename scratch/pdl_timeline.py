@@ -25,9 +25,9 @@ for rep in range(N):
     rel[:, 13:16] = tr[:, 13:16] / 1e3
     acc = rel if acc is None else acc + rel
 acc /= N
-nm = {7: "resident", 4: "dep.wait passed", 1: "G1.prep", 2: "G1.pixels", 10: "G1.done", 0: "bar1.passed", 3: "G3.done", 6: "argmax.done", 5: "bar2.passed", 11: "D1.end", 8: "D.start", 9: "D.end"}
+nm = {7: "resident", 12: "A1.done", 4: "dep.wait passed", 1: "G1.prep", 2: "G1.pixels", 10: "G1.done", 0: "bar1.passed", 3: "G3.done", 6: "argmax.done", 5: "bar2.passed", 11: "D1.end", 8: "D.start", 9: "D.end"}
 print(f"{wl}: stamp            min    mean     max   (us since the previous kernel completed, mean over {N} runs of 30 steps)")
-for k in [7, 4, 1, 2, 10, 0, 3, 6, 5, 11, 8, 9]:
+for k in [7, 12, 4, 1, 2, 10, 0, 3, 6, 5, 11, 8, 9]:
     if k == 6 and not cfg["pred"]: continue
     print(f"{nm[k]:16s} {acc[:, k].min():7.2f} {acc[:, k].mean():7.2f} {acc[:, k].max():7.2f}")
 order_end = np.argsort(-acc[:, 9])[:5]
