@@ -139,6 +139,7 @@ struct IvmGlobal {
     uint32_t scan_chunks;         // chunks of IVM_SCAN_CHUNK cells per edge-line segment (longest segment)
     uint32_t prev_n_seg, prev_scan_chunks;  // last step's edge-line segments (still in P.segs): prefetch hints for the scan
     unsigned long long acc_valid, acc_local;  // per-step accumulators (K1 / K2+F), published and zeroed by F
+    unsigned long long acc_e1, acc_e2;        // direct path: frame-edge winners examined / live records on the world edge lines
     unsigned long long stats[IVM_NSTATS];     // published figures of the last step; stats[IN] accumulates in K4
     // fused step kernel only
     unsigned long long tstamp[8];             // %globaltimer at the phase boundaries of the last fused step:
@@ -507,7 +508,7 @@ IVM_HD_COLD void ivm_pose_matrices(const IvmParams &P, int b, float *T, float *c
 IVM_HD void ivm_reset_step_globals(IvmGlobal *g, bool reset_rastered = true) {
     g->loc[0] = INT32_MAX; g->loc[1] = INT32_MIN; g->loc[2] = INT32_MAX; g->loc[3] = INT32_MIN;
     g->n_e1 = 0; g->n_e2 = 0; g->n_seg = 0; g->any_dirty = 0;
-    g->acc_valid = 0; g->acc_local = 0;
+    g->acc_valid = 0; g->acc_local = 0; g->acc_e1 = 0; g->acc_e2 = 0;
     // (the persistent step kernel rasters BESIDE the fix-up: it zeroes this one at its start instead)
     if (reset_rastered) g->stats[IVM_STAT_IN] = 0;
 }
@@ -554,6 +555,25 @@ IVM_HD int ivm_resolve_pixel(const IvmParams &P, int b, uint32_t pix, const IvmP
     if (ivm_on_frame_edge(p, loc)) {
         ivm_push_edge1<A>(P, b, pix, p, label, idx);
         return 0;
+    }
+    ivm_merge_into_world<A>(P, b, idx, p.r, p.c, p.x, p.y, p.z, label, acc);
+    return 1;
+}
+
+// the same with the direct resolution of frame-edge collisions (ivm_frame_edge_loses, defined below): an edge winner
+// merges at once or is dropped; nothing is deferred.  Only valid for a direct frame box (ivm_box_direct(loc)).
+IVM_HD bool ivm_frame_edge_loses(const IvmParams &P, int b, int32_t r, int32_t c, uint32_t ord, unsigned long long xorder,
+                                 const int32_t *loc);
+template <class A>
+IVM_HD int ivm_resolve_pixel_direct(const IvmParams &P, int b, uint32_t pix, const IvmPoint &p, uint32_t label,
+                                    const int32_t *loc, int32_t origin_r, int32_t origin_c, IvmBoxAcc &acc) {
+    size_t idx;
+    if (!ivm_store_index(P, origin_r, origin_c, b, p.r, p.c, idx)) return 0;
+    const uint32_t cell = (uint32_t)(idx - (size_t)b * P.SR * P.SC);
+    if (ivm_cand_lookup(P, b, cell) != ivm_cand_key(P, p.y, pix)) return 0;
+    if (ivm_on_frame_edge(p, loc)) {
+        A::add_ull(&P.g->acc_e1, 1ull);
+        if (ivm_frame_edge_loses(P, b, p.r, p.c, ivm_orderable(p.y), (unsigned long long)b * (unsigned long long)P.HW + pix, loc)) return 0;
     }
     ivm_merge_into_world<A>(P, b, idx, p.r, p.c, p.x, p.y, p.z, label, acc);
     return 1;
@@ -668,29 +688,24 @@ IVM_HD_COLD void ivm_scan_edge_cell(const IvmParams &P, int b, int32_t r, int32_
     P.e2[k] = ed;
 }
 
-// exact bbox of the envs that lost records, from the per-row / per-column live counts
-// The new box is built in the scratch fields `nb` and then stored field by field: in the persistent step kernel
-// other CTAs raster ego tiles meanwhile and read rmin..cmax; they must see the old or the new value of a field
-// (both bound the live records; deletions only shrink the box), never an intermediate one.
+// exact bbox of the envs that lost records, from the per-row / per-column live counts.  Deletions only shrink a
+// box, so each side walks INWARD from its old extreme to the first row / column that still holds a record (usually
+// the extreme itself): one thread per (dirty env, side).  The fields are stored one by one: in the persistent step
+// kernel other CTAs raster ego tiles meanwhile and read rmin..cmax; they must see the old or the new value of a field
+// (both bound the live records), never an intermediate one.
 template <class A>
 IVM_HD_COLD void ivm_rebuild_dirty_boxes(const IvmParams &P, int tid, int nthreads) {
-    for (int b = tid; b < P.B; b += nthreads) {
-        IvmEnv *e = &P.env[b];
-        if (e->dirty) { e->nb[0] = INT32_MAX; e->nb[1] = INT32_MIN; e->nb[2] = INT32_MAX; e->nb[3] = INT32_MIN; }
-    }
-    A::sync();
-    const long long per_env = (long long)P.SR + P.SC;
-    for (long long i = tid; i < per_env * P.B; i += nthreads) {
-        const int b = (int)(i / per_env);
+    for (int i = tid; i < 4 * P.B; i += nthreads) {
+        const int b = i >> 2, side = i & 3;
         IvmEnv *e = &P.env[b];
         if (!e->dirty) continue;
-        const int j = (int)(i - (long long)b * per_env);
-        if (j < P.SR) {
-            if (P.rowcount[(size_t)b * P.SR + j] > 0) { A::min_i(&e->nb[0], e->origin_r + j); A::max_i(&e->nb[1], e->origin_r + j); }
-        } else {
-            const int jc = j - P.SR;
-            if (P.colcount[(size_t)b * P.SC + jc] > 0) { A::min_i(&e->nb[2], e->origin_c + jc); A::max_i(&e->nb[3], e->origin_c + jc); }
-        }
+        const int32_t *cnt = (side < 2) ? P.rowcount + (size_t)b * P.SR : P.colcount + (size_t)b * P.SC;
+        const int32_t org = (side < 2) ? e->origin_r : e->origin_c;
+        const int32_t lo = (side < 2) ? e->rmin : e->cmin, hi = (side < 2) ? e->rmax : e->cmax;
+        int32_t v;
+        if ((side & 1) == 0) { v = lo; while (v <= hi && ivm_load_u32((const uint32_t *)&cnt[v - org]) == 0u) ++v; if (v > hi) v = INT32_MAX; }
+        else { v = hi; while (v >= lo && ivm_load_u32((const uint32_t *)&cnt[v - org]) == 0u) --v; if (v < lo) v = INT32_MIN; }
+        e->nb[side] = v;
     }
     A::sync();
     for (int b = tid; b < P.B; b += nthreads) {
@@ -699,6 +714,114 @@ IVM_HD_COLD void ivm_rebuild_dirty_boxes(const IvmParams &P, int tid, int nthrea
         e->rmin = e->nb[0]; e->rmax = e->nb[1]; e->cmin = e->nb[2]; e->cmax = e->nb[3];
         e->dirty = 0;
     }
+}
+
+// ---------------------------------------------------------------------------
+// Direct resolution of the edge collisions (the fast path of both de-dup stages).
+// With the reference's key  b*(R'C') + r'*C' + c'  (strides max, not max+1) and a box of at least 3 rows and
+// 2 columns (R' >= 2, C' >= 1), a key class has at most three member cells, and they can be written down:
+// for env b2 in {b-1, b, b+1} the value M = m - (b2-b)*R'C' (m = r'C' + c') decomposes as r2*C' + c2 in at most two
+// ways -- (M / C', M % C') and, when the remainder is 0, (M / C' - 1, C').  So instead of grouping edge entries
+// by key (lists, hashing, one thread block), every edge cell LOOKS UP its few partner cells and decides on its
+// own whether it survives: it loses iff a partner holds a point that is higher, or as high and earlier in the
+// reference's list.  That is a strict total order, so exactly the class winner survives, as in the reference.
+struct IvmPartner { int32_t b, r, c; };   // env, ABSOLUTE half-row / half-col
+#define IVM_MAX_PARTNERS 5
+IVM_HD bool ivm_box_direct(const int32_t *box) {  // box = rmin, rmax, cmin, cmax (a valid box)
+    return (long long)box[1] - box[0] >= 2 && (long long)box[3] - box[2] >= 1;
+}
+IVM_HD int ivm_partners(int b, int32_t r, int32_t c, const int32_t *box, int B, IvmPartner *out) {
+    const long long Rx = (long long)box[1] - box[0], Cx = (long long)box[3] - box[2], S = Rx * Cx;
+    const long long rr = (long long)r - box[0], cc = (long long)c - box[2], m = rr * Cx + cc;
+    int n = 0;
+    for (int db = -1; db <= 1; ++db) {
+        const int b2 = b + db;
+        if (b2 < 0 || b2 >= B) continue;
+        const long long M = m - (long long)db * S;
+        if (M < 0 || M > S + Cx) continue;
+        // (the quotient of two 64-bit integers is slow on the device: the values fit 32 bits unless envs lie far apart)
+        const long long r2 = (M < 0x7FFFFFFFll && Cx < 0x7FFFFFFFll) ? (long long)((uint32_t)M / (uint32_t)Cx) : M / Cx;
+        const long long c2 = M - r2 * Cx;
+        if (r2 <= Rx && !(db == 0 && r2 == rr && c2 == cc)) {
+            out[n].b = b2; out[n].r = (int32_t)(r2 + box[0]); out[n].c = (int32_t)(c2 + box[2]); ++n;
+        }
+        if (c2 == 0 && r2 >= 1 && r2 - 1 <= Rx && !(db == 0 && r2 - 1 == rr && Cx == cc)) {
+            out[n].b = b2; out[n].r = (int32_t)(r2 - 1 + box[0]); out[n].c = (int32_t)(Cx + box[2]); ++n;
+        }
+    }
+    return n;
+}
+// stage 1: does the frame winner (height order `ord`, list position `xorder` = b*HW + pixel) of an edge cell of
+// the frame box `loc` lose its collision class?  The partners' winners sit in the candidate plane (every scatter
+// of the step has completed).  The envs' store windows are read as published this step.
+IVM_HD bool ivm_frame_edge_loses(const IvmParams &P, int b, int32_t r, int32_t c, uint32_t ord, unsigned long long xorder,
+                                 const int32_t *loc) {
+    IvmPartner pt[IVM_MAX_PARTNERS];
+    const int n = ivm_partners(b, r, c, loc, P.B, pt);
+    const int pb = P.pix_bits;
+    bool lose = false;
+    for (int i = 0; i < n; ++i) {
+        const IvmEnv *e = &P.env[pt[i].b];
+        size_t idx;
+        if (!ivm_store_index(P, (int32_t)ivm_load_u32((const uint32_t *)&e->origin_r), (int32_t)ivm_load_u32((const uint32_t *)&e->origin_c),
+                             pt[i].b, pt[i].r, pt[i].c, idx)) continue;
+        const unsigned long long w = ivm_load_ull(&P.cplane[idx]);
+        if ((uint32_t)(w >> (32 + pb)) != P.cstamp) continue;  // nothing offered to that cell this step
+        const uint32_t po = (uint32_t)(w >> pb);
+        const unsigned long long px = (unsigned long long)pt[i].b * (unsigned long long)P.HW +
+                                      (unsigned long long)(((1u << pb) - 1u) - (uint32_t)(w & ((1ull << pb) - 1ull)));
+        lose = lose || po > ord || (po == ord && px < xorder);
+    }
+    return lose;
+}
+// position of a live world record in the concatenated list [world(t-1) ; frame survivors] (see ivm_scan_edge_cell)
+IVM_HD unsigned long long ivm_world_xorder(const IvmParams &P, int b, int32_t r, int32_t c, uint32_t meta, const int32_t *loc) {
+    const IvmGlobal *g = P.g;
+    if ((meta >> 8) == P.step)
+        return (1ull << 62) | ivm_list_key(b, r, c, loc[0], loc[2], (long long)loc[1] - loc[0], (long long)loc[3] - loc[2]);
+    return ivm_list_key(b, r, c, g->prev_rmin, g->prev_cmin, g->prev_R, g->prev_C);
+}
+// stage 2: does the live record `rec` of edge cell (b, r, c) of the world box `glob` lose its collision class?
+IVM_HD bool ivm_world_edge_loses(const IvmParams &P, int b, int32_t r, int32_t c, const IvmRecord &rec, const int32_t *glob,
+                                 const int32_t *loc) {
+    IvmPartner pt[IVM_MAX_PARTNERS];
+    const int n = ivm_partners(b, r, c, glob, P.B, pt);
+    if (n == 0) return false;
+    const uint32_t ord = ivm_orderable(rec.y);
+    const unsigned long long xo = ivm_world_xorder(P, b, r, c, rec.meta, loc);
+    bool lose = false;
+    for (int i = 0; i < n; ++i) {
+        const IvmEnv *e = &P.env[pt[i].b];
+        size_t idx;
+        if (!ivm_store_index(P, e->origin_r, e->origin_c, pt[i].b, pt[i].r, pt[i].c, idx)) continue;
+        const IvmRecord q = ivm_load_record(&P.store[idx]);
+        if (!ivm_live(q.meta, e->reset_stamp)) continue;
+        const uint32_t po = ivm_orderable(q.y);
+        lose = lose || po > ord || (po == ord && ivm_world_xorder(P, pt[i].b, pt[i].r, pt[i].c, q.meta, loc) < xo);
+    }
+    return lose;
+}
+// a loser of stage 2 joins the deletion list (the e2 list, every entry marked as a loser)
+template <class A>
+IVM_HD void ivm_push_loser(const IvmParams &P, int b, int32_t r, int32_t c, size_t idx) {
+    const uint32_t k = A::add_u(&P.g->n_e2, 1u);
+    if (k >= P.ecap) { A::or_u(&P.g->err, IVM_ERR_EDGE_OVERFLOW); return; }
+    IvmEdge ed;
+    ed.x = ed.y = ed.z = 0.f; ed.label = 0u; ed.b = b; ed.r = r; ed.c = c; ed.slot = 0xFFFFFFFFu; ed.xorder = 0ull;
+    ed.addr = idx;
+    P.e2[k] = ed;
+}
+// one store cell of an edge line of the world box, direct path: a live record that loses is listed for deletion;
+// returns 1 if the cell holds a live record (statistics)
+template <class A>
+IVM_HD_COLD int ivm_direct_edge_cell(const IvmParams &P, int b, int32_t r, int32_t c, int32_t origin_r, int32_t origin_c,
+                                uint32_t reset_stamp, const int32_t *glob, const int32_t *loc) {
+    size_t idx;
+    if (!ivm_store_index(P, origin_r, origin_c, b, r, c, idx)) return 0;
+    const IvmRecord rec = ivm_load_record(&P.store[idx]);
+    if (!ivm_live(rec.meta, reset_stamp)) return 0;
+    if (ivm_world_edge_loses(P, b, r, c, rec, glob, loc)) ivm_push_loser<A>(P, b, r, c, idx);
+    return 1;
 }
 
 // F: the edge fix-up of both de-dup stages + bbox bookkeeping, in three parts so that the fused
@@ -887,12 +1010,146 @@ IVM_HD void ivm_fixup_scan_block(const IvmParams &P, const IvmFixScratch &S, int
     A::sync();  // the staged headers are dead: the scratch goes back to the class resolution
 }
 
+// Direct path of the edge-line scan.  The segments (which env touches which edge line of the world box `glob`, and
+// where) are derived from the env boxes by ONE warp-sized group of threads (tid < 32) in a fixed order, so that every
+// block of a team builds the same table on its own: hdr[q] = b, is_col, line, len, lo, origin_r, origin_c,
+// reset_stamp (IVM_SCAN_HDR ints).  Returns the segment count through counts[0] and the longest segment through
+// counts[1]; counts[0] = -1 if the table would not fit `cap` segments.  `tb` = scratch of P.B bytes (block memory).
+#if defined(__CUDA_ARCH__)
+#define IVM_BALLOT(p) __ballot_sync(0xffffffffu, (p))
+#define IVM_LANES 32
+#else
+#define IVM_BALLOT(p) ((p) ? 1u : 0u)
+#define IVM_LANES 1
+#endif
+IVM_HD_COLD void ivm_direct_segments(const IvmParams &P, const int32_t *glob, int32_t *hdr, int cap, int32_t *counts, int lane,
+                                     uint8_t *tb) {
+    // pass 1: which edge lines does each env touch?  (its box is exact, so touching = holding a live record there)
+    // bit 0 first row, bit 1 last row, bit 2 first column, bit 3 last column of the world box
+    for (int b = lane; b < P.B; b += IVM_LANES) {
+        const IvmEnv *e = &P.env[b];
+        unsigned t = 0;
+        if (e->count > 0)
+            t = (e->rmin == glob[0] ? 1u : 0u) | ((e->rmax == glob[1] && glob[1] != glob[0]) ? 2u : 0u) |
+                (e->cmin == glob[2] ? 4u : 0u) | ((e->cmax == glob[3] && glob[3] != glob[2]) ? 8u : 0u);
+        tb[b] = (uint8_t)t;
+    }
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+    // pass 2: a line of env b has to be scanned only if a cell that can share a key with one of its cells may be live.
+    // Keys are shared between (b: last column) ~ (b: first column), and between the last row / last column of env b and
+    // the first row / first column of env b+1 (ivm_partners); so the "max" lines (last row, last column) of env b matter
+    // iff env b touches the first column or env b+1 touches a "min" line, and the "min" lines of env b iff env b touches
+    // the last column or env b-1 touches a "max" line.  In the usual case -- the four edge lines are touched by four
+    // unrelated envs -- nothing has to be scanned at all.
+    int nseg = 0, longest = 0;
+    bool fits = true;
+    const int lines[4] = {glob[0], glob[1], glob[2], glob[3]};
+    for (int b0 = 0; b0 < P.B; b0 += IVM_LANES) {
+        const int b = b0 + lane;
+        bool touch[4] = {false, false, false, false};
+        IvmEnv e;
+        e.count = 0; e.rmin = e.rmax = e.cmin = e.cmax = 0; e.origin_r = e.origin_c = 0; e.reset_stamp = 0;
+        if (b < P.B) {
+            const unsigned t = tb[b], tn = (b + 1 < P.B) ? tb[b + 1] : 0u, tp = (b >= 1) ? tb[b - 1] : 0u;
+            const bool need_max = (t & 4u) || (tn & 5u), need_min = (t & 8u) || (tp & 10u);
+            touch[0] = (t & 1u) && need_min; touch[1] = (t & 2u) && need_max;
+            touch[2] = (t & 4u) && need_min; touch[3] = (t & 8u) && need_max;
+            if (touch[0] || touch[1] || touch[2] || touch[3]) e = P.env[b];
+        }
+        for (int s = 0; s < 4; ++s) {
+            const unsigned m = IVM_BALLOT(touch[s]);
+            if (touch[s]) {
+                const int q = nseg + __builtin_popcount(m & ((1u << lane) - 1u));
+                if (q < cap) {
+                    int32_t *h = hdr + IVM_SCAN_HDR * q;
+                    h[0] = b; h[1] = s >> 1; h[2] = lines[s];
+                    h[3] = (s >> 1) ? e.rmax - e.rmin + 1 : e.cmax - e.cmin + 1;
+                    h[4] = (s >> 1) ? e.rmin : e.cmin; h[5] = e.origin_r; h[6] = e.origin_c; h[7] = (int32_t)e.reset_stamp;
+                } else {
+                    fits = false;
+                }
+            }
+            nseg += __builtin_popcount(m);
+            int len = touch[s] ? ((s >> 1) ? e.rmax - e.rmin + 1 : e.cmax - e.cmin + 1) : 0;
+#if defined(__CUDA_ARCH__)
+            len = __reduce_max_sync(0xffffffffu, len);
+            fits = __all_sync(0xffffffffu, fits);
+#endif
+            longest = len > longest ? len : longest;
+        }
+    }
+    if (lane == 0) { counts[0] = fits ? nseg : -1; counts[1] = longest; }
+}
+// The cells of the staged segments, shared by `nblk` blocks: metas first (independent loads), then every live cell
+// decides for itself (ivm_direct_edge_cell).  Returns the live records this thread found.
 template <class A>
-IVM_HD void ivm_fixup_stage2(const IvmParams &P, const IvmFixScratch &S, int tid, int nthreads) {
+IVM_HD_COLD int ivm_direct_scan(const IvmParams &P, const int32_t *hdr, int nseg, int longest, const int32_t *glob, const int32_t *loc,
+                           int blk, int nblk, int tid, int nthreads) {
+    if (nseg <= 0 || longest <= 0) return 0;
+    const int span = ((longest + IVM_SCAN_CHUNK - 1) / IVM_SCAN_CHUNK) * IVM_SCAN_CHUNK;
+    const long long total = (long long)span * nseg;
+    const int gthreads = nthreads * nblk, gtid = blk * nthreads + tid;
+    int nlive = 0;
+    for (long long base = 0; base < total; base += (long long)gthreads * IVM_SCAN_MLP) {
+        uint32_t meta[IVM_SCAN_MLP];
+#pragma unroll
+        for (int j = 0; j < IVM_SCAN_MLP; ++j) {
+            meta[j] = 0u;
+            const long long i = base + (long long)j * gthreads + gtid;
+            if (i >= total) continue;
+            const int q = (int)(i / span), off = (int)(i - (long long)q * span);
+            const int32_t *h = hdr + IVM_SCAN_HDR * q;
+            if (off >= h[3]) continue;
+            const int32_t v = h[4] + off;
+            if (h[1] && (v == glob[0] || v == glob[1])) continue;  // corners belong to the row scans
+            size_t idx;
+            if (!ivm_store_index(P, h[5], h[6], h[0], h[1] ? v : h[2], h[1] ? h[2] : v, idx)) continue;
+            meta[j] = ivm_load_meta(&P.store[idx]);
+        }
+#pragma unroll
+        for (int j = 0; j < IVM_SCAN_MLP; ++j) {
+            if (meta[j] == 0u) continue;
+            const long long i = base + (long long)j * gthreads + gtid;
+            const int q = (int)(i / span), off = (int)(i - (long long)q * span);
+            const int32_t *h = hdr + IVM_SCAN_HDR * q;
+            if (!ivm_live(meta[j], (uint32_t)h[7])) continue;
+            const int32_t v = h[4] + off;
+            nlive += ivm_direct_edge_cell<A>(P, h[0], h[1] ? v : h[2], h[1] ? h[2] : v, h[5], h[6], (uint32_t)h[7], glob, loc);
+        }
+    }
+    return nlive;
+}
+
+// the listed losers (slot == 0xFFFFFFFF) of the e2 list leave the store: entries first, first + stride, ...
+template <class A>
+IVM_HD void ivm_delete_losers(const IvmParams &P, uint32_t n2, uint32_t first, uint32_t stride) {
+    IvmGlobal *g = P.g;
+    for (uint32_t i = first; i < n2; i += stride) {
+        const IvmEdge ed = P.e2[i];
+        if (ed.slot != 0xFFFFFFFFu) continue;
+        IvmEnv *e = &P.env[ed.b];
+        P.store[(size_t)ed.addr].meta = 0u;  // merged away for good
+        A::add_i(&P.rowcount[(size_t)ed.b * P.SR + (ed.r - e->origin_r)], -1);
+        A::add_i(&P.colcount[(size_t)ed.b * P.SC + (ed.c - e->origin_c)], -1);
+        A::add_i(&e->count, -1);
+        e->dirty = 1;
+        g->any_dirty = 1u;
+        A::add_ull(&g->stats[IVM_STAT_MERGED], 1ull);
+    }
+}
+
+// stage 2 in two halves: `resolve` = the class resolution over the e2 list (generic path); `finish` = deletion of the
+// listed losers, bbox rebuild, release of the deferred raster tiles, bookkeeping.  The direct path lists only losers
+// (already marked) and calls the second half alone; e1_stat / e2_stat = the figures to publish.
+template <class A>
+IVM_HD void ivm_fixup_stage2(const IvmParams &P, const IvmFixScratch &S, int tid, int nthreads, bool resolve = true,
+                             uint32_t e1_stat = 0xFFFFFFFFu, uint32_t e2_stat = 0xFFFFFFFFu, bool deleted = false) {
     IvmGlobal *g = P.g;
     const int32_t grmin = g->glob[0], grmax = g->glob[1], gcmin = g->glob[2], gcmax = g->glob[3];
     const bool alive = grmin <= grmax;
-    const uint32_t n1 = g->n_e1 < P.ecap ? g->n_e1 : P.ecap;
+    const uint32_t n1 = e1_stat != 0xFFFFFFFFu ? e1_stat : (g->n_e1 < P.ecap ? g->n_e1 : P.ecap);
     uint32_t n2 = 0;
     if (tid == 0) { S.ibuf[5] = 0; S.lbuf[0] = 0ull; }
     A::sync();
@@ -900,24 +1157,14 @@ IVM_HD void ivm_fixup_stage2(const IvmParams &P, const IvmFixScratch &S, int tid
     if (alive) {
         // ---- stage 2: collisions on the world bbox edge (mapper.py:844-847)
         n2 = g->n_e2 < P.ecap ? g->n_e2 : P.ecap;
-        if (n2 > 1) {
-            ivm_resolve_classes<A>(P, P.e2, n2, grmin, gcmin, (long long)grmax - grmin, (long long)gcmax - gcmin, S, tid,
-                                   nthreads);
-            for (uint32_t i = tid; i < n2; i += nthreads) {
-                const IvmEdge ed = P.e2[i];
-                if (ed.slot != 0xFFFFFFFFu) continue;
-                IvmEnv *e = &P.env[ed.b];
-                P.store[(size_t)ed.addr].meta = 0u;  // merged away for good
-                A::add_i(&P.rowcount[(size_t)ed.b * P.SR + (ed.r - e->origin_r)], -1);
-                A::add_i(&P.colcount[(size_t)ed.b * P.SC + (ed.c - e->origin_c)], -1);
-                A::add_i(&e->count, -1);
-                e->dirty = 1;
-                S.ibuf[5] = 1;
-                A::add_ull(&g->stats[IVM_STAT_MERGED], 1ull);
-            }
+        if (resolve ? n2 > 1 : n2 > 0) {
+            if (resolve)
+                ivm_resolve_classes<A>(P, P.e2, n2, grmin, gcmin, (long long)grmax - grmin, (long long)gcmax - gcmin, S, tid,
+                                       nthreads);
+            if (!deleted) ivm_delete_losers<A>(P, n2, (uint32_t)tid, (uint32_t)nthreads);  // (else: the team has done it)
             A::sync();
             // ---- rebuild the bbox of envs that lost records
-            if (S.ibuf[5]) ivm_rebuild_dirty_boxes<A>(P, tid, nthreads);
+            if (ivm_load_u32(&g->any_dirty)) ivm_rebuild_dirty_boxes<A>(P, tid, nthreads);
         }
         IVM_TRACE(g, 5, tid);
     }
@@ -948,7 +1195,7 @@ IVM_HD void ivm_fixup_stage2(const IvmParams &P, const IvmFixScratch &S, int tid
         g->stats[IVM_STAT_LOCAL] = g->acc_local;
         g->stats[IVM_STAT_WORLD] = S.lbuf[0];
         g->stats[IVM_STAT_E1] = n1;
-        g->stats[IVM_STAT_E2] = n2;
+        g->stats[IVM_STAT_E2] = e2_stat != 0xFFFFFFFFu ? e2_stat : n2;
         g->stats[7] = ((unsigned long long)g->n_seg << 32) | ((unsigned long long)g->scan_chunks * IVM_SCAN_CHUNK);
         g->prev_n_seg = g->n_seg; g->prev_scan_chunks = g->scan_chunks;
         ivm_reset_step_globals(g, S.release == nullptr);

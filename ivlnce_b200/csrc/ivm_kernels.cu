@@ -761,7 +761,8 @@ __global__ void __launch_bounds__(IVM_RASTER_THREADS) k_raster(IvmParams P, int 
 
 __global__ void k_pose(IvmParams P) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b < P.B) ivm_pose_matrices(P, b, P.T12_buf + 12 * b, P.cs_buf + 2 * b);
+    if (b == 0) P.g->stats[IVM_STAT_IN] = 0ull;  // known-map mode: this step's rastered-record count
+    if (b < P.B && P.orient != nullptr) ivm_pose_matrices(P, b, P.T12_buf + 12 * b, P.cs_buf + 2 * b);
 }
 
 // ------------------------------------------------------------------ persistent step kernel: helpers
@@ -871,6 +872,9 @@ struct OvlShared {
     int32_t pend[4][32];       // raster: tiles of the group that wait for the edge fix-up
     unsigned long long t_start; // %globaltimer when the CTA became resident
     int32_t qoff[NSLOT + 1];   // prefix of the chunk's queue lengths
+    int32_t glob[4], loc4[4];  // world box over the env boxes at grid barrier 2 / frame box of the step
+    int32_t direct;            // both boxes allow the direct resolution of the edge collisions
+    int32_t segcnt[2];         // direct edge-line scan: segments, longest segment
     int32_t gband[8];          // raster: bands of half-rows / half-cols that hold the global bbox edge lines (ovl_global_bands)
 };
 
@@ -893,6 +897,11 @@ __device__ __noinline__ void ovl_defer_edge(const IvmParams &P, int b, uint32_t 
     const float ec = __ldcg(&P.cs[2 * b + 0]), es = __ldcg(&P.cs[2 * b + 1]);
     ivm_mark_tile(P, b, pt.x, pt.y, pt.z, epx, h, epz, ec, es);
     if (ivm_live(old.meta, reset_stamp)) ivm_mark_tile(P, b, old.x, old.y, old.z, epx, h, epz, ec, es);
+}
+
+__device__ __noinline__ bool ovl_frame_edge_loses(const IvmParams &P, int b, int32_t r, int32_t c, uint32_t ord,
+                                                  unsigned long long xorder, const int32_t *loc) {
+    return ivm_frame_edge_loses(P, b, r, c, ord, xorder, loc);
 }
 
 // wait of a thread GROUP (named barrier 1, nthr threads, leader = thread 0) on the grid barrier
@@ -921,7 +930,7 @@ __device__ __forceinline__ bool grid_wait_group(uint32_t *bar, uint32_t target, 
 // not reach beyond the known world: the usual case), and likewise for the other three sides.  Reads that race
 // with stage 1's merges only move Rb2 inside that band.  Called by one warp right after grid barrier 2;
 // band[0..1] first-row band, [2..3] last-row band, [4..5] first-col band, [6..7] last-col band.
-__device__ __forceinline__ void ovl_global_bands(const IvmParams &P, int lane, int32_t *band) {
+__device__ __forceinline__ void ovl_global_bands(const IvmParams &P, int lane, int32_t *band, int32_t *glob, int32_t *loc4, int32_t *direct) {
     int rmin = INT32_MAX, rmax = INT32_MIN, cmin = INT32_MAX, cmax = INT32_MIN;
     for (int b = lane; b < P.B; b += 32) {
         const IvmEnv *e = &P.env[b];
@@ -933,6 +942,12 @@ __device__ __forceinline__ void ovl_global_bands(const IvmParams &P, int lane, i
         const int32_t l0 = __ldcg(&P.g->loc[0]), l1 = __ldcg(&P.g->loc[1]), l2 = __ldcg(&P.g->loc[2]), l3 = __ldcg(&P.g->loc[3]);
         band[0] = min(rmin, l0); band[1] = rmin; band[2] = rmax; band[3] = max(rmax, l1);
         band[4] = min(cmin, l2); band[5] = cmin; band[6] = cmax; band[7] = max(cmax, l3);
+        // direct resolution of the edge collisions (ivm_core.h): the frame box allowed the resolve to merge every frame
+        // winner at once (no stage-1 list is pending), so the env boxes are final and the world box is their union
+        glob[0] = rmin; glob[1] = rmax; glob[2] = cmin; glob[3] = cmax;
+        loc4[0] = l0; loc4[1] = l1; loc4[2] = l2; loc4[3] = l3;
+        const bool frame_direct = l0 > l1 || ivm_box_direct(loc4);
+        *direct = (frame_direct && rmin <= rmax && ivm_box_direct(glob)) ? 1 : 0;
     }
 }
 
@@ -1250,7 +1265,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
 
         // ============================================================ G3: resolve
         const int32_t loc[4] = {__ldcg(&g->loc[0]), __ldcg(&g->loc[1]), __ldcg(&g->loc[2]), __ldcg(&g->loc[3])};
-        unsigned nlocal = 0;
+        const bool direct1 = loc[0] <= loc[1] && ivm_box_direct(loc);  // frame-edge winners decide for themselves (ivm_core.h)
+        unsigned nlocal = 0, nedge1 = 0;
         int chunk = 0;
         for (int c0 = 0; c0 < my_tiles; c0 += nslot, ++chunk) {
             const int cn = min(nslot, my_tiles - c0);
@@ -1330,9 +1346,16 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                         label = (uint32_t)slab[k * IVM_O_TILE + px[u]];
                     }
                     if (ivm_on_frame_edge(pt, loc)) {
-                        ovl_defer_edge(P, sl.b, pix, pt.x, pt.y, pt.z, pt.r, pt.c, label, w, old[u].x, old[u].y, old[u].z,
-                                       old[u].meta, sl.reset_stamp, sl.h);
-                        continue;
+                        ++nedge1;
+                        if (!direct1) {  // tiny frame box: classes of any size, resolved by CTA 0 after grid barrier 2
+                            ovl_defer_edge(P, sl.b, pix, pt.x, pt.y, pt.z, pt.r, pt.c, label, w, old[u].x, old[u].y, old[u].z,
+                                           old[u].meta, sl.reset_stamp, sl.h);
+                            continue;
+                        }
+                        // stage 1 of the edge fix-up, resolved here: the <= 5 cells that share this cell's key are looked up
+                        // in the candidate plane; the class winner merges like any other winner, the others are dropped
+                        if (ovl_frame_edge_loses(P, sl.b, pt.r, pt.c, ivm_orderable(pt.y), (unsigned long long)sl.b * (unsigned long long)P.HW + pix, loc))
+                            continue;
                     }
                     IvmBoxAcc acc;
                     acc.clear();
@@ -1364,6 +1387,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         }
         const unsigned wl = warp_sum(nlocal);
         if (wl && lane == 0) atomicAdd(&g->acc_local, (unsigned long long)wl);
+        const unsigned we = warp_sum(nedge1);
+        if (we && lane == 0) atomicAdd(&g->acc_e1, (unsigned long long)we);
         OVL_STAMP(3, 0);
         group_bar(1, NG);
         if (tid == 0) grid_arrive(P.bar);  // barrier 2
@@ -1453,7 +1478,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     // every resolve of this step is done: the next step's kernel may become resident as CTAs of this one exit (it
     // touches nothing but its own inputs until this kernel has completed)
     if (tid == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (warp == 0) ovl_global_bands(P, lane, sh.gband);  // before anything of the fix-up can have moved an env box for good
+    if (warp == 0) ovl_global_bands(P, lane, sh.gband, sh.glob, sh.loc4, &sh.direct);  // before anything of the fix-up can have moved an env box for good
     __syncthreads();
 
     // ================================================================ edge fix-up beside the raster
@@ -1489,6 +1514,66 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             }
             __threadfence();
         };
+        bool direct = sh.direct != 0;
+        constexpr int SEGCAP = 512;
+        int32_t *seg_hdr = reinterpret_cast<int32_t *>(dyn + 12 * 1024);  // beyond the fix-up scratch (10.3 KB)
+        if (direct) {
+            // Direct flow: nothing of stage 1 is pending and the world box is known, so the team scans the edge lines at
+            // once; every live record on them looks up the cells that share its key and lists itself if it loses.
+            uint8_t *seg_tb = reinterpret_cast<uint8_t *>(dyn + 12 * 1024 + SEGCAP * IVM_SCAN_HDR * 4);  // P.B bytes (<= 4096 here)
+            if (warp == 0) {
+                if (P.B <= 4096) ivm_direct_segments(P, sh.glob, seg_hdr, SEGCAP, sh.segcnt, lane, seg_tb);
+                else if (lane == 0) sh.segcnt[0] = -1;
+            }
+            __syncthreads();
+            direct = sh.segcnt[0] >= 0;  // (else: more segments than the table holds -- the generic flow below)
+        }
+        if (direct) {
+            if (cta == 0) IVM_TRACE(g, 0, tid);
+            const bool scan = sh.segcnt[0] > 0;  // (the same in every team CTA; usually nothing has to be scanned)
+            if (scan) {
+                const int nlive = ivm_direct_scan<IvmAtomics>(P, seg_hdr, sh.segcnt[0], sh.segcnt[1], sh.glob, sh.loc4, cta, team, tid, (int)blockDim.x);
+                const unsigned wn2 = warp_sum((unsigned)nlive);
+                if (wn2 && lane == 0) atomicAdd(&g->acc_e2, (unsigned long long)wn2);
+                __syncthreads();
+            }
+            if (cta == 0) IVM_TRACE(g, 1, tid);
+            // every decision of the team is made (round 1 of the team's arrival counter); then the listed losers are
+            // deleted by the whole team (round 2) -- decisions must all read the store as it was.  The counter always
+            // receives two arrivals per team CTA and step (the host advances its base by that much).
+            if (team > 1) {
+                if (tid == 0) {
+                    __threadfence();
+                    asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(&P.bar[IVM_O_FIX_ARRIVE]), "r"(1u) : "memory");
+                    if (scan) spin_until(&P.bar[IVM_O_FIX_ARRIVE], team_base + (uint32_t)team, false);
+                }
+                __syncthreads();
+            }
+            const uint32_t nlose = scan ? min(__ldcg(&g->n_e2), P.ecap) : 0u;
+            if (nlose) ivm_delete_losers<IvmAtomics>(P, nlose, (uint32_t)(cta * (int)blockDim.x + tid), (uint32_t)(team * (int)blockDim.x));
+            __syncthreads();
+            if (team > 1 && tid == 0) {
+                __threadfence();
+                asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(&P.bar[IVM_O_FIX_ARRIVE]), "r"(1u) : "memory");
+            }
+            if (cta == 0) {
+                IVM_TRACE(g, 2, tid); IVM_TRACE(g, 3, tid);
+                if (team > 1 && nlose) {
+                    if (tid == 0) spin_until(&P.bar[IVM_O_FIX_ARRIVE], team_base + 2u * (uint32_t)team, false);
+                    __syncthreads();
+                }
+                if (tid == 0) {
+                    g->glob[0] = sh.glob[0]; g->glob[1] = sh.glob[1]; g->glob[2] = sh.glob[2]; g->glob[3] = sh.glob[3];
+                    g->n_seg = (uint32_t)sh.segcnt[0];
+                    g->scan_chunks = (uint32_t)((sh.segcnt[1] + IVM_SCAN_CHUNK - 1) / IVM_SCAN_CHUNK);
+                }
+                __syncthreads();
+                ivm_fixup_stage2<IvmAtomics>(P, S, tid, blockDim.x, false, (uint32_t)__ldcg(&g->acc_e1), (uint32_t)__ldcg(&g->acc_e2), true);
+                __syncthreads();
+                if (tid == 0) { g->tstamp[3] = global_timer(); g->tstamp[4] = g->tstamp[3]; }
+                __syncthreads();
+            }
+        } else {
         if (cta == 0) {
             ivm_fixup_stage1<IvmAtomics>(P, S, tid, blockDim.x);
             __syncthreads();
@@ -1505,18 +1590,19 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         ivm_fixup_scan_block<IvmAtomics>(P, S, cta, team, tid, blockDim.x);
         __syncthreads();
         if (team > 1 && tid == 0) {
-            __threadfence();
-            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(&P.bar[IVM_O_FIX_ARRIVE]), "r"(1u) : "memory");
+            __threadfence();  // (two arrivals per team CTA and step, as in the direct flow: the host advances the base by 2 x team)
+            asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(&P.bar[IVM_O_FIX_ARRIVE]), "r"(2u) : "memory");
         }
         if (cta == 0) {
             if (team > 1) {
-                if (tid == 0) spin_until(&P.bar[IVM_O_FIX_ARRIVE], team_base + (uint32_t)team, false);
+                if (tid == 0) spin_until(&P.bar[IVM_O_FIX_ARRIVE], team_base + 2u * (uint32_t)team, false);
                 __syncthreads();
             }
             ivm_fixup_stage2<IvmAtomics>(P, S, tid, blockDim.x);
             __syncthreads();
             if (tid == 0) { g->tstamp[3] = global_timer(); g->tstamp[4] = g->tstamp[3]; }
             __syncthreads();
+        }
         }
     }
     if (warp < RG * IVM_F_GROUP / 32) {
@@ -2151,7 +2237,7 @@ static int launch_overlap(ivm_ctx *ctx, IvmParams &P, const float *logits, int n
     if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaLaunchKernelExC(k_step_overlap)");
     ctx->bar_base += 5u * (uint32_t)grid;
     ctx->done_base += (uint32_t)grid;
-    if (team > 1) ctx->team_base += (uint32_t)team;
+    if (team > 1) ctx->team_base += 2u * (uint32_t)team;
     ctx->launches += 1;
     return IVM_OK;
 }
@@ -2288,13 +2374,12 @@ int ivm_step_known(ivm_ctx *ctx, int32_t num_envs, const float *pose, const floa
     IvmParams P = ctx->P;
     P.B = num_envs; P.pose = pose; P.cs = cs; P.occ = occ; P.sem = sem;
     const int slot = timing_slot(ctx);
-    if (orientation) {
-        P.orient = orientation; P.orient_f64 = orientation_is_f64; P.cs = P.cs_buf;
-        T_BEGIN(0);
-        k_pose<<<(num_envs + 127) / 128, 128, 0, st>>>(P);
-        T_END(0);
-        ctx->launches += 1;
-    }
+    P.orient = nullptr;
+    if (orientation) { P.orient = orientation; P.orient_f64 = orientation_is_f64; P.cs = P.cs_buf; }
+    T_BEGIN(0);
+    k_pose<<<(num_envs + 127) / 128, 128, 0, st>>>(P);
+    T_END(0);
+    ctx->launches += 1;
     T_BEGIN(4);
     launch_raster(ctx, P, st, true);
     T_END(4);

@@ -311,8 +311,9 @@ class _MapEngine:
                 self._tables = (xs, ys)
             self.ctx, self.workspace, self.max_envs = ctx, workspace, max_envs
             R, C = self.md.num_rows, self.md.num_cols
-            self.occ = torch.zeros((max_envs, R, C), dtype=torch.uint8, device=self.device)
-            self.sem = torch.zeros((max_envs, R, C), dtype=torch.uint8, device=self.device)
+            # both output maps in one block, so that a full batch leaves for the host in a single copy (staging.MapEgress)
+            self.maps = torch.zeros((2, max_envs, R, C), dtype=torch.uint8, device=self.device)
+            self.occ, self.sem = self.maps[0], self.maps[1]
             if self.mode == "iterative":
                 H, W = self.camera.features_spatial_dimensions
                 self.labels_out = torch.zeros((max_envs, int(H), int(W)), dtype=torch.uint8, device=self.device)
@@ -567,7 +568,16 @@ class MappingModule(nn.Module):
             _lib.check(lib.ivm_known_clear(eng.ctx, b, st), eng.ctx, "ivm_known_clear")
             self._known_order.remove(b)
             self._known_loaded.pop(b, None)
-        finished = episodes_info.finished_indices().tolist()     # host sync, as the reference does (mapper.py:873-878)
+        # Which envs reload their scene cloud (mask == 0, mapper.py:873-878)?  A reload of the scene an env already
+        # holds changes nothing, so the masks matter only where the scene differs from the loaded one (or nothing is
+        # loaded yet): only then are they read -- a device sync if they live on the device; never in steady state.
+        names = [str(n) for n in episodes_info.env_names[:B]]
+        if all(self._known_loaded.get(b) == names[b] for b in range(B)):
+            finished = []
+        else:
+            m = episodes_info.not_done_masks
+            finished = [b for b in (m == episodes_info.EPISODE_FINISHED).nonzero().flatten().tolist()
+                        if self._known_loaded.get(b) != names[b]]
         for b in finished:
             name = str(episodes_info.env_names[b])
             xyz, sem, o_r, o_c = self._known_cloud(name)

@@ -118,3 +118,35 @@ def load_reference_mapper() -> types.ModuleType:
     exec(compile(src, mod.__file__, "exec"), mod.__dict__)
     mod._ivln_shimmed = True
     return mod
+
+
+def load_reference_function(rel_path: str, name: str, class_name: str = None):
+    """A single function of the reference, compiled from ITS OWN source text (found with `ast`), for modules whose
+    imports (gym, habitat, lmdb ...) do not exist here: `rel_path` relative to the reference root, `name` a
+    top-level function or -- with `class_name` -- a method (returned as a plain function taking `self`)."""
+    import ast
+    import collections
+    import typing
+
+    import numpy as np
+
+    path = os.path.join(REFERENCE_ROOT, rel_path)
+    with open(path, "r") as f:
+        src = f.read()
+    tree = ast.parse(src)
+    body = tree.body
+    if class_name is not None:
+        body = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == class_name).body
+    wanted = [n for n in body if isinstance(n, ast.FunctionDef) and n.name == name]
+    helpers = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name != name] if class_name is None else []
+    assert wanted, f"{name} not found in {path}"
+    ns = {"np": np, "torch": torch, "defaultdict": collections.defaultdict, "DictTree": dict}
+    ns.update({k: getattr(typing, k) for k in ("Any", "DefaultDict", "Dict", "List", "Optional", "Set", "Tuple")})
+    for node in helpers + wanted:
+        try:
+            code = compile(ast.Module(body=[node], type_ignores=[]), path, "exec")
+            exec(code, ns)
+        except Exception:
+            if node in wanted:
+                raise
+    return ns[name]

@@ -9,7 +9,7 @@ N = 330
 pose, orient, masks = bench.make_poses(cfg, N + 10, 1002)
 depth, sem = bench.make_frames(cfg, dev, 1002)
 pose_d, orient_d, masks_d = (torch.from_numpy(x).to(dev) for x in (pose, orient, masks))
-mm = bench.build_module(cfg, dev, B, 0)
+mm = bench.build_module(cfg, dev, B, 0, os.environ.get("IVM_PIPELINED", "1") != "0")
 names = [f"s{b}" for b in range(B)]
 def step(t): bench.call_module(mm, cfg, names, masks_d[t], pose_d[t], orient_d[t], depth[t % 4], sem[t % 4])
 for rep in range(2):

@@ -25,6 +25,7 @@ struct Emu {
     int hi_water;
     int order;  // 0 forward, 1 reverse, 2 strided
     int fix_cap;  // capacity of the fix-up's small-class fast path (0 forces the hash path)
+    int direct;   // 1 = direct (partner look-up) resolution of the edge collisions where the boxes allow it
     std::vector<IvmRecord> store;
     std::vector<unsigned long long> cand;
     std::vector<IvmEnv> env;
@@ -45,7 +46,7 @@ Emu *emu_create(int H, int W, const float *xs, const float *ys, float res, float
     Emu *m = new Emu();
     memset(&m->P, 0, sizeof(m->P));
     memset(&m->g, 0, sizeof(m->g));
-    m->mode = mode; m->step = 0; m->cstep = 0; m->stamp_period = 0; m->last_cstamp = 0; m->hi_water = 0; m->order = 0; m->fix_cap = 512;
+    m->mode = mode; m->step = 0; m->cstep = 0; m->stamp_period = 0; m->last_cstamp = 0; m->hi_water = 0; m->order = 0; m->fix_cap = 512; m->direct = 0;
     ivm_reset_step_globals(&m->g);
     IvmParams &P = m->P;
     P.H = H; P.W = W; P.HW = H * W; P.R = R; P.C = C;
@@ -92,6 +93,7 @@ void emu_set_order(Emu *m, int order) { m->order = order; }
 void emu_set_step(Emu *m, unsigned step) { m->step = step; m->cstep = step; }  // before the first step only (tests the stamp wrap)
 void emu_set_stamp_period(Emu *m, unsigned period) { m->stamp_period = period; }
 void emu_set_fix_cap(Emu *m, int cap) { m->fix_cap = cap < 1 ? 1 : cap; }
+void emu_set_direct(Emu *m, int on) { m->direct = on; }
 
 static inline int visit(const Emu *m, int i, int n) {
     if (m->order == 1) return n - 1 - i;
@@ -215,6 +217,8 @@ int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels,
         IvmAtomics::min_i(&m->g.loc[2], p.c); IvmAtomics::max_i(&m->g.loc[3], p.c);
         m->g.acc_valid++;
     }
+    // the frame box is final: may stage 1 take the direct path?
+    const bool direct1 = m->direct && m->g.loc[0] <= m->g.loc[1] && ivm_box_direct(m->g.loc);
     // K2: resolve (one accumulator per simulated CTA of 1024 pixels, flushed like the kernel does)
     for (int i = 0; i < n; ++i) {
         const int gp = visit(m, n - 1 - i, n);
@@ -224,8 +228,12 @@ int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels,
         if (ivm_unproject(depth[gp], P.xs[u], P.ys[v], T12 + 12 * b, pose[3 * b + 1], P.half_res, p) != 1) continue;
         IvmBoxAcc acc;
         acc.clear();
-        m->g.acc_local += (unsigned)ivm_resolve_pixel<IvmAtomics>(P, b, (uint32_t)pix, p, labels[gp], m->g.loc,
-                                                                  P.env[b].origin_r, P.env[b].origin_c, acc);
+        if (direct1)
+            m->g.acc_local += (unsigned)ivm_resolve_pixel_direct<IvmAtomics>(P, b, (uint32_t)pix, p, labels[gp], m->g.loc,
+                                                                             P.env[b].origin_r, P.env[b].origin_c, acc);
+        else
+            m->g.acc_local += (unsigned)ivm_resolve_pixel<IvmAtomics>(P, b, (uint32_t)pix, p, labels[gp], m->g.loc,
+                                                                      P.env[b].origin_r, P.env[b].origin_c, acc);
         ivm_box_flush<IvmAtomics>(&P.env[b], acc);
     }
     // K3: fix-up
@@ -237,7 +245,28 @@ int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels,
         IvmFixScratch S;
         S.key = key.data(); S.xo = xo.data(); S.ord = ord.data(); S.cap = (uint32_t)m->fix_cap; S.ibuf = ibuf; S.lbuf = lbuf;
         S.release = nullptr; S.release_add = 0u;
-        ivm_fixup_program<IvmAtomics>(P, S, 0, 1);
+        // world box over the env boxes as they stand after the resolve (the direct stage 1 has merged everything)
+        int32_t glob[4] = {INT32_MAX, INT32_MIN, INT32_MAX, INT32_MIN};
+        for (int b = 0; b < B; ++b) {
+            const IvmEnv &e = P.env[b];
+            if (e.count > 0) {
+                glob[0] = std::min(glob[0], e.rmin); glob[1] = std::max(glob[1], e.rmax);
+                glob[2] = std::min(glob[2], e.cmin); glob[3] = std::max(glob[3], e.cmax);
+            }
+        }
+        const bool novalid = m->g.loc[0] > m->g.loc[1];
+        if (m->direct && (direct1 || novalid) && glob[0] <= glob[1] && ivm_box_direct(glob)) {
+            std::vector<int32_t> hdr((size_t)IVM_SCAN_HDR * 4 * B);
+            int32_t counts[2];
+            std::vector<uint8_t> tb((size_t)B + 1);
+            ivm_direct_segments(P, glob, hdr.data(), 4 * B, counts, 0, tb.data());
+            const int nlive = ivm_direct_scan<IvmAtomics>(P, hdr.data(), counts[0], counts[1], glob, m->g.loc, 0, 1, 0, 1);
+            m->g.glob[0] = glob[0]; m->g.glob[1] = glob[1]; m->g.glob[2] = glob[2]; m->g.glob[3] = glob[3];
+            m->g.n_seg = (uint32_t)counts[0]; m->g.scan_chunks = (uint32_t)((counts[1] + IVM_SCAN_CHUNK - 1) / IVM_SCAN_CHUNK);
+            ivm_fixup_stage2<IvmAtomics>(P, S, 0, 1, false, (uint32_t)m->g.acc_e1, (uint32_t)nlive);
+        } else {
+            ivm_fixup_program<IvmAtomics>(P, S, 0, 1);
+        }
     }
     // K4: raster
     emu_raster(m, P, false);

@@ -37,6 +37,7 @@ def lib():
         L.emu_destroy.argtypes = [ctypes.c_void_p]
         L.emu_set_order.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.emu_set_fix_cap.argtypes = [ctypes.c_void_p, ctypes.c_int]
+        L.emu_set_direct.argtypes = [ctypes.c_void_p, ctypes.c_int]
         L.emu_step_iterative.argtypes = [ctypes.c_void_p, ctypes.c_int, f32p, u8p, f32p, f32p, f32p, ctypes.c_void_p, ctypes.c_int, u8p, u8p, u8p]
         L.emu_known_load.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, f32p, u8p, ctypes.c_int, ctypes.c_int]
         L.emu_known_clear.argtypes = [ctypes.c_void_p, ctypes.c_int]
@@ -57,7 +58,7 @@ def _p(a, ct):
 
 class EmuMapper:
     def __init__(self, height, width, vfov, map_m, resolution, max_envs, mode="iterative", store=1024,
-                 tile=32, known_clouds=None, known_capacity=1 << 16, order=0, kernel_trig=False, fix_cap=None):
+                 tile=32, known_clouds=None, known_capacity=1 << 16, order=0, kernel_trig=False, fix_cap=None, direct=False):
         self.kernel_trig = kernel_trig
         self.H, self.W = height, width
         self.R = math.ceil(map_m / resolution)
@@ -77,6 +78,7 @@ class EmuMapper:
         lib().emu_set_order(self._h, order)
         if fix_cap is not None:
             lib().emu_set_fix_cap(self._h, fix_cap)
+        lib().emu_set_direct(self._h, 1 if direct else 0)
         self._B = 0
 
     def __del__(self):

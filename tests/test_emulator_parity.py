@@ -130,3 +130,43 @@ def test_emulator_matches_oracle_fuzz(seed):
         _, stats = emu.status()
         assert int(stats[0]) == orc.counters["n_valid"] and int(stats[1]) == orc.counters["n_local"]
         assert int(stats[2]) == orc.counters["n_world"] and int(stats[3]) == orc.counters["n_in"]
+
+
+@pytest.mark.parametrize("order", [0, 1])
+@pytest.mark.parametrize("name", [n for n in golden_names() if n != "known_map"])
+def test_emulator_direct_edge_resolution_matches_golden(name, order):
+    """Direct resolution of the edge collisions (every edge cell looks up the <= 5 cells that share its key instead
+    of grouping entries by key; ivm_partners / ivm_frame_edge_loses / ivm_world_edge_loses) against the goldens."""
+    scn = load_golden(name)
+    emu = _emu(scn, order=order, direct=True)
+    outs, sizes = run_mapper(emu.step, scn, world_fn=emu.world)
+    for t, (o, s) in enumerate(outs):
+        B = o.shape[0]
+        assert np.array_equal(o, scn["ref_occupancy"][t, :B]) and np.array_equal(s, scn["ref_semantic"][t, :B]), t
+    assert emu.status()[0] == 0
+    assert sizes == scn["ref_world_sizes"].tolist()
+    b, xyz, sem = emu.world()
+    assert np.array_equal(b, scn["ref_world_b"]) and np.array_equal(xyz.view(np.uint32), scn["ref_world_xyz"].view(np.uint32))
+    assert np.array_equal(sem, scn["ref_world_sem"])
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_emulator_direct_edge_resolution_fuzz(seed):
+    cfg, scn, order, tile = _fuzz_case(20_000 + seed)
+    orc = OracleMapper(cfg.height, cfg.width, cfg.vfov_radians, cfg.map_meters, cfg.map_meters, cfg.resolution)
+    emu = EmuMapper(cfg.height, cfg.width, cfg.vfov_radians, cfg.map_meters, cfg.resolution, max_envs=cfg.num_envs,
+                    store=2048 if cfg.resolution < 0.1 else 1024, order=order, tile=tile, direct=True)
+    merged = 0
+    for t in range(cfg.steps):
+        a = (scn["masks"][t], scn["pose"][t], scn["orientation"][t])
+        kw = dict(depth=scn["depth"][t], labels=scn["labels"][t])
+        o1, s1 = orc.step(*a, **kw)
+        o2, s2 = emu.step(*a, **kw)
+        assert emu.status()[0] == 0
+        assert np.array_equal(o1, o2) and np.array_equal(s1, s2), f"maps differ at step {t}"
+        b1, x1, m1 = orc.world()
+        b2, x2, m2 = emu.world()
+        assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(m1, m2)
+        _, stats = emu.status()
+        assert int(stats[0]) == orc.counters["n_valid"] and int(stats[1]) == orc.counters["n_local"]
+        assert int(stats[2]) == orc.counters["n_world"] and int(stats[3]) == orc.counters["n_in"]
