@@ -150,6 +150,17 @@ int ivm_read_cta_trace(ivm_ctx *ctx, uint64_t *ns_out, int32_t num_ctas, ivm_str
 int ivm_map_features(const uint8_t *occ, const uint8_t *sem, int32_t num_envs, int32_t rows, int32_t cols,
                      int32_t num_classes, float *out, uint32_t *err_flag_dev, ivm_stream_t stream);
 
+/* Segmentation front end: PredictSemantics.forward up to the network
+ * (ivlnce_baselines/common/mapping_module/mapper.py:715-736, 788-793) as one kernel.  rgb: u8 device pointer to a
+ * [B,3,rgb_h,rgb_w] tensor with ELEMENT strides rgb_strides4 (host array: batch, channel, row, column -- the sensor's
+ * NHWC layout is strides {h*w*3, 1, w*3, 3}), or NULL; depth: f32 [B,1,height,width] or NULL.
+ * rgb_out f32 [B,3,height,width] = ((bilinear resize of rgb / 255) - mean) / std, depth_out f32 [B,1,height,width] =
+ * (depth - 0.213) / 0.285 (contiguous NCHW, what RedNet consumes).  Stateless.  Floating point: within 1e-5 of the
+ * reference's torch ops (F.interpolate mode="bilinear", align_corners=False). */
+int ivm_rednet_preprocess(const uint8_t *rgb, const int64_t *rgb_strides4, int32_t num_envs, int32_t rgb_h, int32_t rgb_w,
+                          const float *depth, int32_t height, int32_t width, float *rgb_out, float *depth_out,
+                          ivm_stream_t stream);
+
 /* Number of kernels launched by this context so far. */
 int64_t ivm_kernel_launches(const ivm_ctx *ctx);
 

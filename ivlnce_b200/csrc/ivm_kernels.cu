@@ -1874,6 +1874,46 @@ __global__ void __launch_bounds__(256) k_map_features_scalar(const uint8_t *__re
     if (err != nullptr && l >= num_classes) atomicOr(err, 1u);
 }
 
+// ------------------------------------------------------------------ segmentation front end
+// PredictSemantics.forward up to the network (mapper.py:715-736, 788-793): rgb u8 -> /255 -> bilinear resize to the depth
+// size (F.interpolate, align_corners=False) -> (x - mean) / std per channel, and depth -> (d - 0.213) / 0.285, as ONE
+// kernel: one thread per output pixel and all three channels (the 4 source texels of a pixel are 3-byte neighbours in
+// the NHWC sensor layout, read through arbitrary element strides so that an NCHW tensor works too).  Same operation
+// order as torch's upsample_bilinear2d: h0*(w0*v00 + w1*v01) + h1*(w0*v10 + w1*v11).
+struct IvmPreArgs {
+    const uint8_t *rgb; long long sb, sc, sy, sx;   // element strides of [B,3,h,w]
+    int B, h, w, H, W;
+    const float *depth; float *rgb_out, *depth_out;
+    float mean[3], std[3], dmean, dstd;
+    float scale_y, scale_x;
+};
+__global__ void __launch_bounds__(256) k_rednet_preprocess(const IvmPreArgs a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long hw = (long long)a.H * a.W;
+    if (i >= hw * a.B) return;
+    const int b = (int)(i / hw);
+    const int p = (int)(i - (long long)b * hw);
+    const int y = p / a.W, x = p - y * a.W;
+    if (a.rgb) {
+        // area_pixel_compute_source_index(scale, dst, align_corners=false): scale * (dst + 0.5) - 0.5, clamped at 0
+        float fy = a.scale_y * ((float)y + 0.5f) - 0.5f; fy = fy < 0.f ? 0.f : fy;
+        float fx = a.scale_x * ((float)x + 0.5f) - 0.5f; fx = fx < 0.f ? 0.f : fx;
+        const int y0 = min((int)fy, a.h - 1), x0 = min((int)fx, a.w - 1);
+        const int y1 = y0 + (y0 < a.h - 1 ? 1 : 0), x1 = x0 + (x0 < a.w - 1 ? 1 : 0);
+        const float ly = fy - (float)y0, lx = fx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+        const uint8_t *base = a.rgb + (long long)b * a.sb;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const uint8_t *pc = base + (long long)c * a.sc;
+            const float v00 = (float)pc[y0 * a.sy + x0 * a.sx] / 255.0f, v01 = (float)pc[y0 * a.sy + x1 * a.sx] / 255.0f;
+            const float v10 = (float)pc[y1 * a.sy + x0 * a.sx] / 255.0f, v11 = (float)pc[y1 * a.sy + x1 * a.sx] / 255.0f;
+            const float v = hy * (hx * v00 + lx * v01) + ly * (hx * v10 + lx * v11);
+            a.rgb_out[((long long)b * 3 + c) * hw + p] = (v - a.mean[c]) / a.std[c];
+        }
+    }
+    if (a.depth) a.depth_out[i] = (a.depth[i] - a.dmean) / a.dstd;
+}
+
 // ------------------------------------------------------------------ host side
 struct ivm_ctx {
     ivm_config cfg;
@@ -2459,6 +2499,28 @@ int ivm_map_features(const uint8_t *occ, const uint8_t *sem, int32_t num_envs, i
     } else {
         k_map_features_scalar<<<(unsigned)((ncell + 255) / 256), 256, 0, st>>>(occ, sem, ncell, (int)plane, num_classes, out, err_flag_dev);
     }
+    return cudaGetLastError() == cudaSuccess ? IVM_OK : IVM_E_CUDA;
+}
+
+int ivm_rednet_preprocess(const uint8_t *rgb, const int64_t *rgb_strides4, int32_t num_envs, int32_t rgb_h, int32_t rgb_w,
+                          const float *depth, int32_t height, int32_t width, float *rgb_out, float *depth_out,
+                          ivm_stream_t stream) {
+    if (num_envs < 1 || height < 1 || width < 1) return IVM_E_INVALID;
+    if (rgb && (!rgb_strides4 || !rgb_out || rgb_h < 1 || rgb_w < 1)) return IVM_E_INVALID;
+    if (depth && !depth_out) return IVM_E_INVALID;
+    if (!rgb && !depth) return IVM_OK;
+    IvmPreArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rgb = rgb; a.depth = depth; a.rgb_out = rgb_out; a.depth_out = depth_out;
+    if (rgb) { a.sb = rgb_strides4[0]; a.sc = rgb_strides4[1]; a.sy = rgb_strides4[2]; a.sx = rgb_strides4[3]; }
+    a.B = num_envs; a.h = rgb_h; a.w = rgb_w; a.H = height; a.W = width;
+    a.mean[0] = 0.485f; a.mean[1] = 0.456f; a.mean[2] = 0.406f;   // mapper.py:725-727
+    a.std[0] = 0.229f; a.std[1] = 0.224f; a.std[2] = 0.225f;
+    a.dmean = 0.213f; a.dstd = 0.285f;                           // mapper.py:731-733
+    a.scale_y = rgb ? (float)rgb_h / (float)height : 1.f;         // torch: area_pixel_compute_scale (no scale factor given)
+    a.scale_x = rgb ? (float)rgb_w / (float)width : 1.f;
+    const long long n = (long long)num_envs * height * width;
+    k_rednet_preprocess<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
     return cudaGetLastError() == cudaSuccess ? IVM_OK : IVM_E_CUDA;
 }
 

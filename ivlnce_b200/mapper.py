@@ -199,19 +199,65 @@ class GTSemantics(ComputeSemantics):
 
 
 class PredictSemantics(ComputeSemantics):
-    """reference mapper.py:703-800.  The segmentation network itself (RedNet, cuDNN) is outside
-    this repository's scope; `model` is any callable (rgb_normalized [B,3,H,W], depth_normalized
-    [B,1,H,W]) -> class scores f32 [B,Cls,H,W].  The reference's tail
-    `scores.argmax(1, keepdims=True).to(uint8)` (mapper.py:795-798) is NOT done here: the scores
-    go straight into the fused ingest kernel, which does the argmax while streaming the planes."""
+    """reference mapper.py:703-800.  The segmentation network itself (RedNet, dense convolutions on cuDNN, trained
+    weights) is outside this repository's scope; everything round it is here:
 
-    def __init__(self, model: Optional[Callable] = None):
+      * the front end -- rgb / 255 -> bilinear resize to the depth size -> per-channel normalisation, and the depth
+        normalisation (mapper.py:715-736, 788-793) -- is ONE kernel (`ivm_rednet_preprocess`, SURVEY.md 8f-4);
+      * the tail `scores.argmax(1, keepdims=True).to(uint8)` (mapper.py:795-798) is NOT done here: the scores go
+        straight into the step kernel, which does the argmax while streaming the planes.
+
+    `model`: callable (rgb_normalized f32 [B,3,H,W], depth_normalized f32 [B,1,H,W]) -> class scores f32 [B,Cls,H,W].
+    Like the reference, the model is built lazily on the first forward (`setup_finetuned_rednet`, mapper.py:738-752):
+    from `model_factory(device)` if given, else from the factory named by the environment variable
+    IVLN_SEMANTICS_MODEL_FACTORY ("package.module:callable"), else from the reference's own RedNet class and weight
+    file (`data/rednet_mp3d_best_model.pkl`) when `ivlnce_baselines` is importable.  If none of these exists the
+    first forward raises, naming the three options."""
+
+    REDNET_WEIGHTS = "data/rednet_mp3d_best_model.pkl"
+
+    def __init__(self, model: Optional[Callable] = None, model_factory: Optional[Callable] = None):
         super().__init__()
         self.model = model
+        self.model_factory = model_factory
         self._rgb_mean = self._rgb_std = None
 
-    def preprocess(self, observations: Observations):
-        """mapper.py:715-736, 788-793 (torch ops; next-scope row f-4 of SURVEY.md section 8)."""
+    # -- the reference's lazy model construction
+    def setup_finetuned_rednet(self, device: torch.device):
+        if self.model is not None:
+            return
+        factory = self.model_factory
+        spec = os.environ.get("IVLN_SEMANTICS_MODEL_FACTORY", "")
+        if factory is None and spec:
+            import importlib
+
+            mod, _, fn = spec.partition(":")
+            factory = getattr(importlib.import_module(mod), fn)
+        if factory is not None:
+            self.model = factory(device)
+        else:
+            try:
+                from ivlnce_baselines.common.mapping_module.rednet import RedNet  # the reference's own network
+            except Exception as exc:
+                raise Exception(
+                    "PredictSemantics needs a segmentation model: pass model= / model_factory= (callable returning class "
+                    "scores [B,Cls,H,W]), or set IVLN_SEMANTICS_MODEL_FACTORY=package.module:callable, or make the "
+                    "reference's ivlnce_baselines package (RedNet + data/rednet_mp3d_best_model.pkl) importable") from exc
+            cfg_rednet = {"arch": "rednet", "resnet_pretrained": False, "finetune": True, "SUNRGBD_pretrained_weights": "",
+                          "n_classes": 13, "upsample_prediction": True, "load_model": self.REDNET_WEIGHTS}
+            model = RedNet(cfg_rednet).to(device)
+            state = torch.load(cfg_rednet["load_model"])["model_state"]
+            if next(iter(state)).split(".")[0] == "module":          # convert_weights_cuda_cpu(..., "cpu")
+                state = {".".join(k.split(".")[1:]): v for k, v in state.items()}
+            model.load_state_dict(state)
+            self.model = model
+        if isinstance(self.model, nn.Module):
+            self.model.eval()
+            for p in self.model.parameters():
+                p.requires_grad = False
+
+    def preprocess_torch(self, observations: Observations):
+        """mapper.py:715-736, 788-793 as the reference's torch ops (the comparison path of the tests)."""
         depth = observations.depth_normalized
         if self._rgb_mean is None:
             dev = observations.rgb.device
@@ -222,11 +268,31 @@ class PredictSemantics(ComputeSemantics):
         d = (depth - 0.213) / 0.285
         return rgb, d
 
+    def preprocess(self, observations: Observations):
+        """The same through the fused kernel: rgb u8 [B,3,h,w] (any strides: the sensor's NHWC memory seen as NCHW is
+        read in place) + depth f32 [B,1,H,W] -> normalised f32 NCHW tensors."""
+        rgb, depth = observations.rgb, observations.depth_normalized
+        if rgb.device.type != "cuda":
+            raise _lib.MapLibraryError("the segmentation front end runs on CUDA devices only; there is no CPU fallback")
+        if rgb.dtype != torch.uint8:
+            rgb = rgb.to(torch.uint8)
+        depth = _as_f32(depth, rgb.device)
+        B, _, H, W = depth.shape
+        assert rgb.shape[0] == B and rgb.shape[1] == 3
+        rgb_out = torch.empty((B, 3, H, W), dtype=torch.float32, device=rgb.device)
+        depth_out = torch.empty((B, 1, H, W), dtype=torch.float32, device=rgb.device)
+        strides = (ctypes.c_int64 * 4)(*rgb.stride())
+        lib = _lib.load()
+        with torch.cuda.device(rgb.device):
+            _lib.check(lib.ivm_rednet_preprocess(rgb.data_ptr(), strides, B, int(rgb.shape[2]), int(rgb.shape[3]), depth.data_ptr(),
+                                                 H, W, rgb_out.data_ptr(), depth_out.data_ptr(),
+                                                 torch.cuda.current_stream(rgb.device).cuda_stream), None, "ivm_rednet_preprocess")
+        return rgb_out, depth_out
+
     def scores(self, observations: Observations) -> torch.Tensor:
         if observations.rgb is None:
             raise Exception("RGB Sensor not in use")
-        if self.model is None:
-            raise Exception("PredictSemantics needs a segmentation model (callable returning class scores)")
+        self.setup_finetuned_rednet(observations.depth_normalized.device)
         with torch.no_grad():
             rgb, d = self.preprocess(observations)
             return self.model(rgb, d)

@@ -109,11 +109,16 @@ class Mapper(ObservationTransformer):
     @classmethod
     def from_config(cls, config, visualize=False):
         mapper_cfg = config.RL.POLICY.OBS_TRANSFORMS.EGOCENTRIC_MAPPER
+        # optional keys beside the reference's (yacs nodes are created with new_allowed=True): B200_MAPPER = dict of
+        # keyword arguments for the mapping module (store_cells, maps_location, max_envs, ...)
+        extra = getattr(mapper_cfg, "B200_MAPPER", None)
+        kwargs = dict(extra) if extra is not None else {}
         return cls(
             camera_parameters=extract_camera_parameters(
                 depth_sensor_params=config.TASK_CONFIG.SIMULATOR.DEPTH_SENSOR, map_sensor_params=mapper_cfg),
             map_dimensions=extract_egocentric_map_parameters(map_sensor_params=mapper_cfg),
             visualize=(len(getattr(config, "VIDEO_OPTION", [])) > 0) or visualize,
+            **kwargs,
         )
 
 
