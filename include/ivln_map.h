@@ -118,6 +118,16 @@ int ivm_export_world(ivm_ctx *ctx, int32_t num_envs, int64_t cap, int64_t *env_o
 /* Copies error flags and statistics of the last step to host memory; synchronises `stream`. */
 int ivm_read_status(ivm_ctx *ctx, ivm_status *host_out, ivm_stream_t stream);
 
+/* Error flags without a synchronisation: enqueues a 4-byte copy of the flags word into PINNED host memory on
+ * `stream` (the caller looks at it once an event recorded behind the copy has completed); ivm_clear_error_flags
+ * zeroes the word on `stream`.  The flags are sticky until cleared.  What the flags mean for the results:
+ *   1  a point (or a known-map cloud point, 4) fell outside the env's store window: that point is DROPPED -- the
+ *      reference's unbounded cloud would have kept it; enlarge store_rows / store_cols;
+ *   2  the edge lists overflowed: collisions on the bounding-box edge may be unresolved (results invalid);
+ *   8  a grid barrier timed out: the step's results are invalid and the context must be re-created. */
+int ivm_copy_error_flags_async(ivm_ctx *ctx, uint32_t *host_pinned_out, ivm_stream_t stream);
+int ivm_clear_error_flags(ivm_ctx *ctx, ivm_stream_t stream);
+
 /* Per-kernel device timing: when enabled, CUDA events bracket each kernel of the next
  * steps; ivm_stage_times returns the accumulated milliseconds per stage since the last
  * reset (synchronises the events).  Stages: 0 prep, 1 ingest-scatter, 2 ingest-resolve,

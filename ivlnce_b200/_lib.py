@@ -84,12 +84,15 @@ def load() -> ctypes.CDLL:
     L.ivm_map_features.argtypes = [_vp, _vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]
     L.ivm_rednet_preprocess.argtypes = [_vp, ctypes.POINTER(ctypes.c_int64), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _vp,
                                         ctypes.c_int32, ctypes.c_int32, _vp, _vp, _vp]
+    L.ivm_copy_error_flags_async.argtypes = [_vp, _vp, _vp]
+    L.ivm_clear_error_flags.argtypes = [_vp, _vp]
     L.ivm_last_cuda_error.restype = ctypes.c_char_p
     L.ivm_last_cuda_error.argtypes = [_vp]
     L.ivm_version.restype = ctypes.c_char_p
     for name in ("ivm_create", "ivm_destroy", "ivm_set_camera", "ivm_step_iterative", "ivm_known_load", "ivm_known_clear",
                  "ivm_step_known", "ivm_export_world", "ivm_read_status", "ivm_set_timing", "ivm_stage_times",
-                 "ivm_rebase_stamps", "ivm_debug_set_step", "ivm_set_pipelined", "ivm_copy_state", "ivm_read_phase_ns", "ivm_read_cta_trace", "ivm_map_features", "ivm_rednet_preprocess"):
+                 "ivm_rebase_stamps", "ivm_debug_set_step", "ivm_set_pipelined", "ivm_copy_state", "ivm_read_phase_ns", "ivm_read_cta_trace", "ivm_map_features", "ivm_rednet_preprocess", "ivm_copy_error_flags_async",
+                 "ivm_clear_error_flags"):
         getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L

@@ -2462,6 +2462,20 @@ int ivm_read_status(ivm_ctx *ctx, ivm_status *host_out, ivm_stream_t stream) {
     return IVM_OK;
 }
 
+int ivm_copy_error_flags_async(ivm_ctx *ctx, uint32_t *host_pinned_out, ivm_stream_t stream) {
+    if (!ctx || !host_pinned_out) return IVM_E_INVALID;
+    cudaError_t e = cudaMemcpyAsync(host_pinned_out, &ctx->P.g->err, sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "copy_error_flags_async");
+    return IVM_OK;
+}
+
+int ivm_clear_error_flags(ivm_ctx *ctx, ivm_stream_t stream) {
+    if (!ctx) return IVM_E_INVALID;
+    cudaError_t e = cudaMemsetAsync(&ctx->P.g->err, 0, sizeof(uint32_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(ctx, e, "clear_error_flags");
+    return IVM_OK;
+}
+
 int ivm_read_phase_ns(ivm_ctx *ctx, uint64_t *ns_out24, ivm_stream_t stream) {
     if (!ctx || !ns_out24) return IVM_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;

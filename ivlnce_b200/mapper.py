@@ -451,7 +451,7 @@ class MappingModule(nn.Module):
                  store_cells: int = DEFAULT_STORE_CELLS, known_capacity: int = DEFAULT_KNOWN_CAPACITY,
                  trig: str = "kernel", host_trig: bool = False, raster_tile: int = 0,
                  track_start_state: bool = False, scatter_variant: int = 0, stamp_period: int = 0,
-                 pipelined: bool = False):
+                 pipelined: bool = False, error_poll_interval: int = 32, on_overflow: str = "raise"):
         super().__init__()
         assert mode in ("iterative", "known")
         self.device = torch.device(device)
@@ -473,6 +473,16 @@ class MappingModule(nn.Module):
                                  scatter_variant=scatter_variant, stamp_period=stamp_period)
         self._engine: Optional[_MapEngine] = None
         self._pipelined = bool(pipelined)
+        # Errors reach a caller that never asks for them: every `error_poll_interval` forwards the device's error flags
+        # are copied into pinned host memory (asynchronously, no synchronisation); a later forward that finds the copy
+        # complete and a flag set raises MapLibraryError (on_overflow="warn": window overflows only warn, once).
+        assert on_overflow in ("raise", "warn")
+        self.error_poll_interval = int(error_poll_interval)
+        self.on_overflow = on_overflow
+        self._err_host = None
+        self._err_event = None
+        self._err_calls = 0
+        self._warned = False
         self._initial_max_envs = max_envs
         self._hold = _Hold()   # per-call state kept off the nn.Module attribute machinery
         self._known_cache: Dict[str, Tuple[torch.Tensor, torch.Tensor, int, int]] = {}
@@ -553,7 +563,49 @@ class MappingModule(nn.Module):
                 return self._forward_on_device(eng, B, episodes_info, observations, robot_current_state, hold)
         return self._forward_on_device(eng, B, episodes_info, observations, robot_current_state, hold)
 
+    def _poll_errors(self, eng):
+        ev = self._err_event
+        if ev is not None and ev.query():           # the copy issued a while ago has landed
+            self._err_event = None
+            flags = int(self._err_host[0])
+            if flags:
+                self._raise_flags(eng, flags)
+        self._err_calls += 1
+        if self._err_event is None and self.error_poll_interval > 0 and self._err_calls >= self.error_poll_interval:
+            self._err_calls = 0
+            if self._err_host is None:
+                self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            _lib.check(eng.lib.ivm_copy_error_flags_async(eng.ctx, self._err_host.data_ptr(), eng.stream()), eng.ctx,
+                       "ivm_copy_error_flags_async")
+            self._err_event = torch.cuda.Event()
+            self._err_event.record(torch.cuda.current_stream(self.device))
+
+    def _raise_flags(self, eng, flags: int):
+        overflow = flags & (_lib.ERR_STORE_OVERFLOW | _lib.ERR_KNOWN_OVERFLOW)
+        fatal = flags & ~overflow
+        if fatal & _lib.ERR_GRID_BARRIER:
+            self._engine = None                       # the context's barrier counters are out of step: start afresh
+            raise _lib.MapLibraryError("grid barrier time-out in the fused step kernel: the maps are invalid and the world "
+                                       "state has been dropped (a new context is created on the next call)")
+        if fatal & _lib.ERR_EDGE_OVERFLOW:
+            raise _lib.MapLibraryError("edge list capacity exceeded: bounding-box edge collisions may be unresolved")
+        if fatal:
+            raise _lib.MapLibraryError(f"map library error flags {flags}")
+        msg = ("points fell outside an env's world store window and were DROPPED (the reference's unbounded cloud keeps "
+               f"them): raise store_cells (now {eng.store_cells} half-cells = "
+               f"{eng.store_cells * self.map_dimensions.resolution_meters / 2:.1f} m per side)")
+        _lib.check(eng.lib.ivm_clear_error_flags(eng.ctx, eng.stream()), eng.ctx, "ivm_clear_error_flags")
+        if self.on_overflow == "raise":
+            raise _lib.MapLibraryError(msg)
+        if not self._warned:
+            import warnings
+
+            warnings.warn(msg)
+            self._warned = True
+
     def _forward_on_device(self, eng, B, episodes_info, observations, robot_current_state, hold):
+        if self.error_poll_interval > 0:
+            self._poll_errors(eng)
         T12, cs, pose, orient = self._matrices(robot_current_state)
         hold.keepalive = (T12, cs, pose, orient)
         if self.mode == "iterative":

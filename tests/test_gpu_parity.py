@@ -433,3 +433,35 @@ def test_back_to_back_full_size_against_oracle(pred):
     b1, x1, s1 = orc.world()
     b2, x2, s2 = cs.world()
     assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(s1, s2)
+
+
+def test_store_overflow_reaches_a_caller_that_never_asks():
+    """A trainer calls forward() and nothing else: a world-store overflow (points dropped, unlike the reference's
+    unbounded cloud) must surface by itself -- raised by a later forward(), without any synchronising status call --
+    or, with on_overflow="warn", warned once while the run continues."""
+    import warnings
+
+    from cuda_stepper import CudaStepper
+    from ivlnce_b200._lib import MapLibraryError
+
+    scn = load_golden("iid_f32_res005")
+    T = scn["masks"].shape[0]
+
+    def run(cs, steps):
+        for i in range(steps):
+            t = i % T
+            cs.step(scn["masks"][t], scn["pose"][t], scn["orientation"][t], depth=scn["depth"][t], labels=scn["labels"][t])
+
+    cs = CudaStepper(scn["cfg"], store_cells=256, max_envs=2)          # 6.4 m window: far points fall outside
+    cs.mm.error_poll_interval = 2
+    with pytest.raises(MapLibraryError, match="store window"):
+        run(cs, 12)
+    cs = CudaStepper(scn["cfg"], store_cells=256, max_envs=2)
+    cs.mm.error_poll_interval, cs.mm.on_overflow = 2, "warn"
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        run(cs, 12)
+    assert len(w) == 1 and "DROPPED" in str(w[0].message)
+    cs = CudaStepper(scn["cfg"], max_envs=2)                           # the default window holds everything: silent
+    cs.mm.error_poll_interval = 2
+    run(cs, 12)
