@@ -66,6 +66,25 @@ IVM_HD float ivm_fma(float a, float b, float c) { return fmaf(a, b, c); }
 IVM_HD uint32_t ivm_f2u(float f) { union { float f; uint32_t u; } v; v.f = f; return v.u; }
 #endif
 
+// rint(a / d) for a divisor that is fixed for the life of a context (cell size), without the IEEE division on the
+// common path.  The reference computes q = fl(a / d) and rounds it to the nearest integer (ties to even).  With
+// inv = fl(1 / d) and t = fl(a * inv):  |t - a/d| <= 2^-23 |a/d| (1 + eps)  and  |q - a/d| <= 2^-24 |a/d|,  hence
+// |t - q| < 1.8e-7 |t| + (denormal slack).  If t lies further than 1e-6 + 4e-7 |t| from every half-integer, q lies in
+// the same rounding interval and rint(q) == rint(t); otherwise (about 2 values in 10^6, and every NaN) `amb` is set
+// and the caller redoes the value with the true division.  So the result is ALWAYS the reference's integer.
+IVM_HD float ivm_rint_mul(float a, float inv, bool &amb) {
+    const float t = ivm_mul(a, inv);
+    const float r = rintf(t);
+    const float e = fabsf(ivm_sub(t, r));
+    amb = amb || !(e < fmaf(fabsf(t), -4.0e-7f, 0.499999f));
+    return r;
+}
+IVM_HD float ivm_rint_div(float a, float d, float inv) {
+    bool amb = false;
+    const float r = ivm_rint_mul(a, inv, amb);
+    return amb ? rintf(ivm_div(a, d)) : r;
+}
+
 // monotone float -> uint map (x < y  <=>  ord(x) < ord(y)); -0 and +0 map to the
 // same value because the reference compares heights with a float '>'.
 IVM_HD uint32_t ivm_orderable(float y) {
@@ -140,6 +159,8 @@ struct IvmGlobal {
     uint32_t prev_n_seg, prev_scan_chunks;  // last step's edge-line segments (still in P.segs): prefetch hints for the scan
     unsigned long long acc_valid, acc_local;  // per-step accumulators (K1 / K2+F), published and zeroed by F
     unsigned long long acc_e1, acc_e2;        // direct path: frame-edge winners examined / live records on the world edge lines
+    unsigned long long known_in[2];           // known-map mode: rastered points of the even / odd steps (one is counted into while
+                                              // the other is zeroed for the next step)
     unsigned long long stats[IVM_NSTATS];     // published figures of the last step; stats[IN] accumulates in K4
     // fused step kernel only
     unsigned long long tstamp[8];             // %globaltimer at the phase boundaries of the last fused step:
@@ -153,6 +174,7 @@ struct IvmParams {
     int32_t H, W, HW;
     int32_t R, C;                 // ego map rows / cols
     float res, half_res, half_h, half_w;
+    float inv_res, inv_half_res;  // fl(1 / res), fl(1 / half_res): ivm_rint_mul
     int32_t SR, SC;               // world store rows / cols (half-cells) per env
     int32_t maxB;
     int32_t tile_r, tile_c;       // ego tile of one raster CTA
@@ -327,13 +349,13 @@ IVM_HD float ivm_world_y(float d, float xs_u, float ys_v, const float *T) {
 
 // returns 0 = filtered out, 1 = valid point, 2 = valid but its cell index is not representable
 // (non-finite / absurd coordinates; the caller flags IVM_ERR_STORE_OVERFLOW)
-IVM_HD int ivm_unproject(float d, float xs_u, float ys_v, const float *T, float h, float half_res, IvmPoint &p) {
+IVM_HD int ivm_unproject(float d, float xs_u, float ys_v, const float *T, float h, float half_res, float inv, IvmPoint &p) {
     if (!(d > 0.01f && d < 0.99f)) return 0;
     float w[3];
     ivm_world_xyz(d, xs_u, ys_v, T, w[0], w[1], w[2]);
     if (!(w[1] > ivm_sub(h, 1.0f) && w[1] < ivm_add(h, 0.5f))) return 0;
-    const float rf = rintf(ivm_div(w[2], half_res));
-    const float cf = rintf(ivm_div(w[0], half_res));
+    const float rf = ivm_rint_div(w[2], half_res, inv);
+    const float cf = ivm_rint_div(w[0], half_res, inv);
     if (!(fabsf(rf) < 1.0e9f && fabsf(cf) < 1.0e9f)) return 2;
     p.x = w[0]; p.y = w[1]; p.z = w[2];
     p.r = (int32_t)rf; p.c = (int32_t)cf;
@@ -1279,16 +1301,21 @@ IVM_HD void ivm_row_span(const IvmTileGeom &G, int32_t rr, int32_t &clo, int32_t
 // One world record against the ego map: band filter (mapper.py:884-901), translate
 // + rotate (mapper.py:255-267: x+(-px); unfused c*x+s*z), cell index
 // (mapper.py:101-114).  Returns true and (row, col) if the record is inside the map.
-IVM_HD bool ivm_ego_cell(const IvmParams &P, float x, float y, float z, float px, float h, float pz, float c, float s,
-                         int32_t &row, int32_t &col) {
-    // straight-line on purpose (no early exit): independent records interleave in the raster loop
-    const bool band = y > ivm_sub(h, 1.25f) && y < ivm_add(h, 0.75f);
+// the ego-frame quotients' numerators: (ze + half_h, xe + half_w)
+IVM_HD void ivm_ego_numerators(const IvmParams &P, float x, float z, float px, float pz, float c, float s, float &ar, float &ac) {
     const float x1 = ivm_add(x, -px);
     const float z1 = ivm_add(z, -pz);
     const float xe = ivm_add(ivm_mul(c, x1), ivm_mul(s, z1));
     const float ze = ivm_add(ivm_mul(-s, x1), ivm_mul(c, z1));
-    const float rf = rintf(ivm_div(ivm_add(ze, P.half_h), P.res));
-    const float cf = rintf(ivm_div(ivm_add(xe, P.half_w), P.res));
+    ar = ivm_add(ze, P.half_h); ac = ivm_add(xe, P.half_w);
+}
+IVM_HD bool ivm_ego_cell(const IvmParams &P, float x, float y, float z, float px, float h, float pz, float c, float s,
+                         int32_t &row, int32_t &col) {
+    const bool band = y > ivm_sub(h, 1.25f) && y < ivm_add(h, 0.75f);
+    float ar, ac;
+    ivm_ego_numerators(P, x, z, px, pz, c, s, ar, ac);
+    const float rf = ivm_rint_div(ar, P.res, P.inv_res);
+    const float cf = ivm_rint_div(ac, P.res, P.inv_res);
     const bool in = band && rf >= 0.0f && rf < (float)P.R && cf >= 0.0f && cf < (float)P.C;
     row = in ? (int32_t)rf : 0; col = in ? (int32_t)cf : 0;
     return in;

@@ -87,7 +87,7 @@ __device__ __forceinline__ void k1_scatter_pixels(const IvmParams &P, int b, int
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
             IvmPoint p;
-            const int ok = ivm_unproject(d[j], P.xs[u0 + j], ysv, sh.T, h, P.half_res, p);
+            const int ok = ivm_unproject(d[j], P.xs[u0 + j], ysv, sh.T, h, P.half_res, P.inv_half_res, p);
             if (ok == 0) continue;
             size_t idx;
             if (ok == 2 || !ivm_store_index(P, sh.origin_r, sh.origin_c, b, p.r, p.c, idx)) {
@@ -350,7 +350,7 @@ k_ingest_scatter_bulk(IvmParams P, const float *__restrict__ logits, int ncls, u
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             IvmPoint p;
-            const int ok = ivm_unproject(dd[j], P.xs[u0 + j], ysv, sh.T, h, P.half_res, p);
+            const int ok = ivm_unproject(dd[j], P.xs[u0 + j], ysv, sh.T, h, P.half_res, P.inv_half_res, p);
             if (ok == 0) continue;
             size_t idx;
             if (ok == 2 || !ivm_store_index(P, sh.origin_r, sh.origin_c, b, p.r, p.c, idx)) {
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(IVM_THREADS) k_ingest_resolve(IvmParams P) {
         const uint32_t pix = q_pix[warp][i];
         const int v = (int)pix / P.W, u = (int)pix - v * P.W;
         IvmPoint p;
-        if (ivm_unproject(q_d[warp][i], P.xs[u], P.ys[v], sT, h, P.half_res, p) != 1) continue;
+        if (ivm_unproject(q_d[warp][i], P.xs[u], P.ys[v], sT, h, P.half_res, P.inv_half_res, p) != 1) continue;
         nlocal += (unsigned)ivm_resolve_pixel<IvmAtomics>(P, b, pix, p, q_lab[warp][i], sloc, origin_r, origin_c, acc);
     }
     // newly occupied cells: warp -> block -> 5 global atomics per CTA
@@ -510,6 +510,41 @@ __device__ __forceinline__ void group_bar(int bar_id, int nthr) {
         case 3: asm volatile("bar.sync 3, %0;" ::"r"(nthr) : "memory"); break;
         case 4: asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory"); break;
         default: asm volatile("bar.sync 5, %0;" ::"r"(nthr) : "memory"); break;
+    }
+}
+
+// MLP records of one lane together: the common path is branch-free (the rare ambiguous quotient, ivm_rint_mul,
+// sends all of them through the true division once), so that the independent chains interleave.
+template <int MLP, bool KNOWN>
+__device__ __forceinline__ void raster_records(const IvmParams &P, const uint4 *raw, const bool *have, uint32_t rs1, float px, float pz,
+                                               float c, float s, float ylo, float yhi, float fr0, float fr1, float fc0, float fc1,
+                                               int r0, int c0, int tc, const uint32_t *cell, uint32_t *skey, uint8_t *socc, unsigned &n_in) {
+    float ar[MLP], ac[MLP], rf[MLP], cf[MLP];
+    bool amb = false;
+#pragma unroll
+    for (int u = 0; u < MLP; ++u) {
+        ivm_ego_numerators(P, __uint_as_float(raw[u].x), __uint_as_float(raw[u].z), px, pz, c, s, ar[u], ac[u]);
+        rf[u] = ivm_rint_mul(ar[u], P.inv_res, amb);
+        cf[u] = ivm_rint_mul(ac[u], P.inv_res, amb);
+    }
+    if (amb) {
+#pragma unroll
+        for (int u = 0; u < MLP; ++u) { rf[u] = rintf(ivm_div(ar[u], P.res)); cf[u] = rintf(ivm_div(ac[u], P.res)); }
+    }
+#pragma unroll
+    for (int u = 0; u < MLP; ++u) {
+        const float y = __uint_as_float(raw[u].y);
+        bool ok = have[u] && y > ylo && y < yhi && rf[u] >= fr0 && rf[u] < fr1 && cf[u] >= fc0 && cf[u] < fc1;
+        if (!KNOWN) ok = ok && (raw[u].w >> 8) >= rs1;   // live: written since the env's last reset (rs1 >= 1: never-written cells fail)
+        if (ok) {
+            ++n_in;
+            const int t = ((int)rf[u] - r0) * tc + ((int)cf[u] - c0);
+            socc[t] = 1;  // OccupancyStatus.OCCUPIED
+            const uint32_t label = raw[u].w & 0xFFu;
+            // last point in list order wins (mapper.py:569-571): list order within an env is (half-row, half-col)
+            // lexicographic / the npz index in known mode; labels 0 are excluded (mapper.py:611)
+            if (label) atomicMax(&skey[t], KNOWN ? raw[u].w : ((cell[u] << 8) | label));
+        }
     }
 }
 
@@ -582,6 +617,9 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
     ivm_tile_geom(P, px, pz, c, s, r0, r1, c0, c1, G);
     const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
     (void)lane;
+    const uint32_t rs1 = max(e.reset_stamp, 1u);
+    const float ylo = ivm_sub(h, 1.25f), yhi = ivm_add(h, 0.75f);   // FilterPointCloudByRobotHeight, mapper.py:884-901
+    const float fr0 = (float)r0, fr1 = (float)r1, fc0 = (float)c0, fc1 = (float)c1;
     int row_lo = max(G.row_lo, KNOWN ? e.origin_r : e.rmin);
     int row_hi = min(G.row_hi, KNOWN ? e.origin_r + P.SR - 1 : e.rmax);
     if (e.count <= 0) row_hi = row_lo - 1;
@@ -687,6 +725,8 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
         // (Measured: prefetching the next rows' records while a batch is evaluated does not pay inside the
         // 96-register budget of the persistent kernel -- the loop is bound by its dependent arithmetic.)
         (void)hw; (void)nhw;
+        // (Measured: two pairs of half-rows per iteration -- 8 record loads in flight per lane -- spills inside the 72-register
+        // budget of the persistent kernel and loses: record loop 7.4 -> 8.1 us.)
         for (int i0 = 2 * warp; i0 < nrows; i0 += 2 * nwarps) {
             const int i = i0 + (lane >> 4);
             const int len = i < nrows ? s_len[i] : 0;
@@ -695,10 +735,12 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
             for (int k0 = 0; k0 < lenmax; k0 += 16 * IVM_RASTER_MLP) {
                 uint4 raw[IVM_RASTER_MLP];
                 bool have[IVM_RASTER_MLP];
+                uint32_t cellv[IVM_RASTER_MLP];
 #pragma unroll
                 for (int u = 0; u < IVM_RASTER_MLP; ++u) {
                     const int off = k0 + 16 * u + l16;
                     have[u] = off < len;
+                    cellv[u] = rowbase + (uint32_t)off;
                     raw[u] = make_uint4(0, 0, 0, 0);
                     // L2-only load: in the persistent kernel the records were written earlier in the same launch
                     if (have[u]) {
@@ -706,11 +748,8 @@ __device__ __forceinline__ bool raster_tile(const IvmParams &P, int max_rows, in
                         raw[u] = make_uint4(__float_as_uint(q.x), __float_as_uint(q.y), __float_as_uint(q.z), q.meta);
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < IVM_RASTER_MLP; ++u)
-                    if (k0 + 16 * u < lenmax)  // warp-uniform
-                        raster_record(P, raw[u], have[u], e.reset_stamp, px, h, pz, c, s, r0, r1, c0, c1, tc,
-                                      rowbase + (uint32_t)(k0 + 16 * u + l16), skey, socc, n_in);
+                raster_records<IVM_RASTER_MLP, false>(P, raw, have, rs1, px, pz, c, s, ylo, yhi, fr0, fr1, fc0, fc1, r0, c0, tc, cellv,
+                                                      skey, socc, n_in);
             }
         }
     }
@@ -757,6 +796,103 @@ __global__ void __launch_bounds__(IVM_RASTER_THREADS) k_raster(IvmParams P, int 
                        blockDim.x, 0, n_in);
     const unsigned wn = warp_sum(n_in);
     if (wn && (threadIdx.x & 31) == 0) atomicAdd(&P.g->stats[IVM_STAT_IN], (unsigned long long)wn);
+}
+
+// Known-map raster (BASELINE config 5): one 128-thread CTA per ego tile of one env, over the env's CSR store (points
+// sorted by half-cell).  The step is latency-bound (a few hundred KB per env), so everything is arranged for few
+// dependent round trips: (1) one thread per store half-row solves its column span and reads the two CSR offsets;
+// (2) a scan turns the row counts into one flat index space; (3) every thread then loads IVM_KNOWN_MLP points that
+// are independent of each other before it evaluates any (flat index -> row by binary search in shared memory).
+// The whole known-map step is this ONE kernel: thread 0 of a CTA derives (cos, sin)(-heading) from the angles itself
+// (mapper.py:38-48, in the angles' dtype) while the others clear the tile.
+#define IVM_KNOWN_MLP 8
+__global__ void __launch_bounds__(IVM_RASTER_THREADS, 8) k_raster_known(const __grid_constant__ IvmParams P, int max_rows, int parity) {
+    extern __shared__ __align__(16) uint32_t ksm[];
+    const int tr = P.tile_r, tc = P.tile_c, tid = threadIdx.x, nthr = blockDim.x;
+    uint32_t *skey = ksm;
+    uint32_t *s_p0 = skey + tr * tc;
+    int32_t *s_off = reinterpret_cast<int32_t *>(s_p0 + max_rows);   // [max_rows + 1] exclusive prefix of the row counts
+    uint8_t *socc = reinterpret_cast<uint8_t *>(s_off + max_rows + 1);
+    const int b = blockIdx.z, r0 = blockIdx.y * tr, c0 = blockIdx.x * tc;
+    const int r1 = min(r0 + tr, P.R), c1 = min(c0 + tc, P.C);
+    __shared__ float s_cs[2];
+    if (tid == 0) {
+        if (P.orient != nullptr) {
+            float T[12];
+            ivm_pose_matrices(P, b, T, s_cs);
+        } else {
+            s_cs[0] = P.cs[2 * b + 0]; s_cs[1] = P.cs[2 * b + 1];
+        }
+        if (blockIdx.x == 0 && blockIdx.y == 0 && b == 0) P.g->known_in[parity ^ 1] = 0ull;  // the next step's counter
+    }
+    for (int i = tid; i < tr * tc; i += nthr) { skey[i] = 0u; socc[i] = 0; }
+    const IvmEnv e = P.env[b];
+    const float px = P.pose[3 * b + 0], h = P.pose[3 * b + 1], pz = P.pose[3 * b + 2];
+    __syncthreads();
+    const float c = s_cs[0], s = s_cs[1];
+    IvmTileGeom G;
+    ivm_tile_geom(P, px, pz, c, s, r0, r1, c0, c1, G);
+    int row_lo = max(G.row_lo, e.origin_r), row_hi = min(G.row_hi, e.origin_r + P.SR - 1);
+    if (e.count <= 0) row_hi = row_lo - 1;
+    if (row_hi - row_lo + 1 > max_rows) row_hi = row_lo + max_rows - 1;  // cannot happen: max_rows bounds the tile diagonal
+    const int nrows = max(row_hi - row_lo + 1, 0);
+    const uint32_t *off = P.koff + (size_t)b * ((size_t)P.SR * P.SC + 1);
+    for (int i = tid; i < nrows; i += nthr) {
+        int clo, chi;
+        ivm_row_span(G, row_lo + i, clo, chi);
+        clo = max(clo, e.origin_c); chi = min(chi, e.origin_c + P.SC - 1);
+        uint32_t p0 = 0u, p1 = 0u;
+        if (chi >= clo) {
+            const uint32_t *o = off + (size_t)(row_lo + i - e.origin_r) * P.SC;
+            p0 = __ldg(o + (clo - e.origin_c)); p1 = __ldg(o + (chi - e.origin_c + 1));
+        }
+        s_p0[i] = p0; s_off[i + 1] = (int32_t)(p1 - p0);
+    }
+    if (tid == 0) s_off[0] = 0;
+    __syncthreads();
+    if (tid < 32) {  // inclusive scan of the row counts
+        int carry = 0;
+        for (int i0 = 0; i0 < nrows; i0 += 32) {
+            const int i = i0 + tid;
+            int x = i < nrows ? s_off[i + 1] : 0;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (tid >= o) x += y; }
+            if (i < nrows) s_off[i + 1] = carry + x;
+            carry += __shfl_sync(0xffffffffu, x, 31);
+        }
+    }
+    __syncthreads();
+    const int total = nrows > 0 ? s_off[nrows] : 0;
+    const IvmRecord *pts = P.kpts + (size_t)b * P.kcap;
+    unsigned n_in = 0;
+    const float ylo = ivm_sub(h, 1.25f), yhi = ivm_add(h, 0.75f);
+    int row = 0;  // the row of this thread's current flat index: indices only grow, so the row is walked forward
+    for (int base = 0; base < total; base += nthr * IVM_KNOWN_MLP) {
+        uint4 raw[IVM_KNOWN_MLP];
+        bool have[IVM_KNOWN_MLP];
+#pragma unroll
+        for (int u = 0; u < IVM_KNOWN_MLP; ++u) {
+            const int f = base + u * nthr + tid;
+            have[u] = f < total;
+            raw[u] = make_uint4(0, 0, 0, 0);
+            if (have[u]) {
+                while (s_off[row + 1] <= f) ++row;            // last row with s_off[row] <= f
+                raw[u] = __ldg(reinterpret_cast<const uint4 *>(pts + (s_p0[row] + (uint32_t)(f - s_off[row]))));
+            }
+        }
+        // raw.w = (npz index << 8) | label: later points overwrite earlier ones (mapper.py:569-571), label 0 excluded
+        raster_records<IVM_KNOWN_MLP, true>(P, raw, have, 0u, px, pz, c, s, ylo, yhi, (float)r0, (float)r1, (float)c0, (float)c1, r0, c0,
+                                            tc, nullptr, skey, socc, n_in);
+    }
+    __syncthreads();
+    const int wr = r1 - r0, wc = c1 - c0;
+    for (int i = tid; i < wr * wc; i += nthr) {
+        const int rr = i / wc, cc = i - rr * wc;
+        const size_t o = ((size_t)b * P.R + (size_t)(r0 + rr)) * P.C + (size_t)(c0 + cc);
+        P.occ[o] = socc[rr * tc + cc];
+        P.sem[o] = (uint8_t)(skey[rr * tc + cc] & 0xFFu);
+    }
+    const unsigned wn = warp_sum(n_in);
+    if (wn && (tid & 31) == 0) atomicAdd(&P.g->known_in[parity], (unsigned long long)wn);
 }
 
 __global__ void k_pose(IvmParams P) {
@@ -1202,8 +1338,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                 const int v = pix / P.W, u = pix - v * P.W;
                 float x, y, z;
                 ivm_world_xyz(qd[o], P.xs[u], P.ys[v], sl.T, x, y, z);
-                const float rf = rintf(ivm_div(z, P.half_res));
-                const float cf = rintf(ivm_div(x, P.half_res));
+                const float rf = ivm_rint_div(z, P.half_res, P.inv_half_res);
+                const float cf = ivm_rint_div(x, P.half_res, P.inv_half_res);
                 const bool rep = fabsf(rf) < 1.0e9f && fabsf(cf) < 1.0e9f;
                 const int32_t r = rep ? (int32_t)rf : 0, c = rep ? (int32_t)cf : 0;
                 const int32_t rr = r - sl.origin_r, cc = c - sl.origin_c;
@@ -1290,8 +1426,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                     const int v = pix / P.W, u = pix - v * P.W;
                     float x, y, z;
                     ivm_world_xyz(qd[o], P.xs[u], P.ys[v], sl.T, x, y, z);
-                    const float rf = rintf(ivm_div(z, P.half_res));
-                    const float cf = rintf(ivm_div(x, P.half_res));
+                    const float rf = ivm_rint_div(z, P.half_res, P.inv_half_res);
+                    const float cf = ivm_rint_div(x, P.half_res, P.inv_half_res);
                     const bool rep = fabsf(rf) < 1.0e9f && fabsf(cf) < 1.0e9f;
                     const int32_t rr = (rep ? (int32_t)rf : 0) - sl.origin_r, cc = (rep ? (int32_t)cf : 0) - sl.origin_c;
                     qcell[o] = (rep && rr >= 0 && rr < P.SR && cc >= 0 && cc < P.SC) ? (((uint32_t)rr << 16) | (uint32_t)cc) : 0xFFFFFFFFu;
@@ -1687,8 +1823,8 @@ __global__ void k_known_reset_env(IvmParams P, int b, long long n, int origin_r,
 
 __device__ __forceinline__ bool known_cell(const IvmParams &P, const float *xyz, long long i, int origin_r, int origin_c,
                                            uint32_t &cell) {
-    const float rf = rintf(ivm_div(xyz[3 * i + 2], P.half_res));
-    const float cf = rintf(ivm_div(xyz[3 * i + 0], P.half_res));
+    const float rf = ivm_rint_div(xyz[3 * i + 2], P.half_res, P.inv_half_res);
+    const float cf = ivm_rint_div(xyz[3 * i + 0], P.half_res, P.inv_half_res);
     if (!(fabsf(rf) < 1.0e9f && fabsf(cf) < 1.0e9f)) return false;
     const int rr = (int)rf - origin_r, cc = (int)cf - origin_c;
     if (rr < 0 || rr >= P.SR || cc < 0 || cc >= P.SC) return false;
@@ -1929,6 +2065,7 @@ struct ivm_ctx {
     size_t ovl_smem[2];
     uint32_t bar_base;    // value of IvmGlobal.bar_count before the next fused launch
     uint32_t team_base;   // same for the fix-up team's arrival counter (k_step_overlap)
+    uint32_t kstep;       // known-map mode: steps so far (parity selects the rastered-points counter)
     uint32_t done_base;   // same for the CTAs-done counter: CTAs of all fused launches so far
     int pipelined;        // ivm_set_pipelined: consecutive steps may overlap (see ivln_map.h)
     int64_t launches;
@@ -1975,7 +2112,7 @@ static uint32_t hash_size(uint32_t ecap) { uint32_t h = 1024; while (h < 2 * eca
 static void tile_dims(const ivm_config *c, int *tr_out, int *tc_out) {
     int tr = c->tile_rows, tc = c->tile_cols;
     if ((tr <= 0 || tc <= 0) && c->mode == 1) {
-        tr = 32; tc = 32;  // known-map mode: stand-alone raster kernel, no wave to fit (64 envs: 8x8 128, 16x16 94, 32x32 88-94, 64x32 99 us)
+        tr = 16; tc = 16;  // known-map mode: one 128-thread CTA per tile, 16 CTAs per SM -- many small tiles keep the SMs full
     } else if (tr <= 0 || tc <= 0) {
         const double groups = 840.0, fixed = 150.0, margin = 6.0;
         double best = 1.0e300;
@@ -2081,6 +2218,7 @@ int ivm_create(const ivm_config *cfg, void *workspace_dev, size_t workspace_byte
     P.H = cfg->height; P.W = cfg->width; P.HW = cfg->height * cfg->width;
     P.R = cfg->map_rows; P.C = cfg->map_cols;
     P.res = cfg->res; P.half_res = cfg->half_res; P.half_h = cfg->half_h; P.half_w = cfg->half_w;
+    P.inv_res = 1.0f / cfg->res; P.inv_half_res = 1.0f / cfg->half_res;  // IEEE single division on the host
     P.SR = cfg->store_rows; P.SC = cfg->store_cols; P.maxB = cfg->max_envs;
     int tr = 0, tc = 0;
     tile_dims(cfg, &tr, &tc);
@@ -2188,8 +2326,12 @@ static void launch_raster(ivm_ctx *ctx, const IvmParams &P, cudaStream_t st, boo
     dim3 grid((P.C + P.tile_c - 1) / P.tile_c, (P.R + P.tile_r - 1) / P.tile_r, P.B);
     const int max_rows = raster_max_rows(P);
     const size_t smem = raster_smem_bytes(P.tile_r, P.tile_c, max_rows);
-    if (known) k_raster<true><<<grid, IVM_RASTER_THREADS, smem, st>>>(P, max_rows);
-    else k_raster<false><<<grid, IVM_RASTER_THREADS, smem, st>>>(P, max_rows);
+    if (known) {
+        const size_t ksmem = (size_t)P.tile_r * P.tile_c * 5 + (size_t)(2 * max_rows + 1) * 4 + 32;
+        k_raster_known<<<grid, IVM_RASTER_THREADS, ksmem, st>>>(P, max_rows, (int)(ctx->kstep & 1u));
+    } else {
+        k_raster<false><<<grid, IVM_RASTER_THREADS, smem, st>>>(P, max_rows);
+    }
     ctx->launches += 1;
 }
 
@@ -2415,11 +2557,8 @@ int ivm_step_known(ivm_ctx *ctx, int32_t num_envs, const float *pose, const floa
     P.B = num_envs; P.pose = pose; P.cs = cs; P.occ = occ; P.sem = sem;
     const int slot = timing_slot(ctx);
     P.orient = nullptr;
-    if (orientation) { P.orient = orientation; P.orient_f64 = orientation_is_f64; P.cs = P.cs_buf; }
-    T_BEGIN(0);
-    k_pose<<<(num_envs + 127) / 128, 128, 0, st>>>(P);
-    T_END(0);
-    ctx->launches += 1;
+    if (orientation) { P.orient = orientation; P.orient_f64 = orientation_is_f64; }
+    ctx->kstep += 1u;
     T_BEGIN(4);
     launch_raster(ctx, P, st, true);
     T_END(4);
@@ -2459,6 +2598,7 @@ int ivm_read_status(ivm_ctx *ctx, ivm_status *host_out, ivm_stream_t stream) {
     host_out->error_flags = g.err;
     host_out->pad = 0;
     for (int i = 0; i < 8; ++i) host_out->stats[i] = g.stats[i];
+    if (ctx->cfg.mode == 1) host_out->stats[IVM_STAT_IN] = g.known_in[ctx->kstep & 1u];
     return IVM_OK;
 }
 

@@ -488,6 +488,7 @@ class MappingModule(nn.Module):
         self._known_cache: Dict[str, Tuple[torch.Tensor, torch.Tensor, int, int]] = {}
         self._known_order: List[int] = []   # env indices in load order (world-cloud order in known mode)
         self._known_loaded: Dict[int, str] = {}
+        self._known_names = None    # env_names of the last call if every env holds the scene it is in
 
     @property
     def _num_envs(self) -> int:
@@ -689,10 +690,12 @@ class MappingModule(nn.Module):
         # Which envs reload their scene cloud (mask == 0, mapper.py:873-878)?  A reload of the scene an env already
         # holds changes nothing, so the masks matter only where the scene differs from the loaded one (or nothing is
         # loaded yet): only then are they read -- a device sync if they live on the device; never in steady state.
-        names = [str(n) for n in episodes_info.env_names[:B]]
-        if all(self._known_loaded.get(b) == names[b] for b in range(B)):
-            finished = []
+        env_names = episodes_info.env_names
+        last = self._known_names
+        if last is not None and last.shape == env_names.shape and bool((last == env_names).all()):
+            finished = []          # every env still holds the scene it is in (one vectorised comparison)
         else:
+            names = [str(n) for n in env_names[:B]]
             m = episodes_info.not_done_masks
             finished = [b for b in (m == episodes_info.EPISODE_FINISHED).nonzero().flatten().tolist()
                         if self._known_loaded.get(b) != names[b]]
@@ -705,6 +708,9 @@ class MappingModule(nn.Module):
                 self._known_order.remove(b)
             self._known_order.append(b)
             self._known_loaded[b] = name
+        if finished or self._known_names is None:
+            ok = all(self._known_loaded.get(b) == str(env_names[b]) for b in range(B))
+            self._known_names = np.array(env_names[:B], copy=True) if ok else None
         _lib.check(lib.ivm_step_known(eng.ctx, B, pose.data_ptr(), None if cs is None else cs.data_ptr(),
                                       None if orient is None else orient.data_ptr(),
                                       1 if (orient is not None and orient.dtype == torch.float64) else 0,

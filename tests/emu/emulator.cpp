@@ -51,6 +51,7 @@ Emu *emu_create(int H, int W, const float *xs, const float *ys, float res, float
     IvmParams &P = m->P;
     P.H = H; P.W = W; P.HW = H * W; P.R = R; P.C = C;
     P.res = res; P.half_res = half_res; P.half_h = half_h; P.half_w = half_w;
+    P.inv_res = ivm_div(1.0f, res); P.inv_half_res = ivm_div(1.0f, half_res);
     P.SR = SR; P.SC = SC; P.maxB = maxB;
     P.pix_bits = ivm_pix_bits((long long)H * W);
     P.tile_r = tile_r > R ? R : tile_r; P.tile_c = tile_c > C ? C : tile_c;
@@ -208,7 +209,7 @@ int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels,
         const int b = gp / P.HW, pix = gp - b * P.HW;
         const int v = pix / P.W, u = pix - v * P.W;
         IvmPoint p;
-        const int ok = ivm_unproject(depth[gp], P.xs[u], P.ys[v], T12 + 12 * b, pose[3 * b + 1], P.half_res, p);
+        const int ok = ivm_unproject(depth[gp], P.xs[u], P.ys[v], T12 + 12 * b, pose[3 * b + 1], P.half_res, P.inv_half_res, p);
         if (ok == 0) continue;
         size_t idx;
         if (ok == 2 || !ivm_store_index(P, prep[b].origin_r, prep[b].origin_c, b, p.r, p.c, idx)) { m->g.err |= IVM_ERR_STORE_OVERFLOW; continue; }
@@ -225,7 +226,7 @@ int emu_step_iterative(Emu *m, int B, const float *depth, const uint8_t *labels,
         const int b = gp / P.HW, pix = gp - b * P.HW;
         const int v = pix / P.W, u = pix - v * P.W;
         IvmPoint p;
-        if (ivm_unproject(depth[gp], P.xs[u], P.ys[v], T12 + 12 * b, pose[3 * b + 1], P.half_res, p) != 1) continue;
+        if (ivm_unproject(depth[gp], P.xs[u], P.ys[v], T12 + 12 * b, pose[3 * b + 1], P.half_res, P.inv_half_res, p) != 1) continue;
         IvmBoxAcc acc;
         acc.clear();
         if (direct1)
@@ -285,7 +286,7 @@ int emu_known_load(Emu *m, int b, long long n, const float *xyz, const uint8_t *
     memset(off, 0, sizeof(uint32_t) * (ncell + 1));
     std::vector<uint32_t> cell(n, 0xFFFFFFFFu);
     for (long long i = 0; i < n; ++i) {
-        const float rf = rintf(ivm_div(xyz[3 * i + 2], P.half_res)), cf = rintf(ivm_div(xyz[3 * i], P.half_res));
+        const float rf = ivm_rint_div(xyz[3 * i + 2], P.half_res, P.inv_half_res), cf = ivm_rint_div(xyz[3 * i], P.half_res, P.inv_half_res);
         const int rr = (int)rf - origin_r, cc = (int)cf - origin_c;
         if (rr < 0 || rr >= P.SR || cc < 0 || cc >= P.SC) { m->g.err |= IVM_ERR_KNOWN_OVERFLOW; continue; }
         cell[i] = (uint32_t)rr * P.SC + cc;
@@ -352,3 +353,28 @@ long long emu_cand_current(const Emu *m) {
 }
 
 }  // extern "C"
+
+// Exhaustive check of ivm_rint_div against rint of the true fp32 quotient: every float a with lo <= |a| <= hi
+// (both signs).  Returns the number of values whose results differ (must be 0); *ambiguous receives how many
+// took the true-division fallback.
+extern "C" long long emu_check_rint_div(float d, float lo, float hi, long long *ambiguous) {
+    const float inv = ivm_div(1.0f, d);
+    union { float f; uint32_t u; } a, b;
+    a.f = lo; b.f = hi;
+    long long bad = 0, amb_n = 0;
+    for (uint32_t u = a.u; u <= b.u; ++u) {
+        union { float f; uint32_t u; } v;
+        v.u = u;
+        for (int sgn = 0; sgn < 2; ++sgn) {
+            const float x = sgn ? -v.f : v.f;
+            bool amb = false;
+            (void)ivm_rint_mul(x, inv, amb);
+            amb_n += amb;
+            const float want = rintf(ivm_div(x, d));
+            const float got = ivm_rint_div(x, d, inv);
+            bad += !(got == want);
+        }
+    }
+    if (ambiguous) *ambiguous = amb_n;
+    return bad;
+}

@@ -144,3 +144,24 @@ def test_plugin_shim_contract():
     out = plugin(obs)
     assert set(out) == {"depth", "rgb", "not_done_masks", "occupancy_map", "semantic_map"}
     assert out["occupancy_map"].shape == (2, 64, 64) and out["occupancy_map"].dtype == torch.uint8
+
+
+@pytest.mark.parametrize("d", [0.05, 0.025, 0.1, 0.2, 0.07, 1.0 / 3.0])
+def test_rint_of_quotient_without_division_is_exact(d):
+    """ivm_rint_div (ivm_core.h) = rint(a / d) of the true fp32 division for EVERY float a with 2^-20 <= |a| <= 700 d
+    (both signs; ~0.4 G values per divisor): the raster and the scatter use it instead of an IEEE division per point."""
+    import ctypes
+
+    from emu_wrapper import lib
+
+    L = lib()
+    L.emu_check_rint_div.restype = ctypes.c_longlong
+    L.emu_check_rint_div.argtypes = [ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.POINTER(ctypes.c_longlong)]
+    amb = ctypes.c_longlong(0)
+    bad = L.emu_check_rint_div(np.float32(d), np.float32(2.0 ** -20), np.float32(700.0 * d), ctypes.byref(amb))
+    assert bad == 0
+    assert 0 < amb.value < 4_000_000   # the fallback exists, and is rare
+    # huge, tiny and non-finite numerators take the fallback or agree trivially
+    for a in (0.0, 1e-38, 1e-45, 3.0e38, float("inf"), float("nan"), 1.0e9, 123456.789):
+        amb2 = ctypes.c_longlong(0)
+        assert L.emu_check_rint_div(np.float32(d), np.float32(a), np.float32(a), ctypes.byref(amb2)) == 0 or a != a
