@@ -465,3 +465,25 @@ def test_store_overflow_reaches_a_caller_that_never_asks():
     cs = CudaStepper(scn["cfg"], max_envs=2)                           # the default window holds everything: silent
     cs.mm.error_poll_interval = 2
     run(cs, 12)
+
+
+def test_step_counter_rebase_keeps_parity():
+    """the 24-bit step stamps are rebased after 2^24 - 1 steps (ivm_rebase_stamps).  Start a context just below
+    the limit so that the rebase happens in mid-run; maps and world cloud must stay the reference's."""
+    import ctypes
+
+    from cuda_stepper import CudaStepper
+    from ivlnce_b200 import _lib
+
+    scn = load_golden("iid_f64")
+    cs = CudaStepper(scn["cfg"], max_envs=3, trig="kernel")
+    eng = cs.mm.engine(3)
+    _lib.check(eng.lib.ivm_debug_set_step(eng.ctx, ctypes.c_uint32(0xFFFFFF - 5)))
+    T = scn["masks"].shape[0]
+    for t in range(T):
+        o, s = cs.step(scn["masks"][t], scn["pose"][t], scn["orientation"][t], depth=scn["depth"][t], labels=scn["labels"][t])
+        assert np.array_equal(o, scn["ref_occupancy"][t]) and np.array_equal(s, scn["ref_semantic"][t]), t
+    cs.mm.check_errors()
+    b, xyz, sem = cs.world()
+    assert np.array_equal(b, scn["ref_world_b"]) and np.array_equal(xyz.view(np.uint32), scn["ref_world_xyz"].view(np.uint32))
+    assert np.array_equal(sem, scn["ref_world_sem"])
