@@ -167,7 +167,18 @@ struct IvmGlobal {
                                               // 0 start, 1 ingest done, 2 resolve done, 3 fix-up done, 4 raster released,
                                               // 5 max over CTAs of the end time
     unsigned long long ttrace[16];            // %globaltimer at the milestones inside the fix-up program (device only)
+    // fused step kernel, direct edge resolution: the edge-line scan of a step is skipped while nothing that could create
+    // a collision has happened since the last one.  After a scan every key class on the world-box edge lines has one
+    // survivor; a new member needs a cell ON one of those lines to become live (edge_touched), another world box
+    // (scan_glob) or another batch (scan_B) -- resets and deletions only remove members.
+    int32_t scan_glob[4];                     // world box of the last completed direct scan (16-byte aligned)
+    uint32_t scan_valid;                      // scan_glob / scan_B describe the store as the last direct scan left it
+    int32_t scan_B;
+    uint32_t edge_touched;                    // a cell on an edge line of scan_glob became live since that scan
+    uint32_t pad1;
 };
+
+static_assert(offsetof(IvmGlobal, scan_glob) % 16 == 0, "scan_glob is read with one 128-bit load");
 
 struct IvmParams {
     // geometry

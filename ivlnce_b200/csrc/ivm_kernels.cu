@@ -1010,6 +1010,7 @@ struct OvlShared {
     int32_t qoff[NSLOT + 1];   // prefix of the chunk's queue lengths
     int32_t glob[4], loc4[4];  // world box over the env boxes at grid barrier 2 / frame box of the step
     int32_t direct;            // both boxes allow the direct resolution of the edge collisions
+    int32_t skipscan;          // ... and the edge lines are as the last scan left them (IvmGlobal::scan_glob)
     int32_t segcnt[2];         // direct edge-line scan: segments, longest segment
     int32_t gband[8];          // raster: bands of half-rows / half-cols that hold the global bbox edge lines (ovl_global_bands)
 };
@@ -1066,7 +1067,8 @@ __device__ __forceinline__ bool grid_wait_group(uint32_t *bar, uint32_t target, 
 // not reach beyond the known world: the usual case), and likewise for the other three sides.  Reads that race
 // with stage 1's merges only move Rb2 inside that band.  Called by one warp right after grid barrier 2;
 // band[0..1] first-row band, [2..3] last-row band, [4..5] first-col band, [6..7] last-col band.
-__device__ __forceinline__ void ovl_global_bands(const IvmParams &P, int lane, int32_t *band, int32_t *glob, int32_t *loc4, int32_t *direct) {
+__device__ __forceinline__ void ovl_global_bands(const IvmParams &P, int lane, int32_t *band, int32_t *glob, int32_t *loc4, int32_t *direct,
+                                                 int32_t *skipscan) {
     int rmin = INT32_MAX, rmax = INT32_MIN, cmin = INT32_MAX, cmax = INT32_MIN;
     for (int b = lane; b < P.B; b += 32) {
         const IvmEnv *e = &P.env[b];
@@ -1084,12 +1086,17 @@ __device__ __forceinline__ void ovl_global_bands(const IvmParams &P, int lane, i
         loc4[0] = l0; loc4[1] = l1; loc4[2] = l2; loc4[3] = l3;
         const bool frame_direct = l0 > l1 || ivm_box_direct(loc4);
         *direct = (frame_direct && rmin <= rmax && ivm_box_direct(glob)) ? 1 : 0;
+        // nothing has touched the edge lines of the same world box since the last direct scan: no class can have gained a member
+        const int4 sg = __ldcg(reinterpret_cast<const int4 *>(P.g->scan_glob));
+        *skipscan = (*direct && __ldcg(&P.g->scan_valid) != 0u && __ldcg(&P.g->scan_B) == P.B && __ldcg(&P.g->edge_touched) == 0u &&
+                     sg.x == rmin && sg.y == rmax && sg.z == cmin && sg.w == cmax) ? 1 : 0;
     }
 }
 
+#define OVL_STEPLOG(k) P.cta_trace[(size_t)(512 + (P.step & 255u)) * IVM_TRACE_SLOTS + (k)]  // per-step log of CTA 0 (rows 512..767)
 #define OVL_STAMP(k, who)                                                                              \
     do {                                                                                               \
-        if (tid == (who) && blockIdx.x < IVM_TRACE_CTAS)                                               \
+        if (tid == (who) && blockIdx.x < IVM_TRACE_CTAS && trace_on)                                   \
             P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + (k)] = global_timer();                  \
     } while (0)
 
@@ -1113,6 +1120,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     // tiles are dealt round-robin: tile = CTA + j * grid (valid pixels cluster in a few image rows)
     const int grid_n = (int)gridDim.x, cta = (int)blockIdx.x;
     const int my_tiles = (total - cta + grid_n - 1) / grid_n;
+    const bool trace_on = !(P.debug & 4096) || (P.step & 31u) == 20u;  // debug bit 4096: trace one step in 32 (a mid-burst step)
     const int nslot = (P.debug & 128) ? 2 : NSLOT;         // tiles per chunk (debug bit 128: tiny chunks, to test the multi-chunk path)
     const bool keep_queue = my_tiles <= nslot;             // the queue built by G1 is still there in G3
     uint32_t *qcell = reinterpret_cast<uint32_t *>(dyn + RING_BYTES);
@@ -1285,12 +1293,13 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             }
             if (blockIdx.x == 0) {
                 g->tstamp[0] = sh.t_start; g->tstamp[5] = 0ull; g->tstamp[6] = global_timer();
+                OVL_STEPLOG(0) = g->tstamp[6]; OVL_STEPLOG(5) = sh.t_start; OVL_STEPLOG(4) = 0ull; OVL_STEPLOG(3) = 0ull;
                 g->stats[IVM_STAT_IN] = 0ull;  // this step's rastered-record count (added to after grid barrier 2)
                 P.bar[IVM_O_TILE_CTR] = (unsigned)RG * (gridDim.x - (gridDim.x > 1 ? (unsigned)team : 0u));  // raster tiles handed out statically
             }
         }
         group_bar(1, NG1);  // covers A1's queues as well
-        if (tid == 64 && blockIdx.x < IVM_TRACE_CTAS) {
+        if (tid == 64 && blockIdx.x < IVM_TRACE_CTAS && trace_on) {
             P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + 7] = sh.t_start;
             P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + 4] = global_timer();
             for (int k = 13; k < 16; ++k) P.cta_trace[(size_t)blockIdx.x * IVM_TRACE_SLOTS + k] = 0ull;
@@ -1396,7 +1405,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     if (geo) {
         OVL_STAMP(10, 0);
         if (!grid_wait_group(P.bar, bar_base + 1u * gridDim.x, &sh.flag, NG) && tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER);
-        if (blockIdx.x == 0 && tid == 0) g->tstamp[1] = global_timer();
+        if (blockIdx.x == 0 && tid == 0) { g->tstamp[1] = global_timer(); OVL_STEPLOG(1) = g->tstamp[1]; }
         OVL_STAMP(0, 0);
 
         // ============================================================ G3: resolve
@@ -1502,6 +1511,9 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                         atomicMin(&sl.box[0], acc.rmin); atomicMax(&sl.box[1], acc.rmax);
                         atomicMin(&sl.box[2], acc.cmin); atomicMax(&sl.box[3], acc.cmax);
                         atomicAdd(&sl.box[4], 1);
+                        // on an edge line of the last scanned world box?  Then this step scans again (IvmGlobal::scan_glob)
+                        const int4 sg = __ldcg(reinterpret_cast<const int4 *>(g->scan_glob));
+                        if (pt.r == sg.x || pt.r == sg.y || pt.c == sg.z || pt.c == sg.w) g->edge_touched = 1u;
                     }
                 }
             }
@@ -1609,12 +1621,12 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         }
         return;
     }
-    if (blockIdx.x == 0 && tid == 0) g->tstamp[2] = global_timer();
+    if (blockIdx.x == 0 && tid == 0) { g->tstamp[2] = global_timer(); OVL_STEPLOG(2) = g->tstamp[2]; }
     OVL_STAMP(5, 0);
     // every resolve of this step is done: the next step's kernel may become resident as CTAs of this one exit (it
     // touches nothing but its own inputs until this kernel has completed)
     if (tid == 0) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    if (warp == 0) ovl_global_bands(P, lane, sh.gband, sh.glob, sh.loc4, &sh.direct);  // before anything of the fix-up can have moved an env box for good
+    if (warp == 0) ovl_global_bands(P, lane, sh.gband, sh.glob, sh.loc4, &sh.direct, &sh.skipscan);  // before anything of the fix-up can have moved an env box for good
     __syncthreads();
 
     // ================================================================ edge fix-up beside the raster
@@ -1658,7 +1670,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             // once; every live record on them looks up the cells that share its key and lists itself if it loses.
             uint8_t *seg_tb = reinterpret_cast<uint8_t *>(dyn + 12 * 1024 + SEGCAP * IVM_SCAN_HDR * 4);  // P.B bytes (<= 4096 here)
             if (warp == 0) {
-                if (P.B <= 4096) ivm_direct_segments(P, sh.glob, seg_hdr, SEGCAP, sh.segcnt, lane, seg_tb);
+                if (sh.skipscan) { if (lane == 0) { sh.segcnt[0] = 0; sh.segcnt[1] = 0; } }
+                else if (P.B <= 4096) ivm_direct_segments(P, sh.glob, seg_hdr, SEGCAP, sh.segcnt, lane, seg_tb);
                 else if (lane == 0) sh.segcnt[0] = -1;
             }
             __syncthreads();
@@ -1706,7 +1719,12 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                 __syncthreads();
                 ivm_fixup_stage2<IvmAtomics>(P, S, tid, blockDim.x, false, (uint32_t)__ldcg(&g->acc_e1), (uint32_t)__ldcg(&g->acc_e2), true);
                 __syncthreads();
-                if (tid == 0) { g->tstamp[3] = global_timer(); g->tstamp[4] = g->tstamp[3]; }
+                if (tid == 0) {
+                    // the edge lines of this world box are collision-free from here on (every class has one survivor)
+                    g->scan_glob[0] = sh.glob[0]; g->scan_glob[1] = sh.glob[1]; g->scan_glob[2] = sh.glob[2]; g->scan_glob[3] = sh.glob[3];
+                    g->scan_B = P.B; g->edge_touched = 0u; g->scan_valid = 1u;
+                    g->tstamp[3] = global_timer(); g->tstamp[4] = g->tstamp[3]; OVL_STEPLOG(3) = g->tstamp[3];
+                }
                 __syncthreads();
             }
         } else {
@@ -1736,7 +1754,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             }
             ivm_fixup_stage2<IvmAtomics>(P, S, tid, blockDim.x);
             __syncthreads();
-            if (tid == 0) { g->tstamp[3] = global_timer(); g->tstamp[4] = g->tstamp[3]; }
+            if (tid == 0) { g->scan_valid = 0u; g->tstamp[3] = global_timer(); g->tstamp[4] = g->tstamp[3]; }
             __syncthreads();
         }
         }
@@ -1805,6 +1823,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     OVL_STAMP(9, 0);
     if (tid == 0) {
         atomicMax(&g->tstamp[5], global_timer());
+        atomicMax(&OVL_STEPLOG(4), global_timer());
         // this CTA is done with the map state: a pipelined successor waits for all of these instead of for the
         // completion of the whole kernel (which is signalled several microseconds after the last CTA has left)
         __threadfence();

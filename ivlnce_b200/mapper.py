@@ -429,11 +429,12 @@ def _as_f32(t: torch.Tensor, device) -> torch.Tensor:
 
 
 class _Hold:
-    __slots__ = ("keepalive", "num_envs", "views_B", "occ_base", "occ_view", "sem_view")
+    __slots__ = ("keepalive", "num_envs", "views_B", "occ_base", "occ_view", "sem_view", "err_host", "err_event", "err_calls")
 
     def __init__(self):
         self.keepalive, self.num_envs, self.views_B = None, 0, -1
         self.occ_base = self.occ_view = self.sem_view = None
+        self.err_host, self.err_event, self.err_calls = None, None, 0   # error polling (MappingModule._poll_errors)
 
 
 class MappingModule(nn.Module):
@@ -479,9 +480,6 @@ class MappingModule(nn.Module):
         assert on_overflow in ("raise", "warn")
         self.error_poll_interval = int(error_poll_interval)
         self.on_overflow = on_overflow
-        self._err_host = None
-        self._err_event = None
-        self._err_calls = 0
         self._warned = False
         self._initial_max_envs = max_envs
         self._hold = _Hold()   # per-call state kept off the nn.Module attribute machinery
@@ -564,22 +562,23 @@ class MappingModule(nn.Module):
                 return self._forward_on_device(eng, B, episodes_info, observations, robot_current_state, hold)
         return self._forward_on_device(eng, B, episodes_info, observations, robot_current_state, hold)
 
-    def _poll_errors(self, eng):
-        ev = self._err_event
+    def _poll_errors(self, eng, hold):
+        # (the counters live in `hold`, a plain object: an attribute store on an nn.Module costs microseconds)
+        ev = hold.err_event
         if ev is not None and ev.query():           # the copy issued a while ago has landed
-            self._err_event = None
-            flags = int(self._err_host[0])
+            hold.err_event = None
+            flags = int(hold.err_host[0])
             if flags:
                 self._raise_flags(eng, flags)
-        self._err_calls += 1
-        if self._err_event is None and self.error_poll_interval > 0 and self._err_calls >= self.error_poll_interval:
-            self._err_calls = 0
-            if self._err_host is None:
-                self._err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-            _lib.check(eng.lib.ivm_copy_error_flags_async(eng.ctx, self._err_host.data_ptr(), eng.stream()), eng.ctx,
+        hold.err_calls += 1
+        if hold.err_event is None and hold.err_calls >= self.error_poll_interval:
+            hold.err_calls = 0
+            if hold.err_host is None:
+                hold.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+            _lib.check(eng.lib.ivm_copy_error_flags_async(eng.ctx, hold.err_host.data_ptr(), eng.stream()), eng.ctx,
                        "ivm_copy_error_flags_async")
-            self._err_event = torch.cuda.Event()
-            self._err_event.record(torch.cuda.current_stream(self.device))
+            hold.err_event = torch.cuda.Event()
+            hold.err_event.record(torch.cuda.current_stream(self.device))
 
     def _raise_flags(self, eng, flags: int):
         overflow = flags & (_lib.ERR_STORE_OVERFLOW | _lib.ERR_KNOWN_OVERFLOW)
@@ -606,7 +605,7 @@ class MappingModule(nn.Module):
 
     def _forward_on_device(self, eng, B, episodes_info, observations, robot_current_state, hold):
         if self.error_poll_interval > 0:
-            self._poll_errors(eng)
+            self._poll_errors(eng, hold)
         T12, cs, pose, orient = self._matrices(robot_current_state)
         hold.keepalive = (T12, cs, pose, orient)
         if self.mode == "iterative":
@@ -624,7 +623,10 @@ class MappingModule(nn.Module):
     def _forward_iterative(self, eng, B, episodes_info, observations, T12, cs, pose, orient):
         H, W = self.camera_parameters.features_spatial_dimensions
         H, W = int(H), int(W)
-        sem_mod = self.compute_semantics
+        # (an nn.Module attribute that is itself a module is found only after a failed normal lookup: ask the dicts)
+        sem_mod = self.__dict__.get("compute_semantics")
+        if sem_mod is None:
+            sem_mod = self._modules.get("compute_semantics")
         scores = None
         if isinstance(sem_mod, PredictSemantics):
             scores = sem_mod.scores(observations)

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 wl = sys.argv[1] if len(sys.argv) > 1 else "pred16"
 cfg = dict(bench.WORKLOADS[wl]); dev = torch.device("cuda:0"); B = cfg["envs"]
-pose, orient, masks = bench.make_poses(cfg, 3000, 1002)
+pose, orient, masks = bench.make_poses(cfg, 8000, 1002)
 depth, sem = bench.make_frames(cfg, dev, 1002)
 pose_d, orient_d, masks_d = (torch.from_numpy(x).to(dev) for x in (pose, orient, masks))
 mm = bench.build_module(cfg, dev, B, 0, os.environ.get("IVM_PIPELINED", "1") != "0")
