@@ -281,8 +281,9 @@ def peak_hbm():
 def traffic_for(workload, kernel):
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        v = tj.get(workload, {}).get(kernel)
-        return v, tj.get("_source", "profiles/traffic.json (ncu --set full capture: dram__bytes_read.sum + dram__bytes_write.sum per launch)")
+        w = tj.get(workload, {})
+        v = w.get(kernel)
+        return v, (w.get("_source") if v is not None else None)   # the capture the figure comes from (per workload)
     except Exception:
         return None, None
 
@@ -616,9 +617,11 @@ def run_known(env, name, cfg, K, Wm, cpu=True, seed=0):
     bytes_frame = 2 * R * R + 16 * p_in
     peak, peak_src = peak_hbm()
     gbs = B * bytes_frame / ((ms / K) * 1e-3) / 1e9
+    ktraffic, ktsrc = traffic_for(name, "raster_known")
     res.update({"steps": K, "ms_per_step": ms / K, "value": B * K / (ms * 1e-3), "gpu_launches": int(launches),
-                "roofline": {"bound": "hbm", "kernel": "k_raster<known>", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                             "frac": gbs / peak, "traffic": None, "peak_source": peak_src, "alg_bytes_per_env_frame": bytes_frame,
+                "roofline": {"bound": "hbm", "kernel": "k_raster_known", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                             "frac": gbs / peak, "traffic": ktraffic, "traffic_source": ktsrc, "peak_source": peak_src,
+                             "alg_bytes_per_env_frame": bytes_frame,
                              "alg_bytes_per_launch": B * bytes_frame, "p_in": p_in,
                              "duration": "CUDA events round the timed region / steps"}})
     if cpu and rank == 0 and env.world == 1:

@@ -487,3 +487,39 @@ def test_step_counter_rebase_keeps_parity():
     b, xyz, sem = cs.world()
     assert np.array_equal(b, scn["ref_world_b"]) and np.array_equal(xyz.view(np.uint32), scn["ref_world_xyz"].view(np.uint32))
     assert np.array_equal(sem, scn["ref_world_sem"])
+
+
+@pytest.mark.parametrize("nenv,mode", [(1, "iid"), (3, "iid"), (2, "scene")])
+def test_edge_scan_skipping_keeps_parity(nenv, mode):
+    """The step kernel scans the edge lines of the world bounding box (where the reference's key quirk merges distinct
+    cells, mapper.py:461-474) only when a collision can have appeared since the last scan.  Long runs in a small
+    area: the box settles, later frames keep landing on its edge lines, envs are reset in mid-run.  Maps and the
+    size of the world cloud after EVERY step, and the final cloud bitwise, against the oracle; and both kinds of
+    steps (scanned / skipped) must have occurred."""
+    from ivlnce_b200.synthetic import ScenarioConfig, make_scenario
+    from oracle.oracle import OracleMapper
+    from scenarios import _wrap
+
+    c = ScenarioConfig(num_envs=nenv, height=64, width=64, steps=90, resolution=0.1, num_labels=13, depth_mode=mode,
+                       roam_radius=1.0, reset_steps={40: [0], 63: [nenv - 1]}, seed=700 + nenv)
+    scn = _wrap(c, make_scenario(c))
+    orc = OracleMapper(c.height, c.width, c.vfov_radians, c.map_meters, c.map_meters, c.resolution)
+    ref_outs, ref_sizes = run_mapper(orc.step, scn, world_fn=orc.world)
+    from cuda_stepper import CudaStepper
+
+    cs = CudaStepper(scn["cfg"], max_envs=nenv, store_cells=1024)
+    scanned = skipped = 0
+    for t in range(c.steps):
+        o, s = cs.step(scn["masks"][t], scn["pose"][t], scn["orientation"][t], depth=scn["depth"][t], labels=scn["labels"][t])
+        assert np.array_equal(o, ref_outs[t][0]) and np.array_equal(s, ref_outs[t][1]), t
+        assert len(cs.world()[0]) == ref_sizes[t], t
+        _, stats = cs.mm.status()
+        if int(stats[7]) >> 32:
+            scanned += 1
+        else:
+            skipped += 1
+    b1, x1, s1 = orc.world()
+    b2, x2, s2 = cs.world()
+    assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(s1, s2)
+    assert scanned > 0 and skipped > 0, (scanned, skipped)
+    cs.mm.check_errors()
