@@ -194,6 +194,7 @@ struct IvmParams {
     unsigned long long *cplane;   // [maxB][SR][SC] frame candidate plane (see above)
     uint32_t cstamp;              // per step: 1..stamp period (see the candidate plane above)
     int32_t pix_bits;             // pb: bits of a pixel index, ceil(log2(HW)) (<= 24)
+    int32_t w_shift;              // log2(W) if W is a power of two, else -1
     IvmEnv *env;                  // [maxB]
     int32_t *rowcount, *colcount; // [maxB][SR], [maxB][SC] live records per store row / col
     IvmGlobal *g;

@@ -1008,6 +1008,7 @@ struct OvlShared {
     int32_t pend[4][32];       // raster: tiles of the group that wait for the edge fix-up
     unsigned long long t_start; // %globaltimer when the CTA became resident
     int32_t qoff[NSLOT + 1];   // prefix of the chunk's queue lengths
+    uint8_t qblk[NSLOT * IVM_O_TILE / 64];  // slot that holds queue entry 64 * j (the flat loops start their slot search there)
     int32_t glob[4], loc4[4];  // world box over the env boxes at grid barrier 2 / frame box of the step
     int32_t direct;            // both boxes allow the direct resolution of the edge collisions
     int32_t skipscan;          // ... and the edge lines are as the last scan left them (IvmGlobal::scan_glob)
@@ -1091,6 +1092,12 @@ __device__ __forceinline__ void ovl_global_bands(const IvmParams &P, int lane, i
         *skipscan = (*direct && __ldcg(&P.g->scan_valid) != 0u && __ldcg(&P.g->scan_B) == P.B && __ldcg(&P.g->edge_touched) == 0u &&
                      sg.x == rmin && sg.y == rmax && sg.z == cmin && sg.w == cmax) ? 1 : 0;
     }
+}
+
+// image row / column of a pixel index (a shift and a mask for the usual power-of-two widths, P.w_shift >= 0)
+__device__ __forceinline__ void ovl_row_col(const IvmParams &P, int pix, int &v, int &u) {
+    if (P.w_shift >= 0) { v = pix >> P.w_shift; u = pix & (P.W - 1); }
+    else { v = pix / P.W; u = pix - v * P.W; }
 }
 
 #define OVL_STEPLOG(k) P.cta_trace[(size_t)(512 + (P.step & 255u)) * IVM_TRACE_SLOTS + (k)]  // per-step log of CTA 0 (rows 512..767)
@@ -1199,7 +1206,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             const int f = f0 + q * NG1 + tid, k = f / F4T, gt = f % F4T;
             OvlSlot &sl = sh.slot[k];
             const int pix0 = sl.tp0 + gt * 4;
-            const int v = pix0 / P.W, u0 = pix0 - v * P.W;
+            int v, u0;
+            ovl_row_col(P, pix0, v, u0);
             const float ysv = P.ys[v];
             const float dd[4] = {dv[q].x, dv[q].y, dv[q].z, dv[q].w};
             bool ok[4];
@@ -1240,7 +1248,19 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             for (int o = 1; o < 32; o <<= 1) { const unsigned y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
             if (lane < cn) sh.qoff[lane + 1] = (int)x;
             if (lane == 0) sh.qoff[0] = 0;
+            __syncwarp();
+            const int totalq = sh.qoff[cn];
+            for (int j = lane; j * 64 < totalq; j += 32) {
+                int k = 0;
+                while (j * 64 >= sh.qoff[k + 1]) ++k;
+                sh.qblk[j] = (uint8_t)k;
+            }
         }
+    };
+    auto slot_of = [&](int e) {  // the slot (tile of the chunk) that holds flat queue entry e
+        int k = (int)sh.qblk[e >> 6];
+        while (e >= sh.qoff[k + 1]) ++k;
+        return k;
     };
     float4 dv[A1B];
     if (tid < NG1) {
@@ -1339,12 +1359,12 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             // A2: one queue entry per thread
 #pragma unroll 2
             for (int e = tid; e < totalq; e += NG1) {
-                int k = 0;
-                while (e >= sh.qoff[k + 1]) ++k;
+                const int k = slot_of(e);
                 const unsigned o = (unsigned)k * IVM_O_TILE + (unsigned)(e - sh.qoff[k]);
                 const OvlSlot &sl = sh.slot[k];
                 const int pix = sl.tp0 + (int)qpix[o];
-                const int v = pix / P.W, u = pix - v * P.W;
+                int v, u;
+                ovl_row_col(P, pix, v, u);
                 float x, y, z;
                 ivm_world_xyz(qd[o], P.xs[u], P.ys[v], sl.T, x, y, z);
                 const float rf = ivm_rint_div(z, P.half_res, P.inv_half_res);
@@ -1368,14 +1388,14 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             // B: ONE 64-bit RED.MAX per queue entry into the candidate plane (its line is in L2 or on its way)
 #pragma unroll 2
             for (int e = tid; e < totalq; e += NG1) {
-                int k = 0;
-                while (e >= sh.qoff[k + 1]) ++k;
+                const int k = slot_of(e);
                 const unsigned o = (unsigned)k * IVM_O_TILE + (unsigned)(e - sh.qoff[k]);
                 const uint32_t cellv = qcell[o];
                 if (cellv == 0xFFFFFFFFu) continue;
                 const OvlSlot &sl = sh.slot[k];
                 const int pix = sl.tp0 + (int)qpix[o];
-                const int v = pix / P.W, u = pix - v * P.W;
+                int v, u;
+                ovl_row_col(P, pix, v, u);
                 const float y = ivm_world_y(qd[o], P.xs[u], P.ys[v], sl.T);
                 unsigned long long *w = &P.cplane[(size_t)sl.b * P.SR * P.SC + (size_t)(cellv >> 16) * P.SC + (size_t)(cellv & 0xFFFFu)];
                 const unsigned long long key = ivm_cand_key(P, y, (uint32_t)pix);
@@ -1427,12 +1447,12 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                 group_bar(1, NG);
                 const int tq = sh.qoff[cn];
                 for (int e = tid; e < tq; e += NG) {
-                    int k = 0;
-                    while (e >= sh.qoff[k + 1]) ++k;
+                    const int k = slot_of(e);
                     const unsigned o = (unsigned)k * IVM_O_TILE + (unsigned)(e - sh.qoff[k]);
                     const OvlSlot &sl = sh.slot[k];
                     const int pix = sl.tp0 + (int)qpix[o];
-                    const int v = pix / P.W, u = pix - v * P.W;
+                    int v, u;
+                    ovl_row_col(P, pix, v, u);
                     float x, y, z;
                     ivm_world_xyz(qd[o], P.xs[u], P.ys[v], sl.T, x, y, z);
                     const float rf = ivm_rint_div(z, P.half_res, P.inv_half_res);
@@ -1459,8 +1479,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                     kk[u] = 0; ce[u] = 0u; px[u] = 0u; lab[u] = 0u; d[u] = 2.0f; cw[u] = 0ull;
                     old[u].x = old[u].y = old[u].z = 0.f; old[u].meta = 0u;
                     if (act[u]) {
-                        int k = 0;
-                        while (e >= sh.qoff[k + 1]) ++k;
+                        const int k = slot_of(e);
                         const unsigned o = (unsigned)k * IVM_O_TILE + (unsigned)(e - sh.qoff[k]);
                         kk[u] = k; ce[u] = qcell[o]; px[u] = qpix[o]; d[u] = qd[o];
                         act[u] = ce[u] != 0xFFFFFFFFu;  // outside the store window: flagged by the scatter
@@ -1479,7 +1498,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                     const int k = kk[u];
                     OvlSlot &sl = sh.slot[k];
                     const uint32_t pix = (uint32_t)sl.tp0 + px[u];
-                    const int v = (int)pix / P.W, uu = (int)pix - v * P.W;
+                    int v, uu;
+                    ovl_row_col(P, (int)pix, v, uu);
                     IvmPoint pt;
                     ivm_world_xyz(d[u], P.xs[uu], P.ys[v], sl.T, pt.x, pt.y, pt.z);
                     if (cw[u] != ivm_cand_key(P, pt.y, pix)) continue;  // another pixel owns the cell
@@ -2244,6 +2264,9 @@ int ivm_create(const ivm_config *cfg, void *workspace_dev, size_t workspace_byte
     P.tile_r = tr; P.tile_c = tc;
     P.debug = cfg->reserved[1];
     P.pix_bits = ivm_pix_bits((long long)cfg->height * cfg->width);
+    P.w_shift = -1;
+    for (int sft = 0; sft < 30; ++sft)
+        if ((1 << sft) == cfg->width) P.w_shift = sft;
     ctx->first_call = 1;
     ctx->num_sms = 148;
     {
