@@ -15,6 +15,8 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <mutex>
+
 #include "../../include/ivln_map.h"
 #include "ivm_core.h"
 
@@ -22,6 +24,7 @@
 #define IVM_RASTER_THREADS 128
 #define IVM_NSTAGES 5
 #define IVM_EVPOOL 64
+#define IVM_MAX_DEVICES 64
 
 // ------------------------------------------------------------------ helpers
 __device__ __forceinline__ int warp_min(int v) { return __reduce_min_sync(0xffffffffu, v); }
@@ -2422,7 +2425,20 @@ static int launch_overlap(ivm_ctx *ctx, IvmParams &P, const float *logits, int n
     if (smem < ovl_stream_bytes(pred != 0)) smem = ovl_stream_bytes(pred != 0);
     const void *fn = pred ? (const void *)k_step_overlap<true> : (const void *)k_step_overlap<false>;
     if (!ctx->ovl_grid[pred] || ctx->ovl_smem[pred] != smem) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // The attribute belongs to the function and the device, not to this context: it only ever grows (a second
+        // context with smaller tiles must not lower it under a context that launches with more).
+        cudaError_t e = cudaSuccess;
+        {
+            static std::mutex mu;
+            static size_t most[2][IVM_MAX_DEVICES];
+            int dev = 0;
+            cudaGetDevice(&dev);
+            std::lock_guard<std::mutex> lock(mu);
+            if (dev < 0 || dev >= IVM_MAX_DEVICES || most[pred][dev] < smem) {
+                e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e == cudaSuccess && dev >= 0 && dev < IVM_MAX_DEVICES) most[pred][dev] = smem;
+            }
+        }
         if (e != cudaSuccess) return cuda_fail(ctx, e, "cudaFuncSetAttribute(k_step_overlap)");
         int per_sm = 0;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, pred ? IVM_O_THREADS_PRED : IVM_O_THREADS_GT, smem);

@@ -668,8 +668,13 @@ class MappingModule(nn.Module):
     def get_map_file(self, env_name: str) -> str:
         return os.path.join(self.maps_location, f"{env_name}.npz")
 
+    KNOWN_CACHE_SCENES = 8   # scene clouds kept resident on the device (least recently used beyond that are re-read from
+                             # disk on their next reset, which is what the reference does on EVERY reset)
+
     def _known_cloud(self, env_name: str):
-        if env_name not in self._known_cache:
+        if env_name in self._known_cache:
+            self._known_cache[env_name] = self._known_cache.pop(env_name)   # most recently used last
+        else:
             with np.load(self.get_map_file(env_name)) as f:  # SemanticPointcloud.from_npz_file, mapper.py:283-294
                 xyz = np.ascontiguousarray(f["xyz"], dtype=np.float32)
                 sem = np.ascontiguousarray(np.asarray(f["semantics"]).astype(np.int64).astype(np.uint8))
@@ -679,8 +684,14 @@ class MappingModule(nn.Module):
                 o_c = int(np.floor(float(xyz[:, 0].min()) / float(hr))) - 2
             else:
                 o_r = o_c = 0
+            cap = self._engine_args["known_capacity"]
+            if xyz.shape[0] > cap:
+                raise _lib.MapLibraryError(f"scene cloud {self.get_map_file(env_name)} holds {xyz.shape[0]} points, more than "
+                                           f"known_capacity = {cap} per env: construct the mapper with a larger known_capacity")
             self._known_cache[env_name] = (torch.from_numpy(xyz).to(self.device), torch.from_numpy(sem).to(self.device),
                                            o_r, o_c)
+            while len(self._known_cache) > max(self.KNOWN_CACHE_SCENES, 1):
+                self._known_cache.pop(next(iter(self._known_cache)))
         return self._known_cache[env_name]
 
     def _forward_known(self, eng, B, episodes_info, cs, pose, orient):

@@ -523,3 +523,59 @@ def test_edge_scan_skipping_keeps_parity(nenv, mode):
     assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(s1, s2)
     assert scanned > 0 and skipped > 0, (scanned, skipped)
     cs.mm.check_errors()
+
+
+def test_two_contexts_with_different_tiles_alternate():
+    """the dynamic shared memory attribute of the step kernel belongs to the function, not to a context.
+    Two live mappers whose raster tiles (hence shared memory sizes) differ step alternately."""
+    scn = load_golden("scene_overlap")
+    from cuda_stepper import CudaStepper
+
+    a = CudaStepper(scn["cfg"], max_envs=int(scn["num_envs"].max()), raster_tile=64)
+    b = CudaStepper(scn["cfg"], max_envs=int(scn["num_envs"].max()), raster_tile=4)
+    T = scn["masks"].shape[0]
+    for t in range(T):
+        B = int(scn["num_envs"][t])
+        args = (scn["masks"][t, :B], scn["pose"][t, :B], scn["orientation"][t, :B])
+        kw = dict(depth=scn["depth"][t, :B], labels=scn["labels"][t, :B])
+        oa, sa = a.step(*args, **kw)
+        ob, sb = b.step(*args, **kw)
+        assert np.array_equal(oa, ob) and np.array_equal(sa, sb), t
+        assert np.array_equal(oa, scn["ref_occupancy"][t, :B]) and np.array_equal(sa, scn["ref_semantic"][t, :B]), t
+    a.mm.check_errors(); b.mm.check_errors()
+
+
+def test_known_cloud_cache_is_bounded_and_capacity_error_is_clear(tmp_path):
+    """scene clouds are kept on the device for a bounded number of scenes (re-read from disk beyond that), and a
+    cloud larger than known_capacity raises a message that says so."""
+    from ivlnce_b200 import _lib
+    from ivlnce_b200.mapper import EpisodesInfo, MapDimensions, Observations, RobotCurrentState, create_known_mapper
+
+    rng = np.random.default_rng(5)
+    dev = torch.device("cuda:0")
+    names = [f"scene{i}" for i in range(4)]
+    for i, n in enumerate(names):
+        k = 2500 + 400 * i
+        xyz = (rng.random((k, 3), dtype=np.float32) * np.array([8, 1.5, 8], np.float32)).astype(np.float32)
+        np.savez(tmp_path / f"{n}.npz", xyz=xyz, semantics=rng.integers(0, 13, k))
+    np.savez(tmp_path / "huge.npz", xyz=rng.random((5000, 3), dtype=np.float32), semantics=np.zeros(5000, np.int64))
+    md = MapDimensions(6.4, 6.4, 0.1)
+    mm = create_known_mapper(dev, md, str(tmp_path), known_capacity=4096, store_cells=1024)
+    mm.KNOWN_CACHE_SCENES = 2
+    pose = torch.tensor([[4.0, 0.5, 4.0]], device=dev)
+    ori = torch.zeros(1, 2, dtype=torch.float64, device=dev)
+    outs = {}
+    for rnd in range(2):                                   # second round: every scene but the last two is re-read from disk
+        for n in names:
+            ei = EpisodesInfo(torch.zeros(1, 1, dtype=torch.uint8, device=dev), [n])
+            o = mm(ei, Observations(None, None, None), RobotCurrentState(pose, ori[:, 0], ori[:, 1]))
+            occ = o.occupancy.cpu().numpy().copy()
+            assert len(mm._known_cache) <= 2
+            if rnd == 0:
+                outs[n] = occ
+                assert occ.any()
+            else:
+                assert np.array_equal(occ, outs[n]), n
+    with pytest.raises(_lib.MapLibraryError, match="known_capacity"):
+        ei = EpisodesInfo(torch.zeros(1, 1, dtype=torch.uint8, device=dev), ["huge"])
+        mm(ei, Observations(None, None, None), RobotCurrentState(pose, ori[:, 0], ori[:, 1]))
