@@ -35,17 +35,47 @@ DEFAULT_KNOWN_CAPACITY = 1 << 22  # points per env in known-map mode
 
 # ----------------------------------------------------------------------------
 # Interface dataclasses (reference mapper.py:61-138, 195-200, 336-340)
-@dataclass
 class EpisodesInfo:
-    """reference mapper.py:61-86: `not_done_masks` [B,1]; 0 = episode (or tour) finished."""
-    not_done_masks: torch.Tensor
-    env_names: Sequence[str]
-    EPISODE_FINISHED: int = field(default=0, init=False)
-    EPISODE_UNFINISHED: int = field(default=1, init=False)
+    """reference mapper.py:61-86: `not_done_masks` [B,1]; 0 = episode (or tour) finished.
 
-    def __post_init__(self):
-        self.env_names = np.asarray(self.env_names)
-        self.not_done_masks = self.not_done_masks.squeeze(1)
+    Same constructor, attributes and methods as the reference's dataclass.  The two conversions of its
+    `__post_init__` (`np.asarray(env_names)`, `not_done_masks.squeeze(1)`) are made on first use: the map update reads
+    the masks straight from the caller's tensor and compares the names as the sequence they came in."""
+
+    EPISODE_FINISHED = 0
+    EPISODE_UNFINISHED = 1
+    __slots__ = ("_masks_raw", "_masks", "_names_raw", "_names")
+
+    def __init__(self, not_done_masks: torch.Tensor, env_names: Sequence[str]):
+        self._masks_raw, self._masks = not_done_masks, None
+        self._names_raw, self._names = env_names, None
+
+    @property
+    def not_done_masks(self) -> torch.Tensor:
+        if self._masks is None:
+            self._masks = self._masks_raw.squeeze(1)
+        return self._masks
+
+    @not_done_masks.setter
+    def not_done_masks(self, value: torch.Tensor):
+        self._masks_raw = self._masks = value
+
+    @property
+    def env_names(self) -> np.ndarray:
+        if self._names is None:
+            self._names = np.asarray(self._names_raw)
+        return self._names
+
+    @env_names.setter
+    def env_names(self, value):
+        self._names_raw, self._names = value, None
+
+    def __repr__(self):
+        return f"EpisodesInfo(not_done_masks={self.not_done_masks!r}, env_names={self.env_names!r})"
+
+    def __eq__(self, other):
+        return (isinstance(other, EpisodesInfo) and torch.equal(self.not_done_masks, other.not_done_masks)
+                and np.array_equal(self.env_names, other.env_names))
 
     @property
     def indices(self) -> torch.Tensor:  # built on demand: the hot path never needs it
@@ -62,7 +92,15 @@ class EpisodesInfo:
 
     @property
     def num_envs(self) -> int:
-        return len(self.not_done_masks)
+        return self._masks_raw.shape[0]
+
+    def masks_flat(self) -> torch.Tensor:
+        """The masks as the kernels read them, [B] elements in memory: the caller's [B,1] tensor itself when it is
+        contiguous (no torch op), else the squeezed view."""
+        raw = self._masks_raw
+        if raw.dim() == 2 and raw.shape[1] == 1 and raw.stride(0) == 1:
+            return raw
+        return self.not_done_masks
 
 
 @dataclass
@@ -380,9 +418,11 @@ class _MapEngine:
             # both output maps in one block, so that a full batch leaves for the host in a single copy (staging.MapEgress)
             self.maps = torch.zeros((2, max_envs, R, C), dtype=torch.uint8, device=self.device)
             self.occ, self.sem = self.maps[0], self.maps[1]
+            self.occ_ptr, self.sem_ptr, self.labels_out_ptr = self.occ.data_ptr(), self.sem.data_ptr(), None
             if self.mode == "iterative":
                 H, W = self.camera.features_spatial_dimensions
                 self.labels_out = torch.zeros((max_envs, int(H), int(W)), dtype=torch.uint8, device=self.device)
+                self.labels_out_ptr = self.labels_out.data_ptr()
 
     def ensure_capacity(self, num_envs: int) -> bool:
         """True if a new context was created (its per-context switches have to be set again)."""
@@ -487,6 +527,8 @@ class MappingModule(nn.Module):
         self._known_order: List[int] = []   # env indices in load order (world-cloud order in known mode)
         self._known_loaded: Dict[int, str] = {}
         self._known_names = None    # env_names of the last call if every env holds the scene it is in
+        self._known_names_raw = None   # ... as the list the caller passed (a copy), for the cheap comparison
+        self._known_B = -1
 
     @property
     def _num_envs(self) -> int:
@@ -630,13 +672,16 @@ class MappingModule(nn.Module):
         scores = None
         if isinstance(sem_mod, PredictSemantics):
             scores = sem_mod.scores(observations)
+        elif type(sem_mod) is GTSemantics:      # (its forward, without the nn.Module call machinery)
+            if observations.semantics is None:
+                raise Exception("Semantic Sensor not in use")
         elif sem_mod is not None:
             observations = sem_mod(observations)
         depth = observations.depth_normalized
         assert depth.shape[2] == H  # projector/point_cloud.py:68-69
         assert depth.shape[3] == W
         depth = _as_f32(depth, self.device)
-        masks = _as_u8_masks(episodes_info.not_done_masks, self.device)
+        masks = _as_u8_masks(episodes_info.masks_flat(), self.device)
         labels_ptr, logits_ptr, ncls = None, None, 0
         if scores is not None:
             scores = _as_f32(scores, self.device)
@@ -653,11 +698,11 @@ class MappingModule(nn.Module):
                 labels = labels.contiguous()
             assert labels.numel() == B * H * W
             labels_ptr = labels.data_ptr()
-        args = (eng.ctx, B, depth.data_ptr(), labels_ptr, logits_ptr, ncls, eng.labels_out.data_ptr(),
+        args = (eng.ctx, B, depth.data_ptr(), labels_ptr, logits_ptr, ncls, eng.labels_out_ptr,
                 None if T12 is None else T12.data_ptr(), pose.data_ptr(), None if cs is None else cs.data_ptr(),
                 None if orient is None else orient.data_ptr(),
                 1 if (orient is not None and orient.dtype == torch.float64) else 0,
-                masks.data_ptr(), eng.occ.data_ptr(), eng.sem.data_ptr(), eng.stream())
+                masks.data_ptr(), eng.occ_ptr, eng.sem_ptr, eng.stream())
         rc = eng.lib.ivm_step_iterative(*args)
         if rc == 4:  # 2^24 - 1 steps: rebase the stamps and retry once
             _lib.check(eng.lib.ivm_rebase_stamps(eng.ctx, eng.stream()), eng.ctx, "ivm_rebase_stamps")
@@ -703,11 +748,15 @@ class MappingModule(nn.Module):
         # Which envs reload their scene cloud (mask == 0, mapper.py:873-878)?  A reload of the scene an env already
         # holds changes nothing, so the masks matter only where the scene differs from the loaded one (or nothing is
         # loaded yet): only then are they read -- a device sync if they live on the device; never in steady state.
-        env_names = episodes_info.env_names
+        raw = episodes_info._names_raw
         last = self._known_names
-        if last is not None and last.shape == env_names.shape and bool((last == env_names).all()):
-            finished = []          # every env still holds the scene it is in (one vectorised comparison)
+        if last is not None and self._known_B == B and (type(raw) is list and raw == self._known_names_raw):
+            finished = []          # every env still holds the scene it is in (the same list, or an equal one)
+        elif last is not None and last.shape == episodes_info.env_names.shape and bool((last == episodes_info.env_names).all()):
+            finished = []          # ... (one vectorised comparison)
+            self._known_names_raw, self._known_B = (list(raw) if type(raw) is list else None), B
         else:
+            env_names = episodes_info.env_names
             names = [str(n) for n in env_names[:B]]
             m = episodes_info.not_done_masks
             finished = [b for b in (m == episodes_info.EPISODE_FINISHED).nonzero().flatten().tolist()
@@ -722,12 +771,14 @@ class MappingModule(nn.Module):
             self._known_order.append(b)
             self._known_loaded[b] = name
         if finished or self._known_names is None:
+            env_names = episodes_info.env_names
             ok = all(self._known_loaded.get(b) == str(env_names[b]) for b in range(B))
             self._known_names = np.array(env_names[:B], copy=True) if ok else None
+            self._known_names_raw, self._known_B = (list(raw) if (ok and type(raw) is list) else None), B
         _lib.check(lib.ivm_step_known(eng.ctx, B, pose.data_ptr(), None if cs is None else cs.data_ptr(),
                                       None if orient is None else orient.data_ptr(),
                                       1 if (orient is not None and orient.dtype == torch.float64) else 0,
-                                      eng.occ.data_ptr(), eng.sem.data_ptr(), st), eng.ctx, "ivm_step_known")
+                                      eng.occ_ptr, eng.sem_ptr, st), eng.ctx, "ivm_step_known")
 
     # -- inspection
     def get_world_semantic_pointcloud(self) -> SemanticPointcloud:
