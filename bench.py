@@ -368,8 +368,17 @@ def run_iterative(env, name, cfg, K, Wm, headline=False, e2e=False, cpu_steps=0,
     names = [f"scene{rank}_{b}" for b in range(B)]
     mm = build_module(cfg, dev, B, args.variant, pipelined)
 
+    # per-step views of the resident inputs, made once (the timed call is the module call with its three argument objects)
+    from ivlnce_b200.mapper import EpisodesInfo, Observations, RobotCurrentState
+
+    masks_v = list(masks_d.unsqueeze(-1).unbind(0))
+    pose_v, elev_v, head_v = list(pose_d.unbind(0)), list(orient_d[:, :, 0].unbind(0)), list(orient_d[:, :, 1].unbind(0))
+    depth_v, sem_v = list(depth.unbind(0)), list(sem.unbind(0))
+    is_pred = bool(cfg["pred"])
+
     def step(t):
-        return call_module(mm, cfg, names, masks_d[t], pose_d[t], orient_d[t], depth[t % nd], sem[t % RING])
+        obs = Observations(None, depth_v[t % nd], sem_v[t % RING]) if is_pred else Observations(sem_v[t % RING], depth_v[t % nd], None)
+        return mm(EpisodesInfo(masks_v[t], names), obs, RobotCurrentState(pose_v[t], elev_v[t], head_v[t]))
 
     # ---- parity: the CUDA path against the C oracle on the first steps of these very inputs (t = 0 resets every env)
     if parity_steps > 0:
@@ -574,9 +583,13 @@ def run_known(env, name, cfg, K, Wm, cpu=True, seed=0):
     md = MapDimensions(cfg["map_m"], cfg["map_m"], cfg["res"])
     mm = create_known_mapper(dev, md, tmp.name, store_cells=cfg["store"], known_capacity=cfg["points"] + 1024, max_envs=B)
 
+    # per-step views of the resident inputs, made once (the timed call is the module call with its three argument objects)
+    masks_v = [masks_h[t].view(-1, 1) for t in range(n_walk)]
+    pose_v, elev_v, head_v = list(pose_d.unbind(0)), list(orient_d[:, :, 0].unbind(0)), list(orient_d[:, :, 1].unbind(0))
+    no_obs = Observations(None, None, None)
+
     def step(t):
-        return mm(EpisodesInfo(masks_h[t].view(-1, 1), names), Observations(None, None, None),
-                  RobotCurrentState(pose_d[t], orient_d[t, :, 0], orient_d[t, :, 1]))
+        return mm(EpisodesInfo(masks_v[t], names), no_obs, RobotCurrentState(pose_v[t], elev_v[t], head_v[t]))
 
     t0 = time.perf_counter()
     out = step(0)
