@@ -266,3 +266,53 @@ class MapEgress:
                 if k in observations[i]:
                     del observations[i][k]
         return observations
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Episode records of the collection trainers ("keep the msgpack layout").
+# reference `iterative_collection_dagger_trainer.py:60-80` (`save_episode_to_disk`; `dagger_trainer.py:258-270` reads it
+# back): an episode = [ {sensor: array [T, ...]}, prev_actions i64 [T], oracle_actions i64 [T] ], written as
+# `msgpack_numpy.packb(..., use_bin_type=True)`.  msgpack-numpy (0.4.x, not installed here) encodes an ndarray as the map
+# {b"nd": True, b"type": dtype.str, b"kind": b"", b"shape": shape, b"data": raw bytes}; the two functions below write
+# and read exactly that with plain msgpack, so records are interchangeable with the reference's LMDB files.
+def _encode_ndarray(obj):
+    if isinstance(obj, np.ndarray):
+        if obj.dtype.kind in "VO":
+            raise TypeError(f"cannot pack arrays of dtype {obj.dtype}")
+        return {b"nd": True, b"type": obj.dtype.str, b"kind": b"", b"shape": obj.shape, b"data": obj.tobytes()}
+    if isinstance(obj, (np.bool_, np.number)):
+        return {b"nd": False, b"type": obj.dtype.str, b"data": obj.tobytes()}
+    raise TypeError(f"cannot pack {type(obj)}")
+
+
+def _decode_ndarray(obj):
+    if b"nd" in obj:
+        if obj[b"nd"] is True:
+            return np.frombuffer(obj[b"data"], dtype=np.dtype(obj[b"type"])).reshape(obj[b"shape"])
+        return np.frombuffer(obj[b"data"], dtype=np.dtype(obj[b"type"]))[0]
+    return obj
+
+
+def pack_episode(episode: Sequence[Tuple[Dict, int, int]], expert_uuid: Optional[str] = None, lmdb_fp16: bool = False) -> bytes:
+    """`save_episode_to_disk` without the LMDB transaction: `episode` = [(observation dict, prev_action, oracle_action)]
+    per step (observations as `MapEgress.add_map_to_observations` leaves them); returns the value the reference stores
+    under `str(lmdb_idx).encode()`."""
+    import msgpack
+
+    traj_obs = batch_obs([step[0] for step in episode], device=torch.device("cpu"))
+    if expert_uuid is not None:
+        del traj_obs[expert_uuid]
+    for k, v in traj_obs.items():
+        traj_obs[k] = v.numpy()
+        if lmdb_fp16:
+            traj_obs[k] = traj_obs[k].astype(np.float16)
+    transposed_ep = [traj_obs, np.array([step[1] for step in episode], dtype=np.int64),
+                     np.array([step[2] for step in episode], dtype=np.int64)]
+    return msgpack.packb(transposed_ep, default=_encode_ndarray, use_bin_type=True)
+
+
+def unpack_episode(record: bytes):
+    """`msgpack_numpy.unpackb(record, raw=False)` (dagger_trainer.py:258-270): [obs dict of arrays, prev_actions, oracle_actions]."""
+    import msgpack
+
+    return msgpack.unpackb(record, object_hook=_decode_ndarray, raw=False, strict_map_key=False)

@@ -145,3 +145,40 @@ def test_map_egress_device_through_plugin():
             assert np.array_equal(x["occupancy_map"], y["occupancy_map"]) and np.array_equal(x["semantic_map"], y["semantic_map"])
             assert "env_name" not in x
     assert egress.d2h_bytes == 2 * 3 * 64 * 64
+
+
+def test_episode_record_keeps_the_msgpack_layout():
+    """f-3: an episode packed here is what the reference's `save_episode_to_disk` stores
+    (iterative_collection_dagger_trainer.py:60-80): msgpack-numpy's ndarray maps inside [obs, prev_actions, oracle_actions]."""
+    import msgpack
+
+    from ivlnce_b200.staging import pack_episode, unpack_episode
+
+    rng = np.random.default_rng(3)
+    T = 5
+    episode = []
+    for t in range(T):
+        obs = {"rgb": rng.integers(0, 255, (4, 4, 3), dtype=np.uint8), "depth": rng.random((4, 4, 1), dtype=np.float32),
+               "occupancy_map": rng.integers(0, 2, (8, 8), dtype=np.uint8), "semantic_map": rng.integers(0, 13, (8, 8), dtype=np.uint8),
+               "expert": np.array([t % 4], dtype=np.int64)}
+        episode.append((obs, t % 4, (t + 1) % 4))
+    rec = pack_episode(episode, expert_uuid="expert")
+    raw = msgpack.unpackb(rec, raw=True, strict_map_key=False)            # the wire layout, without the numpy hook
+    assert isinstance(raw, list) and len(raw) == 3
+    assert set(raw[0].keys()) == {b"rgb", b"depth", b"occupancy_map", b"semantic_map"}
+    m = raw[0][b"occupancy_map"]
+    assert m[b"nd"] is True and m[b"type"] == b"|u1" and m[b"kind"] == b"" and list(m[b"shape"]) == [T, 8, 8] and len(m[b"data"]) == T * 64
+    assert raw[1][b"type"] == b"<i8" and list(raw[1][b"shape"]) == [T]
+    obs, prev, oracle = unpack_episode(rec)
+    for k in ("rgb", "depth", "occupancy_map", "semantic_map"):
+        want = np.stack([np.asarray(step[0][k].cpu()) if hasattr(step[0][k], "cpu") else step[0][k] for step in episode])
+        assert obs[k].dtype == want.dtype and np.array_equal(obs[k], want), k
+    assert np.array_equal(prev, np.arange(T) % 4) and np.array_equal(oracle, (np.arange(T) + 1) % 4)
+    half = unpack_episode(pack_episode(episode, expert_uuid="expert", lmdb_fp16=True))
+    assert half[0]["depth"].dtype == np.float16 and half[0]["occupancy_map"].dtype == np.float16   # (the reference casts every key)
+    try:
+        import msgpack_numpy
+    except ImportError:
+        return
+    ref = msgpack_numpy.unpackb(rec, raw=False)
+    assert np.array_equal(ref[0]["semantic_map"], obs["semantic_map"])
