@@ -579,3 +579,37 @@ def test_known_cloud_cache_is_bounded_and_capacity_error_is_clear(tmp_path):
     with pytest.raises(_lib.MapLibraryError, match="known_capacity"):
         ei = EpisodesInfo(torch.zeros(1, 1, dtype=torch.uint8, device=dev), ["huge"])
         mm(ei, Observations(None, None, None), RobotCurrentState(pose, ori[:, 0], ori[:, 1]))
+
+
+def test_long_tour_against_oracle():
+    """BASELINE config 3 at length: ONE env, one reset at the start, 800 steps of a walk within 5 m (128x128 depth,
+    0.05 m cells, 2048^2 half-cell store, ~0.6 M world records at the end).  Maps against the oracle every 25th step (and
+    the last 10), the size of the world cloud at those steps, the final cloud bitwise.  Exercises what only long runs
+    reach: a settled world box with the edge-line scan skipped for hundreds of steps, re-scans when the box moves, a
+    store that keeps filling."""
+    from ivlnce_b200.synthetic import ScenarioConfig, make_scenario
+    from oracle.oracle import OracleMapper
+    from scenarios import _wrap
+    from cuda_stepper import CudaStepper
+
+    c = ScenarioConfig(num_envs=1, height=128, width=128, steps=800, resolution=0.05, num_labels=27, depth_mode="iid",
+                       roam_radius=5.0, seed=311)
+    scn = _wrap(c, make_scenario(c))
+    assert int((scn["masks"] == 0).sum()) == 1
+    orc = OracleMapper(c.height, c.width, c.vfov_radians, c.map_meters, c.map_meters, c.resolution)
+    cs = CudaStepper(scn["cfg"], max_envs=1, store_cells=2048)
+    checked = 0
+    for t in range(c.steps):
+        args = (scn["masks"][t], scn["pose"][t], scn["orientation"][t])
+        kw = dict(depth=scn["depth"][t], labels=scn["labels"][t])
+        o_ref, s_ref = orc.step(*args, **kw)
+        o, s = cs.step(*args, **kw)
+        if t % 25 == 0 or t >= c.steps - 10:
+            assert np.array_equal(o, o_ref) and np.array_equal(s, s_ref), t
+            assert len(cs.world()[0]) == len(orc.world()[0]), t
+            checked += 1
+    b1, x1, s1 = orc.world()
+    b2, x2, s2 = cs.world()
+    assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(s1, s2)
+    assert checked >= 40 and len(b1) > 50_000
+    cs.mm.check_errors()
