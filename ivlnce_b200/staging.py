@@ -75,7 +75,7 @@ class ObservationStager:
         self.h2d_bytes = 0   # bytes of the last call (what bench.py reports)
         self._threads = None
 
-    PARALLEL_ROW_BYTES = 1 << 20
+    PARALLEL_SENSOR_BYTES = int(__import__("os").environ.get("IVM_STAGE_PAR", 1 << 20))
 
     def _pool(self):
         if self._threads is None:
@@ -142,9 +142,18 @@ class ObservationStager:
                 if a.shape != first.shape or a.dtype != first.dtype:
                     raise RuntimeError(f"stack expects each tensor to be equal size, but got {tuple(first.shape)} at entry 0 "
                                        f"and {tuple(a.shape)} at entry {i}")
-            if first.nbytes >= self.PARALLEL_ROW_BYTES and B > 1:
-                # large rows (score planes, RGB): the per-env copies run on a few threads (numpy releases the GIL)
-                list(self._pool().map(lambda ia: slab.view.__setitem__((ia[0], Ellipsis), ia[1]), enumerate(arrays)))
+            if first.nbytes * B >= self.PARALLEL_SENSOR_BYTES and B > 1:
+                # a sensor of a megabyte or more per step (depth, labels, RGB, score planes): the per-env copies run on a
+                # few threads, a contiguous group of envs each (numpy releases the GIL while it copies)
+                pool, view = self._pool(), slab.view
+                groups = min(pool._max_workers, B)
+                bounds = [(g * B // groups, (g + 1) * B // groups) for g in range(groups)]
+
+                def copy_rows(lo_hi, view=view, arrays=arrays):
+                    for i in range(lo_hi[0], lo_hi[1]):
+                        view[i, ...] = arrays[i]
+
+                list(pool.map(copy_rows, bounds))
             else:
                 for i, a in enumerate(arrays):
                     slab.view[i, ...] = a
