@@ -512,6 +512,7 @@ __device__ __forceinline__ void group_bar(int bar_id, int nthr) {
         case 2: asm volatile("bar.sync 2, %0;" ::"r"(nthr) : "memory"); break;
         case 3: asm volatile("bar.sync 3, %0;" ::"r"(nthr) : "memory"); break;
         case 4: asm volatile("bar.sync 4, %0;" ::"r"(nthr) : "memory"); break;
+        case 6: asm volatile("bar.sync 6, %0;" ::"r"(nthr) : "memory"); break;
         default: asm volatile("bar.sync 5, %0;" ::"r"(nthr) : "memory"); break;
     }
 }
@@ -972,7 +973,7 @@ __device__ __forceinline__ bool grid_barrier(uint32_t *bar, uint32_t target, int
 //        fixes the bounding-box edge collisions while every other CTA already rasters the ego tiles the fix-up
 //        cannot touch; 128-thread groups (3 per CTA with PRED, 2 with GT), one ego tile each at a time, tiles
 //        handed out dynamically.
-#define IVM_O_THREADS_GT 288    // GT labels: 8 geometry warps (+1 idle)
+#define IVM_O_THREADS_GT 288    // GT labels: 8 geometry warps + a ninth that joins the resolve
 #define IVM_O_THREADS_PRED 416  // score stream: 8 geometry warps + 4 argmax warps + 1 producer warp
 #define IVM_O_RGROUPS_PRED 3    // raster groups of 128 threads per CTA
 #define IVM_O_RGROUPS_GT 2
@@ -1046,7 +1047,7 @@ __device__ __noinline__ bool ovl_frame_edge_loses(const IvmParams &P, int b, int
 }
 
 // wait of a thread GROUP (named barrier 1, nthr threads, leader = thread 0) on the grid barrier
-__device__ __forceinline__ bool grid_wait_group(uint32_t *bar, uint32_t target, int *s_flag, int nthr) {
+__device__ __forceinline__ bool grid_wait_group(uint32_t *bar, uint32_t target, int *s_flag, int nthr, int bar_id) {
     if (threadIdx.x == 0) {
         int ok = 1;
         uint32_t spins = 0;
@@ -1060,7 +1061,7 @@ __device__ __forceinline__ bool grid_wait_group(uint32_t *bar, uint32_t target, 
         __threadfence();
         *s_flag = ok;
     }
-    group_bar(1, nthr);
+    group_bar(bar_id, nthr);
     return *s_flag != 0;
 }
 
@@ -1116,7 +1117,9 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                int nenv_total, uint32_t bar_base, int max_rows, int raster_group_bytes, int stage_cap, int team, uint32_t team_base,
                int pipelined, uint32_t done_target) {
     constexpr int NG1 = 256;                               // G1 (depth scatter): warps 0..7 in both modes
-    constexpr int NG = 256;                                // G3 (resolve) threads: warps 0..7
+    constexpr int NG = PRED ? 256 : IVM_O_THREADS_GT;      // G3 (resolve) threads: warps 0..7, and the ninth warp of the GT
+                                                           // layout (idle in G1: one more warp makes most CTAs' queues ONE round)
+    constexpr int GB3 = PRED ? 1 : 6;                      // named barrier of the G3 group (the GT group is not the G1 group)
     constexpr int RG = PRED ? IVM_O_RGROUPS_PRED : IVM_O_RGROUPS_GT;  // raster groups per CTA
     constexpr int NGW = NG / 32;
     constexpr int NSLOT = PRED ? IVM_O_SLOTS_PRED : IVM_O_SLOTS_GT;
@@ -1427,7 +1430,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     }
     if (geo) {
         OVL_STAMP(10, 0);
-        if (!grid_wait_group(P.bar, bar_base + 1u * gridDim.x, &sh.flag, NG) && tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER);
+        if (!grid_wait_group(P.bar, bar_base + 1u * gridDim.x, &sh.flag, NG, GB3) && tid == 0) atomicOr(&g->err, IVM_ERR_GRID_BARRIER);
         if (blockIdx.x == 0 && tid == 0) { g->tstamp[1] = global_timer(); OVL_STEPLOG(1) = g->tstamp[1]; }
         OVL_STAMP(0, 0);
 
@@ -1440,14 +1443,16 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             const int cn = min(nslot, my_tiles - c0);
             if (!keep_queue) {
                 // more tiles than slots: rebuild this chunk's slots (from the published env state) and queues
-                group_bar(1, NG);
-                prep_inputs(c0, cn);
-                prep_state(c0, cn, true);
-                group_bar(1, NG);
-                a1_rest(c0, cn, 0, dv);
-                group_bar(1, NG);
+                group_bar(GB3, NG);
+                if (tid < NG1) {  // (these are written for the G1 group)
+                    prep_inputs(c0, cn);
+                    prep_state(c0, cn, true);
+                }
+                group_bar(GB3, NG);
+                if (tid < NG1) a1_rest(c0, cn, 0, dv);
+                group_bar(GB3, NG);
                 queue_prefix(cn);
-                group_bar(1, NG);
+                group_bar(GB3, NG);
                 const int tq = sh.qoff[cn];
                 for (int e = tid; e < tq; e += NG) {
                     const int k = slot_of(e);
@@ -1464,7 +1469,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                     const int32_t rr = (rep ? (int32_t)rf : 0) - sl.origin_r, cc = (rep ? (int32_t)cf : 0) - sl.origin_c;
                     qcell[o] = (rep && rr >= 0 && rr < P.SR && cc >= 0 && cc < P.SC) ? (((uint32_t)rr << 16) | (uint32_t)cc) : 0xFFFFFFFFu;
                 }
-                group_bar(1, NG);
+                group_bar(GB3, NG);
             }
             const int totalq = sh.qoff[cn];
             for (int e0 = 0; e0 < totalq; e0 += E3 * NG) {
@@ -1548,7 +1553,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
                 if (lane == 0)
                     for (int k = 0; k < cn; ++k) mbar_arrive(&sh.lab_empty[k]);
             }
-            group_bar(1, NG);
+            group_bar(GB3, NG);
             if (tid < cn && sh.slot[tid].box[4] > 0) {
                 IvmBoxAcc t;
                 const OvlSlot &sl = sh.slot[tid];
@@ -1561,7 +1566,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         const unsigned we = warp_sum(nedge1);
         if (we && lane == 0) atomicAdd(&g->acc_e1, (unsigned long long)we);
         OVL_STAMP(3, 0);
-        group_bar(1, NG);
+        group_bar(GB3, NG);
         if (tid == 0) grid_arrive(P.bar);  // barrier 2
     } else if (PRED && warp < NGW + NCW) {
         // ============================================================ argmax warps: PredictSemantics tail
