@@ -1,8 +1,9 @@
 // ivm_kernels.cu -- sm_100a kernels + C ABI of the semantic-map update.
 //
-// One step (iterative mode) on the caller's stream is ONE cooperative launch of the persistent kernel
-// k_step_overlap (see its header below) whenever the image tiles evenly and the inputs are aligned.  Otherwise
-// the same phases run as four kernels:
+// One step (iterative mode) on the caller's stream is ONE launch of the persistent kernel k_step_overlap (see its
+// header below; all CTAs co-resident, grid barriers between the phases, programmatically serialised behind the
+// previous step) whenever the image tiles evenly and the inputs are aligned.  Otherwise the same phases run as
+// four kernels:
 //   K1 k_ingest_scatter  per-env O(1) reset / store re-centring / pose matrices (mapper.py:310-326, 127-138), then
 //      (_bulk)           [argmax ->] unproject -> transform -> filter -> half-cell ->
 //                        64-bit atomicMax into the frame-candidate plane   (mapper.py:381-474, core.py:117-230)
@@ -918,7 +919,7 @@ __device__ __forceinline__ unsigned long long global_timer() {
     return t;
 }
 
-// Grid barrier over the co-resident CTAs of a cooperative launch, split into ARRIVE and WAIT so
+// Grid barrier over the co-resident CTAs of one launch (the host sizes the grid by occupancy), split into ARRIVE and WAIT so
 // that independent work can sit between the two.  `target` = arrivals expected on the monotone
 // counter.  grid_wait returns false on time-out (never observed; guards against a hang).
 // grid_arrive: called by ONE thread after a CTA-level barrier that covers the writes to publish.
@@ -952,27 +953,28 @@ __device__ __forceinline__ bool grid_barrier(uint32_t *bar, uint32_t target, int
 }
 
 // ------------------------------------------------------------------ persistent step kernel
-// The whole map update as ONE cooperative launch of co-resident CTAs.  With a class-score stream (PRED): 2 CTAs
-// per SM of 13 warps (8 geometry + 4 argmax + 1 producer); with GT labels: 3 CTAs per SM of 9 warps (8 geometry).
-// CTA t owns the 512-pixel tiles t, t + grid, ... (valid pixels cluster in a few image rows, so tiles are dealt
-// round-robin).  The score stream does not sit between the depth scatter and the resolve: it runs beside them on
-// its own warps from the first cycle, so that the only thing left after the last score plane has arrived is the
-// merge of the last tile's winners.
-//   G1 scatter (warps 0..7 as two groups of four; the groups take alternate tiles, 4 pixels per thread):
-//        depth -> world point -> filters -> half-cell; pass A prefetches the candidate word and the world record
-//        of every valid pixel into L2 and queues the pixel per tile in shared memory; pass B issues ONE 64-bit
-//        RED.MAX per valid pixel into the candidate plane.  -> grid barrier 1
-//   G3 resolve (warps 0..7), per tile: candidate word + world record + depth of the queued pixels are loaded,
-//        THEN the tile's labels are awaited (mbarrier) and the winners merge into the world store.
-//        -> grid barrier 2
+// The whole map update as ONE launch of co-resident CTAs.  With a class-score stream (PRED): 2 CTAs per SM of 13
+// warps (8 geometry + 4 argmax + 1 producer); with GT labels: 3 CTAs per SM of 9 warps (8 geometry + 1 that joins the
+// resolve).  CTA t owns the 512-pixel tiles t, t + grid, ... (valid pixels cluster in a few image rows, so tiles are
+// dealt round-robin) and holds the queues of up to NSLOT of them (a chunk) in shared memory.  The score stream runs
+// beside the geometry phases on its own warps from the first cycle.
+//   A1 depth filter (warps 0..7): every pixel of the chunk -- depth -> height of the world point -> strict depth /
+//        height filters; survivors compacted into the tile's queue as (pixel, depth).  Reads INPUTS only, so with
+//        pipelined stepping it runs before the dependency wait on the previous step (a counter of finished CTAs).
+//   G1 scatter (warps 0..7), one queue entry per thread across all tiles of the chunk: A2 = world x / z, half-cell,
+//        store cell, L2 prefetch of the candidate word and the world record; B = ONE 64-bit RED.MAX per entry into
+//        the candidate plane.  -> grid barrier 1
+//   G3 resolve (warps 0..7; 0..8 with GT labels), 4 queue entries in flight per thread: candidate word + world record
+//        (+ GT label) loads first, THEN the tile's labels are awaited (mbarrier); winners merge into the world store,
+//        frame-edge winners decide against their partner cells (ivm_core.h).  -> grid barrier 2, launch_dependents
 //   argmax (warps 8..11, PRED): running argmax over the staged planes (4 pixels per thread, LDS.128), labels to
 //        shared memory (for G3) and to labels_out
 //   producer (warp 12, one lane, PRED): keeps a 3 x 16 KB ring full with cp.async.bulk (TMA 1-D copies, SASS
 //        UBLKCP), full/empty mbarriers; no block-wide barrier inside the stream
-//   edge fix-up beside the raster: a small team of CTAs (CTA 0 = stages 1 and 2, the team = edge-line scan)
-//        fixes the bounding-box edge collisions while every other CTA already rasters the ego tiles the fix-up
-//        cannot touch; 128-thread groups (3 per CTA with PRED, 2 with GT), one ego tile each at a time, tiles
-//        handed out dynamically.
+//   edge fix-up beside the raster: a small team of CTAs resolves the collisions on the edge lines of the world
+//        bounding box (direct flow: scan only when a collision can have appeared since the last scan; generic flow
+//        for degenerate boxes) while every other CTA already rasters the ego tiles the fix-up cannot touch;
+//        128-thread groups (3 per CTA with PRED, 2 with GT), one ego tile each at a time, handed out dynamically.
 #define IVM_O_THREADS_GT 288    // GT labels: 8 geometry warps + a ninth that joins the resolve
 #define IVM_O_THREADS_PRED 416  // score stream: 8 geometry warps + 4 argmax warps + 1 producer warp
 #define IVM_O_RGROUPS_PRED 3    // raster groups of 128 threads per CTA
