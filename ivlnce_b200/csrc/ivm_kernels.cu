@@ -1157,7 +1157,8 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
     //       tile's labels are awaited and the winners merge into the world store                 -> grid barrier 2
     constexpr int F4T = IVM_O_TILE / 4;                    // 128-bit depth loads per tile
     constexpr int A1B = 4;                                 // depth loads in flight per thread
-    constexpr int E3 = 4;                                  // queue entries in flight per thread in G3
+    constexpr int E3 = PRED ? 2 : 1;                       // queue entries in flight per thread in G3 (measured: 4 in flight spill in
+                                                           // the merge and lose 2 us (PRED) / 7 us (GT, 32 envs) per step)
     const int cn0 = min(nslot, my_tiles);                  // tiles of the first chunk
     // input half of the slot prep (pose, camera height, pose matrices): 4 slots per warp at a time, 8 lanes each
     auto prep_inputs = [&](int c0, int cn) {
