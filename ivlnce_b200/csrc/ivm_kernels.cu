@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(1024) k_fixup(const __grid_constant__ IvmParam
 // fused step kernel) = one ego tile of one env (output-stationary).  The store half-rows under the
 // rotated tile are cut into 32-record chunks; warps take chunks round-robin, IVM_RASTER_MLP at a
 // time, so that every lane has that many independent 16-byte loads in flight.
-#define IVM_RASTER_MLP 4
+#define IVM_RASTER_MLP 2   // (measured: 2 beats 4 by 0.4 us per step, 1 loses 1-4 us, 8 spills)
 
 // named barrier with a compile-time id (a register id would make ptxas reserve all 16 barriers)
 __device__ __forceinline__ void group_bar(int bar_id, int nthr) {
