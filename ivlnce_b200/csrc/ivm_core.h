@@ -176,6 +176,8 @@ struct IvmGlobal {
     int32_t scan_B;
     uint32_t edge_touched;                    // a cell on an edge line of scan_glob became live since that scan
     uint32_t pad1;
+    unsigned long long stat_in[4];            // fused step kernel: rastered records of step & 3 (the slot of the NEXT step is zeroed
+                                              // at the start of a step, so that no CTA has to fence its count before it leaves)
 };
 
 static_assert(offsetof(IvmGlobal, scan_glob) % 16 == 0, "scan_glob is read with one 128-bit load");

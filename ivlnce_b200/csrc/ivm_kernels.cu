@@ -1323,7 +1323,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             if (blockIdx.x == 0) {
                 g->tstamp[0] = sh.t_start; g->tstamp[5] = 0ull; g->tstamp[6] = global_timer();
                 OVL_STEPLOG(0) = g->tstamp[6]; OVL_STEPLOG(5) = sh.t_start; OVL_STEPLOG(4) = 0ull; OVL_STEPLOG(3) = 0ull;
-                g->stats[IVM_STAT_IN] = 0ull;  // this step's rastered-record count (added to after grid barrier 2)
+                g->stat_in[(P.step + 1u) & 3u] = 0ull;  // the NEXT step's rastered-record count (this step's was zeroed a step ago)
                 P.bar[IVM_O_TILE_CTR] = (unsigned)RG * (gridDim.x - (gridDim.x > 1 ? (unsigned)team : 0u));  // raster tiles handed out statically
             }
         }
@@ -1848,7 +1848,7 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             raster_tile<false>(P, max_rows, b, ty * P.tile_r, tx * P.tile_c, gsm, gtid, IVM_F_GROUP, 2 + group, n_in, false, stage_cap);
         }
         const unsigned wn = warp_sum(n_in);
-        if (wn && lane == 0) atomicAdd(&g->stats[IVM_STAT_IN], (unsigned long long)wn);
+        if (wn && lane == 0) atomicAdd(&g->stat_in[P.step & 3u], (unsigned long long)wn);
     }
     __syncthreads();
     OVL_STAMP(9, 0);
@@ -1856,8 +1856,11 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
         atomicMax(&g->tstamp[5], global_timer());
         atomicMax(&OVL_STEPLOG(4), global_timer());
         // this CTA is done with the map state: a pipelined successor waits for all of these instead of for the
-        // completion of the whole kernel (which is signalled several microseconds after the last CTA has left)
-        __threadfence();
+        // completion of the whole kernel (which is signalled several microseconds after the last CTA has left).
+        // Only the fix-up team has written anything the successor reads (store deletions, env boxes, the step's
+        // published figures): the raster CTAs have only READ the map state -- their loads have returned -- and need no
+        // fence in front of the signal (their maps and counts are not read by the successor).
+        if (cta < team) __threadfence();
         asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(&P.bar[IVM_O_DONE]), "r"(1u) : "memory");
     }
 }
@@ -2118,6 +2121,7 @@ struct ivm_ctx {
     uint32_t kstep;       // known-map mode: steps so far (parity selects the rastered-points counter)
     uint32_t done_base;   // same for the CTAs-done counter: CTAs of all fused launches so far
     int pipelined;        // ivm_set_pipelined: consecutive steps may overlap (see ivln_map.h)
+    int last_fused;       // the last iterative step ran as the persistent kernel (its rastered-record count is in stat_in)
     int64_t launches;
     // known-mode scratch
     uint32_t *kfill, *ktotals;
@@ -2528,11 +2532,17 @@ int ivm_step_iterative(ivm_ctx *ctx, int32_t num_envs, const float *depth, const
     ctx->hi_water = num_envs;
 
     if (ctx->cfg.reserved[0] == 0 && overlap_applies(ctx, P, depth, P.labels, logits, labels_out)) {
+        if (!ctx->last_fused) {  // (the slots are kept zeroed by the fused steps themselves, one step ahead)
+            cudaError_t e = cudaMemsetAsync(P.g->stat_in, 0, sizeof(P.g->stat_in), st);
+            if (e != cudaSuccess) return cuda_fail(ctx, e, "memset(stat_in)");
+            ctx->last_fused = 1;
+        }
         T_BEGIN(1);
         rc = launch_overlap(ctx, P, logits, num_classes, labels_out, nenv, st);
         T_END(1);
         return rc;
     }
+    ctx->last_fused = 0;
     const bool vec4 = (P.W % 4 == 0) && (((uintptr_t)depth & 15) == 0) && (((uintptr_t)P.labels & 3) == 0) &&
                       (!logits || ((uintptr_t)logits & 15) == 0);
     const int vec = vec4 ? 4 : 1;
@@ -2665,6 +2675,7 @@ int ivm_read_status(ivm_ctx *ctx, ivm_status *host_out, ivm_stream_t stream) {
     host_out->pad = 0;
     for (int i = 0; i < 8; ++i) host_out->stats[i] = g.stats[i];
     if (ctx->cfg.mode == 1) host_out->stats[IVM_STAT_IN] = g.known_in[ctx->kstep & 1u];
+    else if (ctx->last_fused) host_out->stats[IVM_STAT_IN] = g.stat_in[ctx->step & 3u];
     return IVM_OK;
 }
 
@@ -2759,6 +2770,7 @@ int ivm_copy_state(ivm_ctx *dst, const ivm_ctx *src, ivm_stream_t stream) {
         if (_e != cudaSuccess) return cuda_fail(ctx, _e, "copy_state");                          \
     } while (0)
     IVM_COPY(dst->P.g, src->P.g, sizeof(IvmGlobal));
+    dst->last_fused = 0;
     IVM_COPY(dst->P.env, src->P.env, sizeof(IvmEnv) * B);
     IVM_COPY(dst->P.xs, src->P.xs, sizeof(float) * (b.width > 0 ? b.width : 1));
     IVM_COPY(dst->P.ys, src->P.ys, sizeof(float) * (b.height > 0 ? b.height : 1));
@@ -2795,6 +2807,7 @@ int ivm_rebase_stamps(ivm_ctx *ctx, ivm_stream_t stream) {
     k_rebase_env<<<(ctx->P.maxB + 255) / 256, 256, 0, st>>>(ctx->P);
     ctx->launches += 2;
     ctx->step = 1;
+    ctx->last_fused = 0;  // (the step numbering restarts: the per-step count slots are cleared before the next fused step)
     IVM_CHECK_LAUNCH("rebase");
     return IVM_OK;
 }
