@@ -496,6 +496,8 @@ __global__ void __launch_bounds__(1024) k_fixup(const __grid_constant__ IvmParam
     S.key = s_key; S.xo = s_xo; S.ord = s_ord; S.cap = IVM_FIX_SMALL; S.ibuf = s_i; S.lbuf = s_l;
     S.release = nullptr; S.release_add = 0u;
     ivm_fixup_program<IvmAtomics>(P, S, threadIdx.x, blockDim.x);
+    // (the persistent kernel's record of its last edge-line scan says nothing about a store this path has merged into)
+    if (threadIdx.x == 0) P.g->scan_valid = 0u;
 }
 
 // ------------------------------------------------------------------ K4: raster

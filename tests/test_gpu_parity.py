@@ -613,3 +613,45 @@ def test_long_tour_against_oracle():
     assert np.array_equal(b1, b2) and np.array_equal(x1.view(np.uint32), x2.view(np.uint32)) and np.array_equal(s1, s2)
     assert checked >= 40 and len(b1) > 50_000
     cs.mm.check_errors()
+
+
+@pytest.mark.parametrize("name", ["scene_overlap", "identical_envs", "iid_f64"])
+def test_fused_and_four_kernel_steps_alternate_in_one_context(name):
+    """A depth tensor that is not 16-byte aligned sends a step down the four-kernel path; the next aligned one goes back
+    to the persistent kernel.  Both work on the same world state (store, env boxes, edge-scan record, per-step
+    counters), so a run that alternates between them must still match the reference step for step."""
+    from cuda_stepper import CudaStepper
+    from ivlnce_b200.mapper import EpisodesInfo, Observations, RobotCurrentState
+
+    scn = load_golden(name)
+    cs = CudaStepper(scn["cfg"], max_envs=int(scn["num_envs"].max()))
+    dev, mm = cs.dev, cs.mm
+    T = scn["masks"].shape[0]
+    launches = []
+    for t in range(T):
+        B = int(scn["num_envs"][t])
+        d = np.ascontiguousarray(scn["depth"][t, :B])
+        if t % 2 == 1:                       # element offset 1: the same values at a 4-byte-aligned address
+            buf = torch.empty(d.size + 1, dtype=torch.float32, device=dev)
+            buf[1:] = torch.from_numpy(d.reshape(-1)).to(dev)
+            dt = buf[1:].view(B, 1, *d.shape[1:])
+            assert dt.data_ptr() % 16 != 0
+        else:
+            dt = torch.from_numpy(d).to(dev).unsqueeze(1)
+        lab = torch.from_numpy(np.ascontiguousarray(scn["labels"][t, :B])).to(dev).unsqueeze(1)
+        ori = torch.from_numpy(np.ascontiguousarray(scn["orientation"][t, :B])).to(dev)
+        ei = EpisodesInfo(torch.from_numpy(np.ascontiguousarray(scn["masks"][t, :B])).reshape(B, 1).to(dev), [f"scene{b}" for b in range(B)])
+        n0 = mm.kernel_launches()
+        out = mm(ei, Observations(lab, dt, None), RobotCurrentState(torch.from_numpy(np.ascontiguousarray(scn["pose"][t, :B])).to(dev), ori[:, 0], ori[:, 1]))
+        launches.append(mm.kernel_launches() - n0)
+        assert np.array_equal(out.occupancy.cpu().numpy(), scn["ref_occupancy"][t, :B]), t
+        assert np.array_equal(out.semantic.cpu().numpy(), scn["ref_semantic"][t, :B]), t
+        assert len(cs.world()[0]) == int(scn["ref_world_sizes"][t]), t
+    H, W = scn["depth"].shape[2], scn["depth"].shape[3]
+    assert min(launches[1::2]) >= 4, launches                                # the misaligned steps took the four-kernel path
+    if (H * W) % 512 == 0 and W % 4 == 0:
+        assert min(launches[2::2]) == 1, launches                            # ... and the others the persistent kernel
+    b, xyz, sem = cs.world()
+    assert np.array_equal(b, scn["ref_world_b"]) and np.array_equal(xyz.view(np.uint32), scn["ref_world_xyz"].view(np.uint32))
+    assert np.array_equal(sem, scn["ref_world_sem"])
+    mm.check_errors()
