@@ -4,6 +4,12 @@ import os, sys, time
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
+if os.environ.get("TILE"):   # raster tile override (cells per side)
+    import ivlnce_b200.mapper as _M
+    _orig = _M.MappingModule.__init__
+    def _init(self, *a, **k):
+        k["raster_tile"] = int(os.environ["TILE"]); _orig(self, *a, **k)
+    _M.MappingModule.__init__ = _init
 wl = sys.argv[1] if len(sys.argv) > 1 else "pred16"
 cfg = dict(bench.WORKLOADS[wl]); dev = torch.device("cuda:0")
 if os.environ.get("ENVS"): cfg["envs"] = int(os.environ["ENVS"])
