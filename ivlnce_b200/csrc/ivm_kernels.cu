@@ -1220,13 +1220,15 @@ k_step_overlap(const __grid_constant__ IvmParams P, const float *__restrict__ lo
             int v, u0;
             ovl_row_col(P, pix0, v, u0);
             const float ysv = P.ys[v];
+            const float4 xq = __ldg(reinterpret_cast<const float4 *>(P.xs + u0));  // (u0 is a multiple of 4, the table 16-byte aligned)
+            const float xsv[4] = {xq.x, xq.y, xq.z, xq.w};
             const float dd[4] = {dv[q].x, dv[q].y, dv[q].z, dv[q].w};
             bool ok[4];
             unsigned mk[4];
             int n = 0;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const float y = ivm_world_y(dd[j], P.xs[u0 + j], ysv, sl.T);
+                const float y = ivm_world_y(dd[j], xsv[j], ysv, sl.T);
                 ok[j] = dd[j] > 0.01f && dd[j] < 0.99f && y > sl.hlo && y < sl.hhi;
                 mk[j] = __ballot_sync(0xffffffffu, ok[j]);
                 n += __popc(mk[j]);
@@ -2414,7 +2416,7 @@ static bool fused_applies(const ivm_ctx *ctx, const IvmParams &P, const float *d
 static bool overlap_applies(const ivm_ctx *ctx, const IvmParams &P, const float *depth, const uint8_t *labels, const float *logits,
                             const uint8_t *labels_out) {
     if (!fused_applies(ctx, P, depth, labels, logits)) return false;
-    if ((P.W & 3) || ((uintptr_t)depth & 15) || P.SR > 65535 || P.SC > 65535) return false;
+    if ((P.W & 3) || ((uintptr_t)depth & 15) || ((uintptr_t)P.xs & 15) || P.SR > 65535 || P.SC > 65535) return false;
     if ((long long)P.B * (P.HW / IVM_O_TILE) > (1ll << 30)) return false;
     if (logits && ((uintptr_t)labels_out & 3)) return false;
     return true;
