@@ -469,12 +469,13 @@ def _as_f32(t: torch.Tensor, device) -> torch.Tensor:
 
 
 class _Hold:
-    __slots__ = ("keepalive", "num_envs", "views_B", "occ_base", "occ_view", "sem_view", "err_host", "err_event", "err_calls")
+    __slots__ = ("keepalive", "num_envs", "views_B", "occ_base", "occ_view", "sem_view", "err_host", "err_event", "err_calls",
+                 "err_stream")
 
     def __init__(self):
         self.keepalive, self.num_envs, self.views_B = None, 0, -1
         self.occ_base = self.occ_view = self.sem_view = None
-        self.err_host, self.err_event, self.err_calls = None, None, 0   # error polling (MappingModule._poll_errors)
+        self.err_host, self.err_event, self.err_calls, self.err_stream = None, None, 0, None   # error polling (_poll_errors)
 
 
 class MappingModule(nn.Module):
@@ -617,10 +618,15 @@ class MappingModule(nn.Module):
             hold.err_calls = 0
             if hold.err_host is None:
                 hold.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-            _lib.check(eng.lib.ivm_copy_error_flags_async(eng.ctx, hold.err_host.data_ptr(), eng.stream()), eng.ctx,
+                # The flags are sticky, so WHEN they are read does not matter: the copy runs on a side stream and nothing
+                # is put between two steps on the caller's stream (an event or a copy there would end the overlap of
+                # back-to-back steps).  The side stream is ordered once behind the work that created the context.
+                hold.err_stream = torch.cuda.Stream(self.device)
+                hold.err_stream.wait_stream(torch.cuda.current_stream(self.device))
+            _lib.check(eng.lib.ivm_copy_error_flags_async(eng.ctx, hold.err_host.data_ptr(), hold.err_stream.cuda_stream), eng.ctx,
                        "ivm_copy_error_flags_async")
             hold.err_event = torch.cuda.Event()
-            hold.err_event.record(torch.cuda.current_stream(self.device))
+            hold.err_event.record(hold.err_stream)
 
     def _raise_flags(self, eng, flags: int):
         overflow = flags & (_lib.ERR_STORE_OVERFLOW | _lib.ERR_KNOWN_OVERFLOW)
